@@ -1,0 +1,271 @@
+"""Input pipeline with the reference's tf.data semantics (main.py:18-83).
+
+    take(n) → map(flip → bilinear resize 286² → random crop 256² → /127.5 − 1)
+            → cache() → shuffle(256)            per train domain
+    take(n) → map(resize 256² → normalise) → cache()        per test domain
+    zip(A.batch(gbs), B.batch(gbs)) [.prefetch]             no drop_remainder
+    distribute: every global batch is split across the replicas
+
+Kept quirks: ``cache()`` sits *after* the random map, so flip/crop are drawn
+once and frozen for the run; each domain is shuffled independently with a
+256-element buffer (unpaired); the last batch is partial and the replicas get
+uneven shares of it.
+
+Sources: TFDS is unavailable offline, so images come either from a CycleGAN
+style folder (``trainA/ trainB/ testA/ testB/``) or from a deterministic
+synthetic horse2zebra stand-in with the same split sizes (1067/1334/120/140).
+The prefetcher stages batches in pinned host memory and copies them to the
+device on a side stream (the B200 counterpart of MultiDeviceIterator).
+"""
+from __future__ import annotations
+
+import os
+import threading
+import queue
+from math import ceil
+from typing import Callable, Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from ..parallel.strategy import Strategy
+
+H2Z_SPLITS = {"trainA": 1067, "trainB": 1334, "testA": 120, "testB": 140}
+
+
+# ------------------------------------------------------------------ sources
+class SyntheticSource:
+  """Procedural stand-in for cycle_gan/horse2zebra: domain A = smooth blobs,
+  domain B = blobs modulated by stripes. Deterministic per (split, index)."""
+
+  def __init__(self, raw_size: int = 256, sizes: Optional[dict] = None, seed: int = 1234):
+    self.raw_size = raw_size
+    self.sizes = dict(H2Z_SPLITS if sizes is None else sizes)
+    self.seed = seed
+
+  def num_examples(self, split: str) -> int:
+    return self.sizes[split]
+
+  def get(self, split: str, index: int) -> np.ndarray:
+    s = self.raw_size
+    rng = np.random.default_rng([self.seed, sum(map(ord, split)), index])
+    low = rng.random((4, 4, 3), dtype=np.float32)
+    img = F.interpolate(torch.from_numpy(low).permute(2, 0, 1)[None], size=(s, s),
+                        mode="bicubic", align_corners=False)[0].permute(1, 2, 0).numpy()
+    if split.endswith("B"):
+      yy, xx = np.mgrid[0:s, 0:s].astype(np.float32) / s
+      ang, freq = rng.random() * np.pi, 6 + 10 * rng.random()
+      stripes = 0.5 + 0.5 * np.sign(np.sin(2 * np.pi * freq * (np.cos(ang) * xx + np.sin(ang) * yy)))
+      img = img * (0.35 + 0.65 * stripes[..., None])
+    return (np.clip(img, 0, 1) * 255).astype(np.uint8)
+
+
+class FolderSource:
+  """``<data_dir>/{trainA,trainB,testA,testB}/*.{jpg,png}`` (the layout of the
+  original CycleGAN dataset archives)."""
+  EXT = (".jpg", ".jpeg", ".png", ".bmp")
+
+  def __init__(self, data_dir: str):
+    self.files = {}
+    for split in H2Z_SPLITS:
+      d = os.path.join(data_dir, split)
+      if not os.path.isdir(d):
+        raise FileNotFoundError(f"missing split directory {d}")
+      self.files[split] = sorted(os.path.join(d, f) for f in os.listdir(d)
+                                 if f.lower().endswith(self.EXT))
+
+  def num_examples(self, split: str) -> int:
+    return len(self.files[split])
+
+  def get(self, split: str, index: int) -> np.ndarray:
+    from PIL import Image
+    return np.asarray(Image.open(self.files[split][index]).convert("RGB"))
+
+
+# ------------------------------------------------------------ preprocessing
+def normalize_image(image: torch.Tensor) -> torch.Tensor:
+  """normalize image to [-1, 1] (main.py:35-38)."""
+  return image.to(torch.float32) / 127.5 - 1.0
+
+
+def resize_bilinear(image: torch.Tensor, size: Tuple[int, int]) -> torch.Tensor:
+  """tf.image.resize(method=bilinear): half-pixel centres, no antialias. HWC float."""
+  x = image.to(torch.float32).permute(2, 0, 1)[None]
+  y = F.interpolate(x, size=size, mode="bilinear", align_corners=False, antialias=False)
+  return y[0].permute(1, 2, 0)
+
+
+def preprocess_train(image: np.ndarray, rng: np.random.Generator,
+                     resize_shape: Tuple[int, int], crop: int) -> torch.Tensor:
+  """main.py:40-45: random flip → resize → random crop → normalise."""
+  img = torch.from_numpy(np.ascontiguousarray(image))
+  if rng.random() < 0.5:
+    img = torch.flip(img, dims=[1])
+  img = resize_bilinear(img, resize_shape)
+  top = int(rng.integers(0, resize_shape[0] - crop + 1))
+  left = int(rng.integers(0, resize_shape[1] - crop + 1))
+  img = img[top:top + crop, left:left + crop, :]
+  return normalize_image(img)
+
+
+def preprocess_test(image: np.ndarray, size: int) -> torch.Tensor:
+  """main.py:47-50: resize → normalise."""
+  return normalize_image(resize_bilinear(torch.from_numpy(np.ascontiguousarray(image)), (size, size)))
+
+
+def tf_shuffle_order(n: int, buffer_size: int, rng: np.random.Generator) -> List[int]:
+  """Element order produced by ``Dataset.shuffle(buffer_size)`` over range(n)."""
+  buf = list(range(min(buffer_size, n)))
+  nxt = len(buf)
+  out = []
+  while buf:
+    j = int(rng.integers(0, len(buf)))
+    out.append(buf[j])
+    if nxt < n:
+      buf[j] = nxt
+      nxt += 1
+    else:
+      buf[j] = buf[-1]
+      buf.pop()
+  return out
+
+
+# ----------------------------------------------------------------- datasets
+class PairedBatches:
+  """zip(A.batch(gbs), B.batch(gbs)) restricted to this replica's share."""
+
+  def __init__(self, a: torch.Tensor, b: torch.Tensor, global_batch_size: int,
+               strategy: Strategy, shuffle_buffer: int = 0, seed: int = 0,
+               distribute: bool = True, prefetch: int = 0, to_device: bool = True):
+    assert a.shape[0] == b.shape[0]
+    self.a, self.b = a, b
+    self.gbs = global_batch_size
+    self.strategy = strategy
+    self.shuffle_buffer = shuffle_buffer
+    self.rng = np.random.default_rng(seed)
+    self.distribute = distribute
+    self.prefetch = prefetch
+    self.to_device = to_device
+    self.steps = ceil(a.shape[0] / global_batch_size)
+
+  def __len__(self) -> int:
+    return self.steps
+
+  def _orders(self):
+    n = self.a.shape[0]
+    if self.shuffle_buffer:
+      return (tf_shuffle_order(n, self.shuffle_buffer, self.rng),
+              tf_shuffle_order(n, self.shuffle_buffer, self.rng))
+    return list(range(n)), list(range(n))
+
+  def _host_batches(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
+    oa, ob = self._orders()
+    n = self.a.shape[0]
+    for s in range(0, n, self.gbs):
+      ia, ib = oa[s:s + self.gbs], ob[s:s + self.gbs]
+      if self.distribute:
+        lo, hi = self.strategy.shard_bounds(len(ia))
+        ia, ib = ia[lo:hi], ib[lo:hi]
+      idx_a = torch.as_tensor(ia, dtype=torch.long)
+      idx_b = torch.as_tensor(ib, dtype=torch.long)
+      yield self.a.index_select(0, idx_a), self.b.index_select(0, idx_b)
+
+  def _upload(self, x: torch.Tensor, y: torch.Tensor):
+    dev = self.strategy.device
+    if not self.to_device or dev.type != "cuda":
+      return x, y
+    return (x.pin_memory().to(dev, non_blocking=True),
+            y.pin_memory().to(dev, non_blocking=True))
+
+  def __iter__(self):
+    if self.prefetch <= 0:
+      for x, y in self._host_batches():
+        yield self._upload(x, y)
+      return
+    q: "queue.Queue" = queue.Queue(maxsize=self.prefetch)
+    dev = self.strategy.device
+    stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" and self.to_device else None
+
+    def worker():
+      try:
+        for x, y in self._host_batches():
+          if stream is not None:
+            with torch.cuda.stream(stream):
+              xd, yd = self._upload(x, y)
+              ev = torch.cuda.Event()
+              ev.record(stream)
+            q.put((xd, yd, ev))
+          else:
+            q.put((x, y, None))
+      except BaseException as e:  # surface worker errors in the consumer
+        q.put(e)
+      q.put(None)
+
+    t = threading.Thread(target=worker, daemon=True)
+    t.start()
+    while True:
+      item = q.get()
+      if item is None:
+        break
+      if isinstance(item, BaseException):
+        raise item
+      x, y, ev = item
+      if ev is not None:
+        torch.cuda.current_stream(dev).wait_event(ev)
+        x.record_stream(torch.cuda.current_stream(dev))
+        y.record_stream(torch.cuda.current_stream(dev))
+      yield x, y
+    t.join()
+
+
+def _materialise(source, split: str, n: int, fn: Callable[[np.ndarray, int], torch.Tensor]) -> torch.Tensor:
+  first = fn(source.get(split, 0), 0)
+  out = torch.empty((n,) + tuple(first.shape), dtype=torch.float32)
+  out[0] = first
+  for i in range(1, n):
+    out[i] = fn(source.get(split, i), i)
+  return out
+
+
+def get_datasets(args, strategy: Strategy, buffer_size: int = 256, source=None):
+  """Load and return preprocessed and distributed datasets (main.py:18-83).
+
+  Side effect (kept): sets ``args.train_steps`` / ``args.test_steps``."""
+  size = int(getattr(args, "image_size", 256))
+  resize = int(round(size * 286 / 256))
+  seed = int(getattr(args, "seed", 1234))
+  if source is None:
+    data_dir = getattr(args, "data_dir", None)
+    if data_dir:
+      source = FolderSource(data_dir)
+    else:
+      sizes = None
+      lim = getattr(args, "synthetic_size", None)
+      if lim:
+        sizes = {"trainA": lim, "trainB": lim + lim // 4,
+                 "testA": max(1, lim // 8), "testB": max(1, lim // 8) + 1}
+      source = SyntheticSource(raw_size=size, sizes=sizes, seed=seed)
+
+  num_train = min(source.num_examples("trainA"), source.num_examples("trainB"))
+  num_test = min(source.num_examples("testA"), source.num_examples("testB"))
+  args.train_steps = ceil(num_train / args.global_batch_size)
+  args.test_steps = ceil(num_test / args.global_batch_size)
+
+  # cache() after the random map: augmentation is drawn ONCE (main.py:53-54).
+  rng_a = np.random.default_rng([seed, 1])
+  rng_b = np.random.default_rng([seed, 2])
+  train_a = _materialise(source, "trainA", num_train,
+                         lambda im, i: preprocess_train(im, rng_a, (resize, resize), size))
+  train_b = _materialise(source, "trainB", num_train,
+                         lambda im, i: preprocess_train(im, rng_b, (resize, resize), size))
+  test_a = _materialise(source, "testA", num_test, lambda im, i: preprocess_test(im, size))
+  test_b = _materialise(source, "testB", num_test, lambda im, i: preprocess_test(im, size))
+
+  train_ds = PairedBatches(train_a, train_b, args.global_batch_size, strategy,
+                           shuffle_buffer=buffer_size, seed=seed, prefetch=2)
+  test_ds = PairedBatches(test_a, test_b, args.global_batch_size, strategy)
+  # take 5 samples from the test set for plotting; NOT distributed (main.py:76-77)
+  k = min(5, num_test)
+  plot_ds = PairedBatches(test_a[:k], test_b[:k], 1, strategy, distribute=False)
+  return train_ds, test_ds, plot_ds
