@@ -1,0 +1,312 @@
+"""sm_100a kernels vs the PyTorch fp32 oracle (SURVEY §4 'kernel (GPU)').
+
+Inputs / weights are rounded to bf16 first so the only differences are fp32
+accumulation order and the bf16 rounding of stored outputs.
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+  from tf2_cyclegan_b200.engine import native_ops as no
+  from tf2_cyclegan_b200.ops import native as nv
+  from tf2_cyclegan_b200.ops import oracle as O
+  return nv, no, O
+
+
+def bf(t):
+  return t.to(torch.bfloat16).float()
+
+
+def rel_err(a, b):
+  return ((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-6)).item()
+
+
+def run(plan):
+  plan.run(0, -1, torch.cuda.current_stream().cuda_stream, True)
+  torch.cuda.synchronize()
+
+
+def fill_reflect(buf, x):
+  """reference fill of a haloed buffer (python side)."""
+  nv, no, O = _mods()
+  buf.t.copy_(O.reflect_pad(x, buf.halo).to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("n,h,c,cout", [(2, 64, 256, 256), (1, 16, 64, 128), (3, 32, 128, 512)])
+def test_conv3x3_reflect_box(n, h, c, cout):
+  nv, no, O = _mods()
+  C = nv.load()
+  torch.manual_seed(0)
+  x = bf(torch.randn(n, h, h, c, device="cuda"))
+  k = bf(torch.randn(3, 3, c, cout, device="cuda") * 0.05)
+  xin = nv.Buf(n, h, h, c, halo=1)
+  fill_reflect(xin, x)
+  w2 = no.pack_conv_weight(k).to(torch.bfloat16)
+  out = nv.Buf(n, h, h, cout)
+  stats = torch.zeros(n, cout, 2, device="cuda")
+  plan = C.Plan()
+  bw, bh = nv.tile_shape(h, h)
+  no.add_conv(plan, "conv", [xin.tmap_padded(bw, bh)], no.taps_conv(3, c), c, w2, out.view(), h, h,
+              n, cout, stats=stats.data_ptr())
+  run(plan)
+  ref = O.conv2d(O.reflect_pad(x, 1), k, 1, "valid")
+  assert rel_err(out.t, ref) < 1e-2
+  got = out.t.float()
+  assert torch.allclose(stats[..., 0], got.sum((1, 2)), rtol=1e-3, atol=1e-2 * h)
+  assert torch.allclose(stats[..., 1], (got * got).sum((1, 2)), rtol=1e-3, atol=1e-2 * h)
+
+
+@pytest.mark.parametrize("k,pad_before,cin,cout,h", [(3, 0, 64, 128, 32), (4, 1, 64, 128, 32),
+                                                     (4, 1, 128, 256, 64)])
+def test_conv_stride2_parity(k, pad_before, cin, cout, h):
+  nv, no, O = _mods()
+  C = nv.load()
+  torch.manual_seed(1)
+  n = 2
+  x = bf(torch.randn(n, h, h, cin, device="cuda"))
+  kern = bf(torch.randn(k, k, cin, cout, device="cuda") * 0.05)
+  xin = nv.Buf(n, h, h, cin)
+  xin.t.copy_(x.to(torch.bfloat16))
+  oh = h // 2
+  bw, bh = nv.tile_shape(oh, oh)
+  maps = [xin.tmap_parity(a, b, bw, bh) for a in (0, 1) for b in (0, 1)]
+  w2 = no.pack_conv_weight(kern).to(torch.bfloat16)
+  out = nv.Buf(n, oh, oh, cout)
+  plan = C.Plan()
+  no.add_conv(plan, "s2", maps, no.taps_conv_s2(k, cin, pad_before), cin, w2, out.view(), oh, oh, n, cout)
+  run(plan)
+  ref = O.conv2d(x, kern, 2, "same")
+  assert O.same_pad_amounts(h, k, 2)[0] == pad_before
+  assert rel_err(out.t, ref) < 1e-2
+
+
+@pytest.mark.parametrize("cout,bias,act", [(512, False, None), (1, True, None), (3, True, "tanh")])
+def test_conv4x4_s1_same_and_small_n(cout, bias, act):
+  nv, no, O = _mods()
+  C = nv.load()
+  torch.manual_seed(2)
+  n, h, cin = 2, 32, 256
+  x = bf(torch.randn(n, h, h, cin, device="cuda"))
+  kern = bf(torch.randn(4, 4, cin, cout, device="cuda") * 0.03)
+  b = torch.randn(cout, device="cuda") if bias else None
+  xin = nv.Buf(n, h, h, cin)
+  xin.t.copy_(x.to(torch.bfloat16))
+  bw, bh = nv.tile_shape(h, h)
+  w2 = no.pack_conv_weight(kern).to(torch.bfloat16)
+  cpad = 8 if cout < 8 else cout
+  out = nv.Buf(n, h, h, cpad)
+  plan = C.Plan()
+  no.add_conv(plan, "c4", [xin.tmap_interior(bw, bh)], no.taps_conv(4, cin, origin=-1), cin, w2,
+              out.view(), h, h, n, cout, bias=no.fptr(b), act=nv.ACT[act])
+  run(plan)
+  ref = O.conv2d(x, kern, 1, "same", b)
+  if act == "tanh":
+    ref = torch.tanh(ref)
+  assert rel_err(out.t[..., :cout], ref) < 1e-2
+  if cpad > cout:
+    assert out.t[..., cout:].abs().max() == 0
+
+
+def test_conv_transpose_phases():
+  nv, no, O = _mods()
+  C = nv.load()
+  torch.manual_seed(3)
+  n, h, cin, cout = 2, 32, 128, 64
+  x = bf(torch.randn(n, h, h, cin, device="cuda"))
+  kern = bf(torch.randn(3, 3, cout, cin, device="cuda") * 0.05)   # [kh, kw, out, in]
+  xin = nv.Buf(n, h, h, cin)
+  xin.t.copy_(x.to(torch.bfloat16))
+  w2 = no.pack_conv_weight(kern, transpose_conv=True).to(torch.bfloat16)
+  out = nv.Buf(n, 2 * h, 2 * h, cout)
+  stats = torch.zeros(n, cout, 2, device="cuda")
+  bw, bh = nv.tile_shape(h, h)
+  plan = C.Plan()
+  for a in (0, 1):
+    for b in (0, 1):
+      view = (out.ptr(0, a, b), out.sn, 2 * out.sh, 2 * out.sw)
+      no.add_conv(plan, f"up{a}{b}", [xin.tmap_interior(bw, bh)], no.taps_convT_phase(a, b, cin), cin,
+                  w2, view, h, h, n, cout, stats=stats.data_ptr())
+  run(plan)
+  ref = O.conv2d_transpose(x, kern, 2)
+  assert rel_err(out.t, ref) < 1e-2
+  assert torch.allclose(stats[..., 0], out.t.float().sum((1, 2)), rtol=1e-3, atol=0.5)
+
+
+def test_dgrad_flat_mn_major_and_fold():
+  """dgrad of the reflect-padded 3x3 conv in the zero-ringed flat domain, using the
+  forward weight matrix as an MN-major B operand."""
+  nv, no, O = _mods()
+  C = nv.load()
+  torch.manual_seed(4)
+  n, h, c, cout = 2, 32, 128, 256
+  x = bf(torch.randn(n, h, h, c, device="cuda")).requires_grad_(True)
+  kern = bf(torch.randn(3, 3, c, cout, device="cuda") * 0.05)
+  dy = bf(torch.randn(n, h, h, cout, device="cuda"))
+  y = O.conv2d(O.reflect_pad(x, 1), kern, 1, "valid")
+  (gx,) = torch.autograd.grad(y, x, dy)
+
+  dyb = nv.Buf(n, h, h, cout, halo=1)           # zero ring
+  dyb.interior().copy_(dy.to(torch.bfloat16))
+  w2 = no.pack_conv_weight(kern).to(torch.bfloat16)
+  P = h + 2
+  rows = n * P * P
+  dxpad = nv.Buf(n, h, h, c, halo=1)
+  # dXpad[q] = sum_{r,s} dYz[q + (1 - r) * P + (1 - s)] W[r, s]
+  taps = [(0, 0, (1 - r) * P + (1 - s), 0, (r * 3 + s) * c) for r in range(3) for s in range(3)]
+  plan = C.Plan()
+  no.add_conv_flat(plan, "dgrad", dyb.tmap_flat(), taps, cout, w2, dxpad.ptr(padded=True), c, rows, c,
+                   b_mn=True)
+  # fold the halo back with the IN-backward reduce kernel (no norm: dy = folded g)
+  g = nv.Buf(n, h, h, c)
+  plan.add_in_bwd_reduce("fold", dxpad.view(), 1, nv.NULL_VIEW, nv.NULL_VIEW, 0, 0, 0, 1.0, 1e-3, 0,
+                         g.view(), 0, n, h, h, c)
+  run(plan)
+  assert rel_err(g.t, gx) < 1.5e-2
+
+
+@pytest.mark.parametrize("n,h,cin,cout", [(2, 32, 256, 256), (2, 32, 128, 64)])
+def test_wgrad_conv3x3(n, h, cin, cout):
+  nv, no, O = _mods()
+  C = nv.load()
+  torch.manual_seed(5)
+  x = bf(torch.randn(n, h, h, cin, device="cuda"))
+  kern = bf(torch.randn(3, 3, cin, cout, device="cuda") * 0.05).requires_grad_(True)
+  dy = bf(torch.randn(n, h, h, cout, device="cuda"))
+  y = O.conv2d(O.reflect_pad(x, 1), kern, 1, "valid")
+  (gk,) = torch.autograd.grad(y, kern, dy)
+
+  xin = nv.Buf(n, h, h, cin, halo=1)
+  fill_reflect(xin, x)
+  dyb = nv.Buf(n, h, h, cout, halo=1)
+  dyb.interior().copy_(dy.to(torch.bfloat16))
+  dw = torch.zeros(max(cout, 16), 9 * cin, device="cuda")
+  kbw, kbh = nv.tile_shape(h, h, 64)
+  plan = C.Plan()
+  no.add_wgrad(plan, "wgrad", dyb.tmap_interior(kbw, kbh), [xin.tmap_padded(kbw, kbh)],
+               no.taps_conv(3, cin), h // kbw, h // kbh, kbw, kbh, n, cin, cout, dw.data_ptr(), 9 * cin)
+  run(plan)
+  got = no.unpack_conv_weight(dw, 3, cin, cout)
+  assert rel_err(got, gk) < 1e-2
+
+
+def test_overlapped_stride_stem():
+  """7x7 stem conv (Cin = 3) as a GEMM: 8-channel pixels, one tap per kernel row, the 64-wide
+  K block is an overlapping window of 8 consecutive pixels (TMA map with a 16-byte w stride)."""
+  nv, no, O = _mods()
+  C = nv.load()
+  torch.manual_seed(6)
+  n, h = 2, 64
+  x = bf(torch.randn(n, h, h, 3, device="cuda"))
+  kern = bf(torch.randn(7, 7, 3, 64, device="cuda") * 0.1)
+  xin = nv.Buf(n, h, h, 8, halo=3, slack_rows=1)
+  xp = O.reflect_pad(x, 3)
+  xin.t[..., :3].copy_(xp.to(torch.bfloat16))
+  # packed weights W2[co][r*64 + s*8 + c]
+  w2 = torch.zeros(64, 7, 8, 8, device="cuda")
+  w2[:, :, :7, :3] = kern.permute(3, 0, 1, 2)
+  w2 = w2.reshape(64, 448).to(torch.bfloat16)
+  bw, bh = nv.tile_shape(h, h)
+  amap = nv.tmap(xin.ptr(padded=True), [64, h, xin.hp, n], [8, xin.sh, xin.sn], [64, bw, bh, 1])
+  out = nv.Buf(n, h, h, 64)
+  taps = [(0, 0, 0, r, r * 64) for r in range(7)]
+  plan = C.Plan()
+  no.add_conv(plan, "stem", [amap], taps, 64, w2, out.view(), h, h, n, 64)
+  run(plan)
+  ref = O.conv2d(xp, kern, 1, "valid")
+  assert rel_err(out.t, ref) < 1e-2
+
+
+def test_in_apply_and_backward_match_autograd():
+  nv, no, O = _mods()
+  C = nv.load()
+  torch.manual_seed(7)
+  n, h, c = 2, 16, 64
+  x = bf(torch.randn(n, h, h, c, device="cuda") * 2 + 0.5).requires_grad_(True)
+  gamma = (torch.randn(c, device="cuda") * 0.5).requires_grad_(True)
+  beta = (torch.randn(c, device="cuda") * 0.1).requires_grad_(True)
+  skip = bf(torch.randn(n, h, h, c, device="cuda"))
+  y = torch.relu(O.instance_norm(x, gamma, beta)) + skip
+  ypad = O.reflect_pad(y, 1)
+  gpad = bf(torch.randn_like(ypad))
+  gx, gg, gb = torch.autograd.grad(ypad, [x, gamma, beta], gpad)
+
+  xb = nv.Buf(n, h, h, c); xb.t.copy_(x.detach().to(torch.bfloat16))
+  sb = nv.Buf(n, h, h, c); sb.t.copy_(skip.to(torch.bfloat16))
+  stats = torch.stack([x.detach().sum((1, 2)), (x.detach() ** 2).sum((1, 2))], -1).contiguous()
+  dst = nv.Buf(n, h, h, c, halo=1)
+  gp = nv.Buf(n, h, h, c, halo=1); gp.t.copy_(gpad.to(torch.bfloat16))
+  dyb = nv.Buf(n, h, h, c)
+  dxb = nv.Buf(n, h, h, c, halo=1)
+  bst = torch.zeros(n, c, 2, device="cuda")
+  dgam = torch.zeros(c, device="cuda"); dbet = torch.zeros(c, device="cuda")
+  inv = 1.0 / (h * h)
+  plan = C.Plan()
+  plan.add_in_apply("apply", xb.view(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), inv, 1e-3,
+                    nv.ACT["relu"], sb.view(), dst.view(), 1, n, h, h, c)
+  plan.add_in_bwd_reduce("red", gp.view(), 1, nv.NULL_VIEW, xb.view(), stats.data_ptr(),
+                         gamma.data_ptr(), beta.data_ptr(), inv, 1e-3, nv.ACT["relu"], dyb.view(),
+                         bst.data_ptr(), n, h, h, c)
+  plan.add_in_bwd_apply("app", dyb.view(), xb.view(), stats.data_ptr(), bst.data_ptr(), gamma.data_ptr(),
+                        inv, 1e-3, dxb.view(), dgam.data_ptr(), dbet.data_ptr(), n, h, h, c)
+  run(plan)
+  assert rel_err(dst.t, ypad) < 1e-2
+  assert rel_err(dxb.interior(), gx) < 2e-2
+  assert dxb.t[:, 0].abs().max() == 0          # zero ring untouched
+  assert rel_err(dgam, gg) < 2e-2 and rel_err(dbet, gb) < 2e-2
+
+
+def test_losses_adam_imgprep():
+  nv, no, O = _mods()
+  C = nv.load()
+  torch.manual_seed(8)
+  n, h = 2, 32
+  img = torch.rand(n, h, h, 3, device="cuda") * 2 - 1
+  pred = nv.Buf(n, h, h, 8)
+  pred.t[..., :3].copy_((torch.rand(n, h, h, 3, device="cuda") * 2 - 1).to(torch.bfloat16))
+  g = nv.Buf(n, h, h, 8)
+  slots = torch.zeros(4, device="cuda")
+  refl = nv.Buf(n, h, h, 8, halo=3)
+  plain = nv.Buf(n, h, h, 8, halo=1)
+  d = nv.Buf(n, 8, 8, 8)
+  d.t[..., 0].copy_(torch.randn(n, 8, 8, device="cuda").to(torch.bfloat16))
+  gd = nv.Buf(n, 8, 8, 8)
+  plan = C.Plan()
+  gbs = 4
+  scale = 10.0 / (h * h * 3 * gbs)
+  plan.add_l1_loss("l1", pred.view(), img.data_ptr(), scale, scale, slots.data_ptr(),
+                   slots[1:].data_ptr(), 1.0 / (h * h * 3 * gbs), g.view(), n, h, h)
+  plan.add_mse_loss("mse", d.view(), 1.0, 1.0 / (64 * gbs), 2.0 / (64 * gbs), slots[2:].data_ptr(),
+                    gd.view(), n, 8, 8)
+  plan.add_img_prep("prep", img.data_ptr(), nv.NULL_VIEW, refl.view(), 3, plain.view(), n, h, h)
+  # adam
+  w = torch.randn(1024, device="cuda"); w0 = w.clone()
+  gr = torch.randn(1024, device="cuda")
+  m = torch.zeros(1024, device="cuda"); v = torch.zeros(1024, device="cuda")
+  wb = torch.zeros(1024, device="cuda", dtype=torch.bfloat16)
+  step = torch.zeros(1, device="cuda", dtype=torch.int32)
+  for _ in range(2):
+    plan.add_adam("adam", w.data_ptr(), m.data_ptr(), v.data_ptr(), gr.data_ptr(), wb.data_ptr(),
+                  step.data_ptr(), 2e-4, 0.5, 0.9, 1e-7, 1.0, 1024)
+    plan.add_step_increment("inc", step.data_ptr())
+  run(plan)
+  p3 = pred.t[..., :3].float()
+  assert math.isclose(slots[0].item(), 10 * (img - p3).abs().flatten(1).mean(1).sum().item() / gbs, rel_tol=1e-3)
+  assert math.isclose(slots[1].item(), (img - p3).abs().flatten(1).mean(1).sum().item() / gbs, rel_tol=1e-3)
+  assert torch.allclose(g.t[..., :3].float(), -scale * torch.sign(img - p3), atol=1e-3 * scale, rtol=1e-2)
+  dd = d.t[..., 0].float()
+  assert math.isclose(slots[2].item(), ((1 - dd) ** 2).flatten(1).mean(1).sum().item() / gbs, rel_tol=1e-3)
+  assert rel_err(gd.t[..., 0], 2.0 / (64 * gbs) * (dd - 1)) < 1e-2
+  assert rel_err(refl.t[..., :3], O.reflect_pad(img, 3)) < 1e-2
+  assert rel_err(plain.interior()[..., :3], img) < 1e-2 and plain.t[:, 0].abs().max() == 0
+  from tf2_cyclegan_b200.ops.keras_adam import KerasAdam
+  opt = KerasAdam()
+  ref = {"w": w0.clone()}
+  for _ in range(2):
+    opt.apply_gradients(ref, {"w": gr})
+  assert torch.allclose(w, ref["w"], atol=1e-6) and step.item() == 2
+  assert torch.allclose(wb.float(), w, atol=1e-2)

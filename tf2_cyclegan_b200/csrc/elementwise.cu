@@ -1,0 +1,527 @@
+// Bandwidth-bound kernels around the GEMMs (see elementwise.cuh).
+#include "elementwise.cuh"
+
+namespace b2 {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ const __nv_bfloat16* vptr(const View& v, int n, int h, int w) {
+  return reinterpret_cast<const __nv_bfloat16*>(v.p) + n * v.sn + h * v.sh + w * v.sw;
+}
+__device__ __forceinline__ __nv_bfloat16* vptr_mut(const View& v, int n, int h, int w) {
+  return reinterpret_cast<__nv_bfloat16*>(v.p) + n * v.sn + h * v.sh + w * v.sw;
+}
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = unpack_bf16x2(w[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]);
+  u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]);
+  u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
+  *reinterpret_cast<uint4*>(p) = pack8(f);
+}
+
+// reflected halo coordinates of interior coordinate i (size n, pad p): up to 2 values incl. i
+__device__ __forceinline__ int reflect_set(int i, int n, int p, int (&out)[2]) {
+  out[0] = i;
+  int cnt = 1;
+  if (p > 0) {
+    if (i >= 1 && i <= p) out[cnt++] = -i;
+    else if (i >= n - 1 - p && i <= n - 2) out[cnt++] = 2 * (n - 1) - i;
+  }
+  return cnt;
+}
+
+__device__ __forceinline__ float act_grad_from_pre(float y, int act) {
+  if (act == ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (act == ACT_LEAKY) return y > 0.f ? 1.f : 0.2f;
+  return 1.f;
+}
+
+// gradient gather with optional reflect-fold (sum of the halo positions that mirror (h, w))
+__device__ __forceinline__ void gather_g(const View& g1, int fold, const View& g2, int n, int h,
+                                         int w, int H, int W, int c, float (&g)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = 0.f;
+  int hs[2], ws[2];
+  const int nh = reflect_set(h, H, fold, hs);
+  const int nw = reflect_set(w, W, fold, ws);
+  for (int a = 0; a < nh; ++a)
+    for (int b = 0; b < nw; ++b) {
+      float t[8];
+      load8(vptr(g1, n, hs[a], ws[b]) + c, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += t[j];
+    }
+  if (g2.p != nullptr) {
+    float t[8];
+    load8(vptr(g2, n, h, w) + c, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] += t[j];
+  }
+}
+
+// ------------------------------------------------------------------ in_apply
+__global__ void __launch_bounds__(kThreads) in_apply_kernel(const InApplyParams p) {
+  const int c8 = p.C >> 3;
+  const long long total = static_cast<long long>(p.N) * p.H * p.W * c8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % c8) * 8;
+    long long r = i / c8;
+    const int w = static_cast<int>(r % p.W);
+    r /= p.W;
+    const int h = static_cast<int>(r % p.H);
+    const int n = static_cast<int>(r / p.H);
+    float v[8];
+    load8(vptr(p.x, n, h, w) + c, v);
+    if (p.stats != nullptr) {
+      const float* st = p.stats + (static_cast<long long>(n) * p.C + c) * 2;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float mean = st[2 * j] * p.inv_count;
+        const float var = fmaxf(st[2 * j + 1] * p.inv_count - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + p.eps);
+        v[j] = (v[j] - mean) * rstd * __ldg(p.gamma + c + j) + __ldg(p.beta + c + j);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], p.act);
+    if (p.skip.p != nullptr) {
+      float s[8];
+      load8(vptr(p.skip, n, h, w) + c, s);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += s[j];
+    }
+    const uint4 pk = pack8(v);
+    int hs[2], ws[2];
+    const int nh = reflect_set(h, p.H, p.halo, hs);
+    const int nw = reflect_set(w, p.W, p.halo, ws);
+    for (int a = 0; a < nh; ++a)
+      for (int b = 0; b < nw; ++b)
+        *reinterpret_cast<uint4*>(vptr_mut(p.dst, n, hs[a], ws[b]) + c) = pk;
+  }
+}
+
+// ------------------------------------------------------------ in_bwd_reduce
+// grid: (pixel chunks, N). Threads: (C/8 channel groups) x (256 / (C/8) pixel lanes).
+__global__ void __launch_bounds__(kThreads) in_bwd_reduce_kernel(const InBwdReduceParams p,
+                                                                 int pix_per_block) {
+  extern __shared__ float red[];   // [lanes][C][2]
+  const int c8 = p.C >> 3;
+  const int lanes = kThreads / c8;
+  const int cg = threadIdx.x % c8;
+  const int ln = threadIdx.x / c8;
+  const int c = cg * 8;
+  const int n = blockIdx.y;
+  const int HW = p.H * p.W;
+  const int pix0 = blockIdx.x * pix_per_block;
+  const int pix1 = min(HW, pix0 + pix_per_block);
+
+  float mean[8], rstd[8], gam[8], bet[8];
+  const bool has_in = p.stats != nullptr;
+  if (has_in) {
+    const float* st = p.stats + (static_cast<long long>(n) * p.C + c) * 2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mean[j] = st[2 * j] * p.inv_count;
+      const float var = fmaxf(st[2 * j + 1] * p.inv_count - mean[j] * mean[j], 0.f);
+      rstd[j] = rsqrtf(var + p.eps);
+      gam[j] = __ldg(p.gamma + c + j);
+      bet[j] = __ldg(p.beta + c + j);
+    }
+  }
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+
+  for (int pix = pix0 + ln; pix < pix1; pix += lanes) {
+    const int h = pix / p.W, w = pix - h * p.W;
+    float g[8], x[8];
+    gather_g(p.g1, p.fold1, p.g2, n, h, w, p.H, p.W, c, g);
+    if (has_in) {
+      load8(vptr(p.x, n, h, w) + c, x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (x[j] - mean[j]) * rstd[j];
+        const float y = xh * gam[j] + bet[j];
+        g[j] *= act_grad_from_pre(y, p.act);
+        // statistics of the value that is actually stored (bf16)
+        const float gq = __bfloat162float(__float2bfloat16(g[j]));
+        s1[j] += gq;
+        s2[j] += gq * xh;
+      }
+    }
+    store8(vptr_mut(p.dy, n, h, w) + c, g);
+  }
+  if (!has_in || p.bstats == nullptr) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[(ln * p.C + c + j) * 2 + 0] = s1[j];
+    red[(ln * p.C + c + j) * 2 + 1] = s2[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.C * 2; i += kThreads) {
+    float acc = 0.f;
+    for (int l = 0; l < lanes; ++l) acc += red[l * p.C * 2 + i];
+    atomicAdd(p.bstats + static_cast<long long>(n) * p.C * 2 + i, acc);
+  }
+}
+
+// ------------------------------------------------------------- in_bwd_apply
+__global__ void __launch_bounds__(kThreads) in_bwd_apply_kernel(const InBwdApplyParams p) {
+  const int c8 = p.C >> 3;
+  const long long total = static_cast<long long>(p.N) * p.H * p.W * c8;
+  if (blockIdx.x == 0 && p.dgamma != nullptr) {   // parameter gradients: sum over images
+    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+      float dg = 0.f, db = 0.f;
+      for (int n = 0; n < p.N; ++n) {
+        const float* bs = p.bstats + (static_cast<long long>(n) * p.C + c) * 2;
+        db += bs[0];
+        dg += bs[1];
+      }
+      p.dgamma[c] += dg;
+      p.dbeta[c] += db;
+    }
+  }
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % c8) * 8;
+    long long r = i / c8;
+    const int w = static_cast<int>(r % p.W);
+    r /= p.W;
+    const int h = static_cast<int>(r % p.H);
+    const int n = static_cast<int>(r / p.H);
+    float dy[8], x[8], out[8];
+    load8(vptr(p.dy, n, h, w) + c, dy);
+    load8(vptr(p.x, n, h, w) + c, x);
+    const float* st = p.stats + (static_cast<long long>(n) * p.C + c) * 2;
+    const float* bs = p.bstats + (static_cast<long long>(n) * p.C + c) * 2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float mean = st[2 * j] * p.inv_count;
+      const float var = fmaxf(st[2 * j + 1] * p.inv_count - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + p.eps);
+      const float xh = (x[j] - mean) * rstd;
+      const float m1 = bs[2 * j] * p.inv_count;
+      const float m2 = bs[2 * j + 1] * p.inv_count;
+      out[j] = __ldg(p.gamma + c + j) * rstd * (dy[j] - m1 - xh * m2);
+    }
+    store8(vptr_mut(p.dx, n, h, w) + c, out);
+  }
+}
+
+// ------------------------------------------------------------------ act_bwd
+__global__ void __launch_bounds__(kThreads) act_bwd_kernel(const ActBwdParams p) {
+  __shared__ float sb[64];
+  const int c8 = p.C >> 3;
+  const long long total = static_cast<long long>(p.N) * p.H * p.W * c8;
+  if (threadIdx.x < 64) sb[threadIdx.x] = 0.f;
+  __syncthreads();
+  float bacc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bacc[j] = 0.f;
+  int my_c = -1;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % c8) * 8;
+    long long r = i / c8;
+    const int w = static_cast<int>(r % p.W);
+    r /= p.W;
+    const int h = static_cast<int>(r % p.H);
+    const int n = static_cast<int>(r / p.H);
+    float g[8], o[8];
+    gather_g(p.g1, p.fold1, p.g2, n, h, w, p.H, p.W, c, g);
+    load8(vptr(p.out, n, h, w) + c, o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float d = 1.f;
+      if (p.act == ACT_TANH) d = 1.f - o[j] * o[j];
+      else if (p.act == ACT_LEAKY) d = o[j] > 0.f ? 1.f : 0.2f;
+      else if (p.act == ACT_RELU) d = o[j] > 0.f ? 1.f : 0.f;
+      g[j] = (c + j < p.c_valid) ? g[j] * d : 0.f;
+      bacc[j] += __bfloat162float(__float2bfloat16(g[j]));
+    }
+    my_c = c;   // grid stride is a multiple of c8 => a thread always sees the same c
+    store8(vptr_mut(p.dy, n, h, w) + c, g);
+  }
+  if (p.dbias != nullptr) {
+    if (my_c >= 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (my_c + j < p.c_valid) atomicAdd(&sb[my_c + j], bacc[j]);
+    }
+    __syncthreads();
+    if (threadIdx.x < p.c_valid) atomicAdd(p.dbias + threadIdx.x, sb[threadIdx.x]);
+  }
+}
+
+// ----------------------------------------------------------------- img_prep
+__global__ void __launch_bounds__(kThreads) img_prep_kernel(const ImgPrepParams p) {
+  const long long total = static_cast<long long>(p.N) * p.H * p.W;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(i % p.W);
+    long long r = i / p.W;
+    const int h = static_cast<int>(r % p.H);
+    const int n = static_cast<int>(r / p.H);
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (p.src_is_f32) {
+      const float* s = reinterpret_cast<const float*>(p.src) + i * 3;
+      v[0] = s[0]; v[1] = s[1]; v[2] = s[2];
+    } else {
+      float t[8];
+      load8(vptr(p.src_view, n, h, w), t);
+      v[0] = t[0]; v[1] = t[1]; v[2] = t[2];
+    }
+    const uint4 pk = pack8(v);
+    if (p.dst_plain.p != nullptr)
+      *reinterpret_cast<uint4*>(vptr_mut(p.dst_plain, n, h, w)) = pk;
+    if (p.dst_reflect.p != nullptr) {
+      int hs[2], ws[2];
+      const int nh = reflect_set(h, p.H, p.reflect_pad, hs);
+      const int nw = reflect_set(w, p.W, p.reflect_pad, ws);
+      for (int a = 0; a < nh; ++a)
+        for (int b = 0; b < nw; ++b)
+          *reinterpret_cast<uint4*>(vptr_mut(p.dst_reflect, n, hs[a], ws[b])) = pk;
+    }
+  }
+}
+
+// ------------------------------------------------------------------- losses
+__device__ __forceinline__ float block_sum(float v) {
+  __shared__ float sh[kThreads / 32];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (threadIdx.x < kThreads / 32) t = sh[threadIdx.x];
+  if (threadIdx.x < 32) t = warp_sum(t);
+  __syncthreads();
+  return t;   // valid in thread 0
+}
+
+__global__ void __launch_bounds__(kThreads) l1_loss_kernel(const L1LossParams p) {
+  const long long total = static_cast<long long>(p.N) * p.H * p.W;
+  float acc = 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(i % p.W);
+    long long r = i / p.W;
+    const int h = static_cast<int>(r % p.H);
+    const int n = static_cast<int>(r / p.H);
+    float pr[8];
+    load8(vptr(p.pred, n, h, w), pr);
+    const float* t = p.target + i * 3;
+    float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float d = t[j] - pr[j];
+      acc += fabsf(d);
+      g[j] = d > 0.f ? -p.grad_scale : (d < 0.f ? p.grad_scale : 0.f);
+    }
+    if (p.g.p != nullptr) store8(vptr_mut(p.g, n, h, w), g);
+  }
+  const float tot = block_sum(acc);
+  if (threadIdx.x == 0) {
+    atomicAdd(p.loss_slot, tot * p.loss_scale);
+    if (p.err_slot != nullptr) atomicAdd(p.err_slot, tot * p.err_scale);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) mse_loss_kernel(const MseLossParams p) {
+  const long long total = static_cast<long long>(p.N) * p.H * p.W;
+  float acc = 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(i % p.W);
+    long long r = i / p.W;
+    const int h = static_cast<int>(r % p.H);
+    const int n = static_cast<int>(r / p.H);
+    const float d = __bfloat162float(*vptr(p.d, n, h, w));
+    const float e = p.target - d;
+    acc += e * e;
+    if (p.g.p != nullptr) *vptr_mut(p.g, n, h, w) = __float2bfloat16(-p.grad_scale * e);
+  }
+  const float tot = block_sum(acc);
+  if (threadIdx.x == 0) atomicAdd(p.loss_slot, tot * p.loss_scale);
+}
+
+// --------------------------------------------------------------------- adam
+__global__ void __launch_bounds__(kThreads) adam_kernel(const AdamParams p) {
+  const int t = *p.step + 1;
+  const float lr_t = p.lr * sqrtf(1.f - powf(p.beta2, static_cast<float>(t))) /
+                     (1.f - powf(p.beta1, static_cast<float>(t)));
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < p.n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float g = p.g[i] * p.grad_scale;
+    const float m = p.beta1 * p.m[i] + (1.f - p.beta1) * g;
+    const float v = p.beta2 * p.v[i] + (1.f - p.beta2) * g * g;
+    const float w = p.w[i] - lr_t * m / (sqrtf(v) + p.eps);
+    p.m[i] = m;
+    p.v[i] = v;
+    p.w[i] = w;
+    if (p.w_bf16 != nullptr) p.w_bf16[i] = __float2bfloat16(w);
+  }
+}
+__global__ void step_increment_kernel(int* step) { *step += 1; }
+
+__global__ void __launch_bounds__(kThreads) mask_grad_kernel(float* g, const uint8_t* mask,
+                                                             long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    if (mask[i] == 0) g[i] = 0.f;
+}
+
+// --------------------------------------------------- PatchGAN output layer bwd
+// dX[n,h,w,c] = sum_{r,s} gd[n, h - r + pb, w - s + pb] * W[0][r*4+s][c]
+__global__ void __launch_bounds__(kThreads) d4_dgrad_kernel(const D4BwdParams p) {
+  const int c8 = p.C >> 3;
+  const long long total = static_cast<long long>(p.N) * p.H * p.W * c8;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % c8) * 8;
+    long long r = i / c8;
+    const int w = static_cast<int>(r % p.W);
+    r /= p.W;
+    const int h = static_cast<int>(r % p.H);
+    const int n = static_cast<int>(r / p.H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int kr = 0; kr < 4; ++kr) {
+      const int oh = h - kr + p.pad_before;
+      if (oh < 0 || oh >= p.H) continue;
+      for (int ks = 0; ks < 4; ++ks) {
+        const int ow = w - ks + p.pad_before;
+        if (ow < 0 || ow >= p.W) continue;
+        const float g = __bfloat162float(*vptr(p.gd, n, oh, ow));
+        float wv[8];
+        load8(p.w + static_cast<long long>(kr * 4 + ks) * p.C + c, wv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += g * wv[j];
+      }
+    }
+    store8(vptr_mut(p.dx, n, h, w) + c, acc);
+  }
+}
+
+// dW[0][t][c] += sum_pix gd[pix] * a[pix + tap]; grid: (16 taps, pixel chunks)
+__global__ void __launch_bounds__(kThreads) d4_wgrad_kernel(const D4BwdParams p, int chunks) {
+  const int t = blockIdx.x;
+  const int kr = t >> 2, ks = t & 3;
+  const long long npix = static_cast<long long>(p.N) * p.H * p.W;
+  const long long per = (npix + chunks - 1) / chunks;
+  const long long i0 = blockIdx.y * per, i1 = min(npix, i0 + per);
+  float gsum = 0.f;
+  // each thread owns channels threadIdx.x*2 .. (C <= 512 => 2 channels per thread)
+  const int c = threadIdx.x * 2;
+  float a0 = 0.f, a1 = 0.f;
+  for (long long i = i0; i < i1; ++i) {
+    const int w = static_cast<int>(i % p.W);
+    long long r = i / p.W;
+    const int h = static_cast<int>(r % p.H);
+    const int n = static_cast<int>(r / p.H);
+    const float g = __bfloat162float(*vptr(p.gd, n, h, w));
+    gsum += g;
+    const int ih = h + kr - p.pad_before, iw = w + ks - p.pad_before;
+    if (ih < 0 || ih >= p.H || iw < 0 || iw >= p.W || c >= p.C) continue;
+    const float2 av = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vptr(p.a, n, ih, iw) + c));
+    a0 += g * av.x;
+    a1 += g * av.y;
+  }
+  if (c < p.C) {
+    atomicAdd(p.dw + static_cast<long long>(t) * p.C + c, a0);
+    atomicAdd(p.dw + static_cast<long long>(t) * p.C + c + 1, a1);
+  }
+  if (t == 0 && threadIdx.x == 0 && p.dbias != nullptr) atomicAdd(p.dbias, gsum);
+}
+
+inline int grid_for(long long total, int cap = 148 * 16) {
+  long long b = (total + kThreads - 1) / kThreads;
+  return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
+}
+// grid size that is a multiple of c8 channel groups so a thread keeps the same channel group
+inline int grid_for_fixed_c(long long total, int c8) {
+  int g = grid_for(total);
+  // stride = g * 256 must be a multiple of c8 (c8 is a power of two <= 64 => always true)
+  (void)c8;
+  return g;
+}
+
+}  // namespace
+
+void launch_in_apply(const InApplyParams& p, cudaStream_t s) {
+  const long long total = static_cast<long long>(p.N) * p.H * p.W * (p.C / 8);
+  in_apply_kernel<<<grid_for(total), kThreads, 0, s>>>(p);
+}
+
+void launch_in_bwd_reduce(const InBwdReduceParams& p, cudaStream_t s) {
+  const int HW = p.H * p.W;
+  const int c8 = p.C / 8;
+  const int lanes = kThreads / c8;
+  int pix_per_block = lanes * 16;
+  if (pix_per_block > HW) pix_per_block = HW;
+  dim3 grid((HW + pix_per_block - 1) / pix_per_block, p.N);
+  const size_t smem = static_cast<size_t>(lanes) * p.C * 2 * sizeof(float);
+  in_bwd_reduce_kernel<<<grid, kThreads, smem, s>>>(p, pix_per_block);
+}
+
+void launch_in_bwd_apply(const InBwdApplyParams& p, cudaStream_t s) {
+  const long long total = static_cast<long long>(p.N) * p.H * p.W * (p.C / 8);
+  in_bwd_apply_kernel<<<grid_for(total), kThreads, 0, s>>>(p);
+}
+
+void launch_act_bwd(const ActBwdParams& p, cudaStream_t s) {
+  const long long total = static_cast<long long>(p.N) * p.H * p.W * (p.C / 8);
+  act_bwd_kernel<<<grid_for_fixed_c(total, p.C / 8), kThreads, 0, s>>>(p);
+}
+
+void launch_img_prep(const ImgPrepParams& p, cudaStream_t s) {
+  const long long total = static_cast<long long>(p.N) * p.H * p.W;
+  img_prep_kernel<<<grid_for(total), kThreads, 0, s>>>(p);
+}
+
+void launch_l1_loss(const L1LossParams& p, cudaStream_t s) {
+  const long long total = static_cast<long long>(p.N) * p.H * p.W;
+  l1_loss_kernel<<<grid_for(total, 148 * 4), kThreads, 0, s>>>(p);
+}
+
+void launch_mse_loss(const MseLossParams& p, cudaStream_t s) {
+  const long long total = static_cast<long long>(p.N) * p.H * p.W;
+  mse_loss_kernel<<<grid_for(total, 148), kThreads, 0, s>>>(p);
+}
+
+void launch_adam(const AdamParams& p, cudaStream_t s) {
+  adam_kernel<<<grid_for(p.n, 148 * 8), kThreads, 0, s>>>(p);
+}
+void launch_step_increment(int* step, cudaStream_t s) { step_increment_kernel<<<1, 1, 0, s>>>(step); }
+
+void launch_mask_grad(float* g, const uint8_t* mask, long long n, cudaStream_t s) {
+  mask_grad_kernel<<<grid_for(n), kThreads, 0, s>>>(g, mask, n);
+}
+
+void launch_d4_dgrad(const D4BwdParams& p, cudaStream_t s) {
+  const long long total = static_cast<long long>(p.N) * p.H * p.W * (p.C / 8);
+  d4_dgrad_kernel<<<grid_for(total), kThreads, 0, s>>>(p);
+}
+void launch_d4_wgrad(const D4BwdParams& p, cudaStream_t s) {
+  const int chunks = 32;
+  d4_wgrad_kernel<<<dim3(16, chunks), kThreads, 0, s>>>(p, chunks);
+}
+
+}  // namespace b2

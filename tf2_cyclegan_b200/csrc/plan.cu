@@ -1,0 +1,328 @@
+// Host runtime: the Plan (a flat, pre-resolved list of kernel launches) and its
+// Python bindings. Python compiles a network + batch size into a Plan ONCE —
+// buffer addresses, TMA descriptors, tap tables and launch geometry are all
+// baked into parameter blocks — and then `run()` replays it with no Python, no
+// allocation and no descriptor encoding on the hot path; the whole range is
+// also CUDA-graph capturable. This is the B200 counterpart of the reference's
+// tf.function graph executor (main.py:197,269,325).
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <functional>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "allreduce_adam.cuh"
+#include "conv_gemm.cuh"
+#include "elementwise.cuh"
+#include "wgrad_gemm.cuh"
+
+namespace py = pybind11;
+using namespace b2;
+
+namespace {
+
+void check(cudaError_t e, const char* what) {
+  if (e != cudaSuccess)
+    throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    check(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q),
+          "cudaGetDriverEntryPoint(cuTensorMapEncodeTiled)");
+    if (ptr == nullptr || q != cudaDriverEntryPointSuccess)
+      throw std::runtime_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// dtype: 0 = bf16, 1 = fp32, 2 = uint8 (fp8 payload). swizzle: 0 none, 3 = 128B.
+py::bytes encode_tmap(uint64_t ptr, int dtype, std::vector<uint64_t> dims,
+                      std::vector<uint64_t> strides_bytes, std::vector<uint32_t> box,
+                      int swizzle) {
+  const int rank = static_cast<int>(dims.size());
+  if (rank < 1 || rank > 5 || static_cast<int>(box.size()) != rank ||
+      static_cast<int>(strides_bytes.size()) != rank - 1)
+    throw std::runtime_error("encode_tmap: bad rank / argument sizes");
+  CUtensorMap m;
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  cuuint64_t gdim[5], gstr[5];
+  cuuint32_t bx[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
+  CUtensorMapDataType dt = dtype == 0 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                          : dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                       : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  CUtensorMapSwizzle sw = swizzle == 3 ? CU_TENSOR_MAP_SWIZZLE_128B
+                         : swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B
+                         : swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                        : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = get_encode_fn()(&m, dt, rank, reinterpret_cast<void*>(ptr), gdim, gstr, bx, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    throw std::runtime_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
+  return py::bytes(reinterpret_cast<const char*>(&m), sizeof(m));
+}
+
+CUtensorMap tmap_from(const py::bytes& b) {
+  std::string s = b;
+  if (s.size() != sizeof(CUtensorMap)) throw std::runtime_error("tensor map must be 128 bytes");
+  CUtensorMap m;
+  memcpy(&m, s.data(), sizeof(m));
+  return m;
+}
+
+using ViewT = std::tuple<uint64_t, long long, long long, long long>;
+View view_from(const ViewT& t) {
+  View v;
+  v.p = reinterpret_cast<void*>(std::get<0>(t));
+  v.sn = std::get<1>(t);
+  v.sh = std::get<2>(t);
+  v.sw = std::get<3>(t);
+  return v;
+}
+template <class T>
+T* P(uint64_t p) { return reinterpret_cast<T*>(p); }
+
+using TapT = std::tuple<int, int, int, int, int>;   // map, dn, dw, dh, bk
+void fill_taps(const std::vector<TapT>& taps, Tap* dst, int* n) {
+  if (taps.size() > static_cast<size_t>(kMaxTaps)) throw std::runtime_error("too many taps");
+  *n = static_cast<int>(taps.size());
+  for (size_t i = 0; i < taps.size(); ++i) {
+    dst[i].map = static_cast<int16_t>(std::get<0>(taps[i]));
+    dst[i].dn = static_cast<int16_t>(std::get<1>(taps[i]));
+    dst[i].dw = std::get<2>(taps[i]);
+    dst[i].dh = std::get<3>(taps[i]);
+    dst[i].bk = std::get<4>(taps[i]);
+  }
+}
+
+class Plan {
+ public:
+  struct Op {
+    std::string name;
+    std::function<void(cudaStream_t)> fn;
+  };
+
+  int add(std::string name, std::function<void(cudaStream_t)> fn) {
+    ops_.push_back({std::move(name), std::move(fn)});
+    return static_cast<int>(ops_.size()) - 1;
+  }
+  int size() const { return static_cast<int>(ops_.size()); }
+  std::vector<std::string> names() const {
+    std::vector<std::string> n;
+    for (auto& o : ops_) n.push_back(o.name);
+    return n;
+  }
+
+  void run(int begin, int end, uint64_t stream, bool check_each) {
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (end < 0 || end > size()) end = size();
+    for (int i = begin; i < end; ++i) {
+      ops_[i].fn(s);
+      if (check_each) {
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess)
+          throw std::runtime_error("plan op #" + std::to_string(i) + " (" + ops_[i].name +
+                                   ") failed: " + cudaGetErrorString(e));
+      }
+    }
+    check(cudaGetLastError(), "plan launch");
+  }
+
+  // ------------------------------------------------------------- GEMM ops
+  int add_conv_gemm(std::string name, std::vector<py::bytes> a_maps, py::bytes b_map,
+                    std::vector<TapT> taps, int cin_blocks, int tiles_w, int tiles_h, int bw,
+                    int bh, int w_limit, uint64_t out, long long sn, long long sh, long long sw,
+                    int cout, uint64_t bias, int act, uint64_t stats, int block_n, bool b_mn,
+                    int num_images) {
+    auto p = std::make_shared<ConvGemmParams>();
+    memset(p.get(), 0, sizeof(ConvGemmParams));
+    if (a_maps.empty() || a_maps.size() > kMaxAMaps) throw std::runtime_error("bad a_maps");
+    for (size_t i = 0; i < a_maps.size(); ++i) p->tmA[i] = tmap_from(a_maps[i]);
+    p->tmB = tmap_from(b_map);
+    fill_taps(taps, p->taps, &p->num_taps);
+    if (bw * bh != 128) throw std::runtime_error("conv_gemm tile must be 128 pixels");
+    p->cin_blocks = cin_blocks; p->tiles_w = tiles_w; p->tiles_h = tiles_h;
+    p->bw = bw; p->bh = bh; p->w_limit = w_limit;
+    p->out = P<__nv_bfloat16>(out); p->out_sn = sn; p->out_sh = sh; p->out_sw = sw;
+    p->cout = cout; p->bias = P<const float>(bias); p->act = act; p->stats = P<float>(stats);
+    return add(std::move(name), [p, block_n, b_mn, num_images](cudaStream_t s) {
+      launch_conv_gemm(*p, block_n, b_mn, num_images, s);
+    });
+  }
+
+  int add_wgrad(std::string name, py::bytes dy_map, std::vector<py::bytes> a_maps,
+                std::vector<TapT> taps, int ktiles_w, int ktiles_h, int kbw, int kbh,
+                int num_images, int cin, int cout, uint64_t dw, long long ldw, int block_n,
+                int ksplit) {
+    auto p = std::make_shared<WgradParams>();
+    memset(p.get(), 0, sizeof(WgradParams));
+    p->tmDY = tmap_from(dy_map);
+    if (a_maps.empty() || a_maps.size() > kMaxAMaps) throw std::runtime_error("bad a_maps");
+    for (size_t i = 0; i < a_maps.size(); ++i) p->tmA[i] = tmap_from(a_maps[i]);
+    fill_taps(taps, p->taps, &p->num_taps);
+    if (kbw * kbh != 64) throw std::runtime_error("wgrad K tile must be 64 pixels");
+    p->ktiles_w = ktiles_w; p->ktiles_h = ktiles_h; p->kbw = kbw; p->kbh = kbh;
+    p->num_images = num_images; p->cin = cin; p->cout = cout;
+    p->dw = P<float>(dw); p->ldw = ldw;
+    return add(std::move(name), [p, block_n, ksplit](cudaStream_t s) {
+      launch_wgrad_gemm(*p, block_n, ksplit, s);
+    });
+  }
+
+  // ------------------------------------------------------ elementwise ops
+  int add_in_apply(std::string name, ViewT x, uint64_t stats, uint64_t gamma, uint64_t beta,
+                   float inv_count, float eps, int act, ViewT skip, ViewT dst, int halo, int N,
+                   int H, int W, int C) {
+    InApplyParams p{view_from(x), P<const float>(stats), P<const float>(gamma),
+                    P<const float>(beta), inv_count, eps, act, view_from(skip), view_from(dst),
+                    halo, N, H, W, C};
+    return add(std::move(name), [p](cudaStream_t s) { launch_in_apply(p, s); });
+  }
+  int add_in_bwd_reduce(std::string name, ViewT g1, int fold1, ViewT g2, ViewT x, uint64_t stats,
+                        uint64_t gamma, uint64_t beta, float inv_count, float eps, int act,
+                        ViewT dy, uint64_t bstats, int N, int H, int W, int C) {
+    InBwdReduceParams p{view_from(g1), fold1, view_from(g2), view_from(x),
+                        P<const float>(stats), P<const float>(gamma), P<const float>(beta),
+                        inv_count, eps, act, view_from(dy), P<float>(bstats), N, H, W, C};
+    return add(std::move(name), [p](cudaStream_t s) { launch_in_bwd_reduce(p, s); });
+  }
+  int add_in_bwd_apply(std::string name, ViewT dy, ViewT x, uint64_t stats, uint64_t bstats,
+                       uint64_t gamma, float inv_count, float eps, ViewT dx, uint64_t dgamma,
+                       uint64_t dbeta, int N, int H, int W, int C) {
+    InBwdApplyParams p{view_from(dy), view_from(x), P<const float>(stats),
+                       P<const float>(bstats), P<const float>(gamma), inv_count, eps,
+                       view_from(dx), P<float>(dgamma), P<float>(dbeta), N, H, W, C};
+    return add(std::move(name), [p](cudaStream_t s) { launch_in_bwd_apply(p, s); });
+  }
+  int add_act_bwd(std::string name, ViewT g1, int fold1, ViewT g2, ViewT out, int act, ViewT dy,
+                  uint64_t dbias, int c_valid, int N, int H, int W, int C) {
+    ActBwdParams p{view_from(g1), fold1, view_from(g2), view_from(out), act, view_from(dy),
+                   P<float>(dbias), c_valid, N, H, W, C};
+    return add(std::move(name), [p](cudaStream_t s) { launch_act_bwd(p, s); });
+  }
+  int add_img_prep(std::string name, uint64_t src_f32, ViewT src_view, ViewT dst_reflect,
+                   int reflect_pad, ViewT dst_plain, int N, int H, int W) {
+    ImgPrepParams p{P<const void>(src_f32), src_f32 != 0 ? 1 : 0, view_from(src_view),
+                    view_from(dst_reflect), reflect_pad, view_from(dst_plain), N, H, W};
+    return add(std::move(name), [p](cudaStream_t s) { launch_img_prep(p, s); });
+  }
+  int add_l1_loss(std::string name, ViewT pred, uint64_t target, float loss_scale,
+                  float grad_scale, uint64_t loss_slot, uint64_t err_slot, float err_scale,
+                  ViewT g, int N, int H, int W) {
+    L1LossParams p{view_from(pred), P<const float>(target), loss_scale, grad_scale,
+                   P<float>(loss_slot), P<float>(err_slot), err_scale, view_from(g), N, H, W};
+    return add(std::move(name), [p](cudaStream_t s) { launch_l1_loss(p, s); });
+  }
+  int add_mse_loss(std::string name, ViewT d, float target, float loss_scale, float grad_scale,
+                   uint64_t loss_slot, ViewT g, int N, int H, int W) {
+    MseLossParams p{view_from(d), target, loss_scale, grad_scale, P<float>(loss_slot),
+                    view_from(g), N, H, W};
+    return add(std::move(name), [p](cudaStream_t s) { launch_mse_loss(p, s); });
+  }
+  int add_adam(std::string name, uint64_t w, uint64_t m, uint64_t v, uint64_t g, uint64_t w_bf16,
+               uint64_t step, float lr, float b1, float b2, float eps, float grad_scale,
+               long long n) {
+    AdamParams p{P<float>(w), P<float>(m), P<float>(v), P<const float>(g),
+                 P<__nv_bfloat16>(w_bf16), P<const int>(step), lr, b1, b2, eps, grad_scale, n};
+    return add(std::move(name), [p](cudaStream_t s) { launch_adam(p, s); });
+  }
+  int add_step_increment(std::string name, uint64_t step) {
+    return add(std::move(name), [step](cudaStream_t s) { launch_step_increment(P<int>(step), s); });
+  }
+  int add_mask_grad(std::string name, uint64_t g, uint64_t mask, long long n) {
+    return add(std::move(name),
+               [g, mask, n](cudaStream_t s) { launch_mask_grad(P<float>(g), P<const uint8_t>(mask), n, s); });
+  }
+  int add_gather_bf16(std::string name, uint64_t dst, uint64_t src_f32, uint64_t idx, long long n) {
+    return add(std::move(name), [dst, src_f32, idx, n](cudaStream_t s) {
+      launch_gather_bf16(P<__nv_bfloat16>(dst), P<const float>(src_f32), P<const int>(idx), n, s);
+    });
+  }
+  int add_memset(std::string name, uint64_t ptr, long long nbytes) {
+    return add(std::move(name), [ptr, nbytes](cudaStream_t s) {
+      check(cudaMemsetAsync(P<void>(ptr), 0, nbytes, s), "cudaMemsetAsync");
+    });
+  }
+  int add_d4_bwd(std::string name, ViewT gd, ViewT a, uint64_t w, ViewT dx, uint64_t dw,
+                 uint64_t dbias, int pad_before, int N, int H, int W, int C, bool dgrad,
+                 bool wgrad) {
+    D4BwdParams p{view_from(gd), view_from(a), P<const __nv_bfloat16>(w), view_from(dx),
+                  P<float>(dw), P<float>(dbias), pad_before, N, H, W, C};
+    return add(std::move(name), [p, dgrad, wgrad](cudaStream_t s) {
+      if (dgrad) launch_d4_dgrad(p, s);
+      if (wgrad) launch_d4_wgrad(p, s);
+    });
+  }
+  int add_allreduce_adam(std::string name, std::vector<uint64_t> grad_ptrs,
+                         std::vector<uint64_t> wbf16_ptrs, std::vector<uint64_t> signal_ptrs,
+                         uint64_t w, uint64_t m, uint64_t v, uint64_t step, float lr, float b1,
+                         float b2, float eps, long long n, int rank, int world, int num_blocks,
+                         uint64_t mc_grad, uint64_t mc_wbf16) {
+    auto p = std::make_shared<AllreduceAdamParams>();
+    memset(p.get(), 0, sizeof(AllreduceAdamParams));
+    if (world > kMaxRanks) throw std::runtime_error("world too large");
+    for (int r = 0; r < world; ++r) {
+      p->grad[r] = P<float>(grad_ptrs[r]);
+      p->w_bf16[r] = P<__nv_bfloat16>(wbf16_ptrs[r]);
+      p->signal[r] = P<uint32_t>(signal_ptrs[r]);
+    }
+    p->w = P<float>(w); p->m = P<float>(m); p->v = P<float>(v); p->step = P<const int>(step);
+    p->lr = lr; p->beta1 = b1; p->beta2 = b2; p->eps = eps; p->n = n; p->rank = rank;
+    p->world = world; p->mc_grad = P<float>(mc_grad); p->mc_w_bf16 = P<__nv_bfloat16>(mc_wbf16);
+    return add(std::move(name), [p, num_blocks](cudaStream_t s) {
+      launch_allreduce_adam(*p, num_blocks, s);
+    });
+  }
+
+ private:
+  std::vector<Op> ops_;
+};
+
+}  // namespace
+
+PYBIND11_MODULE(_C, m) {
+  m.doc() = "b200-cyclegan native runtime (sm_100a kernels + plan executor)";
+  m.def("encode_tmap", &encode_tmap, py::arg("ptr"), py::arg("dtype"), py::arg("dims"),
+        py::arg("strides_bytes"), py::arg("box"), py::arg("swizzle") = 3);
+  m.def("device_sync", []() { check(cudaDeviceSynchronize(), "cudaDeviceSynchronize"); });
+  m.attr("MAX_TAPS") = kMaxTaps;
+  py::class_<Plan>(m, "Plan")
+      .def(py::init<>())
+      .def("size", &Plan::size)
+      .def("names", &Plan::names)
+      .def("run", &Plan::run, py::arg("begin") = 0, py::arg("end") = -1, py::arg("stream") = 0,
+           py::arg("check_each") = false, py::call_guard<py::gil_scoped_release>())
+      .def("add_conv_gemm", &Plan::add_conv_gemm)
+      .def("add_wgrad", &Plan::add_wgrad)
+      .def("add_in_apply", &Plan::add_in_apply)
+      .def("add_in_bwd_reduce", &Plan::add_in_bwd_reduce)
+      .def("add_in_bwd_apply", &Plan::add_in_bwd_apply)
+      .def("add_act_bwd", &Plan::add_act_bwd)
+      .def("add_img_prep", &Plan::add_img_prep)
+      .def("add_l1_loss", &Plan::add_l1_loss)
+      .def("add_mse_loss", &Plan::add_mse_loss)
+      .def("add_adam", &Plan::add_adam)
+      .def("add_step_increment", &Plan::add_step_increment)
+      .def("add_mask_grad", &Plan::add_mask_grad)
+      .def("add_gather_bf16", &Plan::add_gather_bf16)
+      .def("add_memset", &Plan::add_memset)
+      .def("add_d4_bwd", &Plan::add_d4_bwd)
+      .def("add_allreduce_adam", &Plan::add_allreduce_adam);
+}

@@ -1,0 +1,177 @@
+// Weight-gradient GEMM for sm_100a (tcgen05, both operands MN-major, split-K).
+//
+//   dW[co, tap, ci] += sum_pixels dY[pixel, co] * A_tap[pixel, ci]
+//
+// The reduction dimension is the pixel axis, which is the *strided* axis of the
+// NHWC tensors, so both MMA operands are MN-major: the TMA boxes {64 channels,
+// 64 pixels} land in shared memory exactly as the canonical SWIZZLE_128B
+// MN-major atoms. One CTA owns (co tile of 128) x (ci tile <= 256) x (one tap)
+// x (one K split); partial sums are reduced into the fp32 gradient buffer with
+// vector red.global.add, which also accumulates the three calls of a generator.
+#include "wgrad_gemm.cuh"
+
+namespace b2 {
+
+template <int BLOCK_N>
+struct WgradCfg {
+  static constexpr int kABytes = 2 * 64 * 128;          // 128 co x 64 pixels (2 MN atoms)
+  static constexpr int kBBytes = (BLOCK_N / 64) * 64 * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+  static constexpr int kTmemCols = BLOCK_N;
+  static constexpr int kBarrierBytes = (2 * kStages + 1) * 8 + 16;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + 1024;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b),
+               "f"(c), "f"(d)
+               : "memory");
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(256, 1)
+wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
+  using Cfg = WgradCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles = (p.cin + BLOCK_N - 1) / BLOCK_N;
+  const int m0 = (blockIdx.x / n_tiles) * 128;
+  const int n0 = (blockIdx.x % n_tiles) * BLOCK_N;
+  const Tap tap = p.taps[blockIdx.y];
+  const int ktiles_per_img = p.ktiles_w * p.ktiles_h;
+  const int total_kt = ktiles_per_img * p.num_images;
+  // contiguous K range of this split
+  const int per = (total_kt + gridDim.z - 1) / gridDim.z;
+  const int kt_begin = blockIdx.z * per;
+  const int kt_end = min(total_kt, kt_begin + per);
+  const int num_kb = kt_end - kt_begin;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmDY);
+    tma_prefetch_desc(&p.tmA[tap.map]);
+  } else if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  } else if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (num_kb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        const CUtensorMap* amap = &p.tmA[tap.map];
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int kt = kt_begin + kb;
+          const int img = kt / ktiles_per_img;
+          const int t_in = kt - img * ktiles_per_img;
+          const int th = t_in / p.ktiles_w;
+          const int w0 = (t_in - th * p.ktiles_w) * p.kbw;
+          const int h0 = th * p.kbh;
+          const int s = kb % Cfg::kStages;
+          const uint32_t ph = (kb / Cfg::kStages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+          // channels beyond the tensor extent are zero-filled by TMA (cout / cin < tile)
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            tma_load_4d(sa + j * (64 * 128), &p.tmDY, &full_bar[s], m0 + j * 64, w0, h0, img);
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j)
+            tma_load_4d(sb + j * (64 * 128), amap, &full_bar[s], n0 + j * 64, w0 + tap.dw,
+                        h0 + tap.dh, img + tap.dn);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int s = kb % Cfg::kStages;
+          const uint32_t ph = (kb / Cfg::kStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+          const uint64_t da = make_desc_mnmajor(sa, 64);
+          const uint64_t db = make_desc_mnmajor(sb, 64);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // 16 pixels per MMA = 16 rows x 128 B = 128 x 16-byte units
+            umma_bf16(tmem_base, da + static_cast<uint64_t>(k * 128),
+                      db + static_cast<uint64_t>(k * 128), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(tmem_full_bar);
+      }
+    } else if (warp >= 4) {
+      const int e = threadIdx.x - 128;
+      const int ew = warp - 4;
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+      const int co = m0 + e;
+      float* row = p.dw + static_cast<long long>(co) * p.ldw + tap.bk + n0;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(taddr + c, r);
+        tmem_ld_wait();
+        if (co < p.cout) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (n0 + c + j < p.cin)
+              red_add_v4(row + c + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                         __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+template <int BLOCK_N>
+static void launch_t(const WgradParams& p, int ksplit, cudaStream_t stream) {
+  using Cfg = WgradCfg<BLOCK_N>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(wgrad_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         Cfg::kSmemBytes);
+    configured = true;
+  }
+  const int m_tiles = (p.cout + 127) / 128;
+  const int n_tiles = (p.cin + BLOCK_N - 1) / BLOCK_N;
+  dim3 grid(m_tiles * n_tiles, p.num_taps, ksplit);
+  wgrad_gemm_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(p);
+}
+
+void launch_wgrad_gemm(const WgradParams& p, int block_n, int ksplit, cudaStream_t stream) {
+  switch (block_n) {
+    case 64: return launch_t<64>(p, ksplit, stream);
+    case 128: return launch_t<128>(p, ksplit, stream);
+    case 256: return launch_t<256>(p, ksplit, stream);
+  }
+  fprintf(stderr, "launch_wgrad_gemm: unsupported block_n=%d\n", block_n);
+  abort();
+}
+
+}  // namespace b2

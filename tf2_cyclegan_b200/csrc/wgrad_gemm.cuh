@@ -1,0 +1,22 @@
+// Weight-gradient GEMM (split-K, MN-major operands): shared parameter block.
+#pragma once
+#include "conv_gemm.cuh"
+
+namespace b2 {
+
+struct WgradParams {
+  CUtensorMap tmDY;             // bf16 gradient view [.., Cout], box {64, kbw, kbh, 1}
+  CUtensorMap tmA[kMaxAMaps];   // bf16 activation views [.., Cin], box {64, kbw, kbh, 1}
+  Tap taps[kMaxTaps];           // same tap table as the forward conv (bk = dW column)
+  int num_taps;
+  int ktiles_w, ktiles_h;       // K tiles (64 pixels each) per image
+  int kbw, kbh;                 // kbw * kbh == 64
+  int num_images;
+  int cin, cout;
+  float* dw;                    // fp32 [cout][ldw], column = tap.bk + ci
+  long long ldw;
+};
+
+void launch_wgrad_gemm(const WgradParams& p, int block_n, int ksplit, cudaStream_t stream);
+
+}  // namespace b2

@@ -1,0 +1,440 @@
+"""Per-network executor of the native backend: owns the activation / gradient
+buffers of one network for a fixed batch and emits its forward / backward kernel
+launches into a ``_C.Plan``.
+
+Layouts (all bf16 NHWC):
+  * the input of a reflection-padded conv is stored already padded (the
+    producing kernel writes the mirrored halo), so those convs are "valid";
+  * TF-SAME zero padding is TMA out-of-bounds fill (negative / past-the-end
+    coordinates), stride-2 convs read four parity views of the plain tensor;
+  * transposed convs are four sub-pixel phase GEMMs writing an interleaved output;
+  * dgrad of a reflection-padded conv runs in the zero-ringed "flat" domain
+    (taps are constant row offsets) and the halo is folded back by the
+    InstanceNorm-backward pass of the layer below;
+  * 3-channel tensors use 8-channel pixels; their convs take one GEMM tap per
+    kernel row over an overlapping 8-pixel window (16-byte TMA stride).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from ..models.spec import ConvLayer, NetSpec
+from ..ops import native as nv
+from ..ops import oracle as O
+from ..ops.native import ACT, NULL_VIEW, Buf
+from . import native_ops as no
+from .native_params import FlatLayout, is_small_cin
+
+IN_EPS = O.IN_EPS
+
+
+class NetState:
+  """Flat parameter / optimizer / gradient buffers of one network."""
+
+  def __init__(self, spec: NetSpec, logical: Dict[str, torch.Tensor], device,
+               grad_buffer: Optional[torch.Tensor] = None,
+               wb_buffer: Optional[torch.Tensor] = None):
+    self.spec = spec
+    self.layout = FlatLayout(spec)
+    n = self.layout.numel
+    self.n = n
+    self.w = self.layout.pack(logical).to(device)
+    self.m = torch.zeros(n, device=device)
+    self.v = torch.zeros(n, device=device)
+    self.g = grad_buffer if grad_buffer is not None else torch.zeros(n, device=device)
+    self.wb = wb_buffer if wb_buffer is not None else torch.zeros(n, device=device, dtype=torch.bfloat16)
+    self.wb.copy_(self.w.to(torch.bfloat16))
+    self.mask = self.layout.mask().to(device)
+    self.step = torch.zeros(1, dtype=torch.int32, device=device)
+    self.derived: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}   # name -> (bf16 dst, int32 idx)
+
+  def seg(self, l: ConvLayer, what: str):
+    return self.layout.seg(l, what)
+
+  def kernel_bf16(self, l: ConvLayer) -> torch.Tensor:
+    s = self.seg(l, "kernel")
+    return self.wb[s.offset:s.offset + s.numel].view(*s.shape)
+
+  def wptr(self, l: ConvLayer, what: str) -> int:
+    return self.w.data_ptr() + 4 * self.seg(l, what).offset
+
+  def gptr(self, l: ConvLayer, what: str) -> int:
+    return self.g.data_ptr() + 4 * self.seg(l, what).offset
+
+  def add_derived(self, name: str, idx: torch.Tensor) -> torch.Tensor:
+    """bf16 matrix gathered from the master weights through ``idx`` (-1 = zero)."""
+    idx32 = idx.to(torch.int32).contiguous().to(self.w.device)
+    dst = torch.zeros(idx.shape, dtype=torch.bfloat16, device=self.w.device)
+    self.derived[name] = (dst, idx32)
+    return dst
+
+  def refresh_derived_ops(self, plan, tag: str):
+    for name, (dst, idx) in self.derived.items():
+      plan.add_gather_bf16(f"{tag}.gather.{name}", dst.data_ptr(), self.w.data_ptr(), idx.data_ptr(),
+                           idx.numel())
+
+  def refresh_derived_now(self):
+    for dst, idx in self.derived.values():
+      src = torch.cat([self.w, self.w.new_zeros(1)])
+      dst.copy_(src[idx.long().clamp_min(-1)].to(torch.bfloat16).view_as(dst))
+
+
+def _out_hw(l: ConvLayer, h: int, w: int) -> Tuple[int, int]:
+  return l.out_hw(h, w)
+
+
+class NetExec:
+  """Buffers + op emission for ``nb`` images of one network at resolution ``size``."""
+
+  def __init__(self, spec: NetSpec, state: NetState, nb: int, size: int, device, tag: str):
+    self.spec, self.st, self.nb, self.size, self.tag = spec, state, nb, size, tag
+    self.layers = list(spec.layers)
+    L = len(self.layers)
+    dev = device
+    # resolution of every layer input / output
+    self.in_hw: List[Tuple[int, int]] = []
+    h = w = size
+    for l in self.layers:
+      self.in_hw.append((h, w))
+      h, w = _out_hw(l, h, w)
+    self.out_hw = [(_out_hw(l, *hw)) for l, hw in zip(self.layers, self.in_hw)]
+
+    def cpad(c):  # channel storage (3 -> 8)
+      return 8 if c < 8 else c
+
+    # ---- forward activations: inp[j] feeds layer j; inp[L] is the network output
+    self.inp: List[Buf] = []
+    for j, l in enumerate(self.layers):
+      hh, ww = self.in_hw[j]
+      halo = l.k // 2 if l.pad == "reflect" else (1 if is_small_cin(l) and l.pad == "same" else 0)
+      slack = 1 if is_small_cin(l) else 0
+      self.inp.append(Buf(nb, hh, ww, cpad(l.cin), halo=halo, device=dev, slack_rows=slack))
+    ho, wo = self.out_hw[-1]
+    self.inp.append(Buf(nb, ho, wo, cpad(self.layers[-1].cout), device=dev))
+    self.raw: List[Optional[Buf]] = []
+    self.stats: List[Optional[torch.Tensor]] = []
+    self.bstats: List[Optional[torch.Tensor]] = []
+    stat_sizes = [nb * l.cout * 2 if l.norm else 0 for l in self.layers]
+    self.stat_arena = torch.zeros(2 * sum(stat_sizes) + 8, device=dev)
+    off = 0
+    for j, l in enumerate(self.layers):
+      ho, wo = self.out_hw[j]
+      if l.norm:
+        self.raw.append(Buf(nb, ho, wo, l.cout, device=dev))
+        self.stats.append(self.stat_arena[off:off + stat_sizes[j]].view(nb, l.cout, 2))
+        off += stat_sizes[j]
+        self.bstats.append(self.stat_arena[off:off + stat_sizes[j]].view(nb, l.cout, 2))
+        off += stat_sizes[j]
+      else:
+        self.raw.append(None)
+        self.stats.append(None)
+        self.bstats.append(None)
+
+    # ---- backward buffers (allocated lazily by enable_backward)
+    self.dY: List[Optional[Buf]] = [None] * L      # grad wrt conv output (zero ring for flat dgrad)
+    self.dyt: List[Optional[Buf]] = [None] * L     # g * act' scratch (doubles as the residual-sum gradient)
+    self.gin: List[Optional[Buf]] = [None] * L     # grad wrt layer input, as produced by the layer's dgrad
+    self.gout_final: Optional[Buf] = None          # grad wrt the network output (images / logits)
+    self._bwd = False
+    self._special_weights()
+
+  # --------------------------------------------------------------- weights
+  def _special_weights(self):
+    """Derived weight matrices for the small-channel layers' dgrad."""
+    st = self.st
+    self.w_dgrad: Dict[int, torch.Tensor] = {}
+    for j, l in enumerate(self.layers):
+      if l.kind == "conv" and l.cout < 8 and l.cout > 1:
+        # generator final conv (Cout = 3): dgrad B (K-major) Wfd[ci][r*64 + jj*8 + co] = K[r][k-1-jj][ci][co]
+        idx_tf = st.layout.index_tensor(l)                       # [k, k, cin, cout]
+        d = torch.full((l.cin, l.k, 8, 8), -1, dtype=torch.int64)
+        for jj in range(l.k):
+          d[:, :, jj, :l.cout] = idx_tf[:, l.k - 1 - jj, :, :].permute(1, 0, 2)
+        self.w_dgrad[j] = st.add_derived(f"{self.tag}.L{j}.dgradW", d.reshape(l.cin, l.k * 64))
+      elif is_small_cin(l) and l.stride == 2:
+        # PatchGAN conv0 (Cin = 3): dgrad B (K-major) W[c(16)][(r*k+s)*cout + co] = K[r][s][c][co]
+        idx_tf = st.layout.index_tensor(l)                       # [k, k, cin, cout]
+        d = torch.full((16, l.k * l.k * l.cout), -1, dtype=torch.int64)
+        d[:l.cin] = idx_tf.permute(2, 0, 1, 3).reshape(l.cin, -1)
+        self.w_dgrad[j] = st.add_derived(f"{self.tag}.L{j}.dgradW", d)
+    st.refresh_derived_now()
+
+  def enable_backward(self):
+    if self._bwd:
+      return
+    self._bwd = True
+    dev = self.inp[0].t.device
+    nb = self.nb
+    L = len(self.layers)
+    for j, l in enumerate(self.layers):
+      ho, wo = self.out_hw[j]
+      hi, wi = self.in_hw[j]
+      c_out = 8 if l.cout < 8 else l.cout
+      flat_dgrad = l.kind == "conv" and l.pad == "reflect" and not is_small_cin(l)
+      halo = l.k // 2 if flat_dgrad else 0
+      self.dY[j] = Buf(nb, ho, wo, c_out, halo=halo, device=dev, slack_rows=1 if c_out == 8 else 0)
+      if l.norm:
+        self.dyt[j] = Buf(nb, ho, wo, l.cout, device=dev)
+      if j > 0 or True:
+        c_in = 8 if l.cin < 8 else l.cin
+        self.gin[j] = Buf(nb, hi, wi, c_in, halo=halo, device=dev) if not is_small_cin(l) else None
+    ho, wo = self.out_hw[-1]
+    self.gout_final = Buf(nb, ho, wo, self.inp[-1].c, device=dev)
+    # scratch for the swapped wgrad of small-Cout reflect convs (generator final layer)
+    self.wgrad_scratch: Dict[int, torch.Tensor] = {}
+    for j, l in enumerate(self.layers):
+      if j in self.w_dgrad and not is_small_cin(l):
+        self.wgrad_scratch[j] = torch.zeros(128, l.k * 64, device=dev)
+
+  # --------------------------------------------------------------- helpers
+  def _small_cin_maps(self, j: int, n0: int, nimg: int, bw: int, bh: int):
+    """Overlapping-window A views + taps of a 3-channel-input conv (8-channel pixels)."""
+    l = self.layers[j]
+    src = self.inp[j]
+    ho, wo = self.out_hw[j]
+    if l.stride == 1:
+      maps = [nv.tmap(src.ptr(n0, padded=True), [64, wo, src.hp, nimg], [8, src.sh, src.sn],
+                      [64, bw, bh, 1])]
+      taps = [(0, 0, 0, r, r * 64) for r in range(l.k)]
+    else:
+      maps = []
+      for a in (0, 1):
+        nrows = (src.hp - a + 1) // 2
+        maps.append(nv.tmap(src.ptr(n0, padded=True) + 2 * a * src.sh, [64, wo, nrows, nimg],
+                            [16, 2 * src.sh, src.sn], [64, bw, bh, 1]))
+      taps = [(r % 2, 0, 0, r // 2, r * 64) for r in range(l.k)]
+    return maps, taps
+
+  def _pad_before(self, j: int) -> int:
+    l = self.layers[j]
+    hi, _ = self.in_hw[j]
+    if l.kind == "convT":
+      return 0
+    return O.same_pad_amounts(hi, l.k, l.stride)[0]
+
+  # --------------------------------------------------------------- forward
+  def forward(self, plan, n0: int, nimg: int, first: int = 0):
+    """Emit the forward pass for images [n0, n0 + nimg)."""
+    st = self.st
+    L = len(self.layers)
+    for j in range(first, L):
+      l = self.layers[j]
+      src = self.inp[j]
+      hi, wi = self.in_hw[j]
+      ho, wo = self.out_hw[j]
+      dst = self.raw[j] if l.norm else self.inp[j + 1]
+      name = f"{self.tag}.{l.name}.fwd[{n0}:{n0 + nimg}]"
+      bias = st.wptr(l, "bias") if l.bias else 0
+      act = 0 if l.norm else ACT[l.act]
+      stats = self.stats[j][n0:].data_ptr() if l.norm else 0
+      w2 = st.kernel_bf16(l)
+      if l.kind == "convT":
+        bw, bh = nv.tile_shape(hi, wi)
+        amap = src.tmap_interior(bw, bh, n0, nimg)
+        for a in (0, 1):
+          for b in (0, 1):
+            view = (dst.ptr(n0, a, b), dst.sn, 2 * dst.sh, 2 * dst.sw)
+            no.add_conv(plan, f"{name}.p{a}{b}", [amap], no.taps_convT_phase(a, b, l.cin), l.cin, w2,
+                        view, hi, wi, nimg, l.cout, bias, act, stats)
+      else:
+        bw, bh = nv.tile_shape(ho, wo)
+        if is_small_cin(l):
+          maps, taps = self._small_cin_maps(j, n0, nimg, bw, bh)
+          kch = 64
+        elif l.pad == "reflect":
+          maps, taps, kch = [src.tmap_padded(bw, bh, n0, nimg)], no.taps_conv(l.k, l.cin), l.cin
+        elif l.stride == 2:
+          maps = [src.tmap_parity(a, b, bw, bh, n0, nimg) for a in (0, 1) for b in (0, 1)]
+          taps, kch = no.taps_conv_s2(l.k, l.cin, self._pad_before(j)), l.cin
+        else:
+          maps = [src.tmap_interior(bw, bh, n0, nimg)]
+          taps, kch = no.taps_conv(l.k, l.cin, origin=-self._pad_before(j)), l.cin
+        no.add_conv(plan, name, maps, taps, kch, w2, dst.view(n0), ho, wo, nimg, l.cout, bias, act, stats)
+      if l.norm:
+        nxt = self.inp[j + 1]
+        skip = self.inp[j - 1].view(n0) if l.res == "b" else NULL_VIEW
+        plan.add_in_apply(f"{self.tag}.{l.name}.in_apply[{n0}:{n0 + nimg}]", self.raw[j].view(n0),
+                          stats, st.wptr(l, "gamma"), st.wptr(l, "beta"), 1.0 / (ho * wo), IN_EPS,
+                          ACT[l.act], skip, nxt.view(n0), nxt.halo, nimg, ho, wo, l.cout)
+
+  # -------------------------------------------------------------- backward
+  def backward(self, plan, n0: int, nimg: int, wgrad: bool, stop_layer: int = 0,
+               input_grad_target: Optional[Tuple[Buf, int]] = None,
+               gout_view=None, gout_is_dy: bool = False):
+    """Emit the backward pass for images [n0, n0 + nimg).
+
+    ``gout_view``: view of the gradient wrt the network output (default: self.gout_final).
+    ``gout_is_dy``: the output layer is linear (PatchGAN logits) so gout is already dY.
+    ``wgrad``: accumulate parameter gradients into the flat fp32 gradient buffer.
+    ``input_grad_target``: (Buf, image offset) receiving the gradient wrt the input image
+    (only for the adversarial pass through a discriminator); otherwise the first layer
+    has no dgrad. Layers below ``stop_layer`` are skipped entirely."""
+    self.enable_backward()
+    st = self.st
+    L = len(self.layers)
+    g1 = (gout_view if gout_view is not None else self.gout_final.view(n0), 0)
+    g2 = NULL_VIEW
+    pending_skip = None
+    for j in range(L - 1, stop_layer - 1, -1):
+      l = self.layers[j]
+      hi, wi = self.in_hw[j]
+      ho, wo = self.out_hw[j]
+      tagj = f"{self.tag}.{l.name}"
+      rng = f"[{n0}:{n0 + nimg}]"
+      dY = self.dY[j]
+      last = (j == L - 1)
+      # ---- 1. gradient wrt the conv output
+      if l.norm:
+        dyt = self.dyt[j]
+        plan.add_in_bwd_reduce(f"{tagj}.in_bwd_reduce{rng}", g1[0], g1[1], g2, self.raw[j].view(n0),
+                               self.stats[j][n0:].data_ptr(), st.wptr(l, "gamma"), st.wptr(l, "beta"),
+                               1.0 / (ho * wo), IN_EPS, ACT[l.act], dyt.view(n0),
+                               self.bstats[j][n0:].data_ptr(), nimg, ho, wo, l.cout)
+        plan.add_in_bwd_apply(f"{tagj}.in_bwd_apply{rng}", dyt.view(n0), self.raw[j].view(n0),
+                              self.stats[j][n0:].data_ptr(), self.bstats[j][n0:].data_ptr(),
+                              st.wptr(l, "gamma"), 1.0 / (ho * wo), IN_EPS, dY.view(n0),
+                              st.gptr(l, "gamma") if wgrad else 0, st.gptr(l, "beta") if wgrad else 0,
+                              nimg, ho, wo, l.cout)
+        if l.res == "b":
+          pending_skip = dyt.view(n0)   # == gradient wrt the block output (IN-b has no activation)
+      elif last and gout_is_dy:
+        dY_view_override = g1[0]
+      else:
+        plan.add_act_bwd(f"{tagj}.act_bwd{rng}", g1[0], g1[1], g2, self.inp[j + 1].view(n0),
+                         ACT[l.act], dY.view(n0), st.gptr(l, "bias") if (wgrad and l.bias) else 0,
+                         l.cout, nimg, ho, wo, dY.c)
+      g2 = NULL_VIEW
+      need_dgrad = j > stop_layer or (j == 0 and input_grad_target is not None)
+      if j == 0 and input_grad_target is None:
+        need_dgrad = False
+
+      # ---- PatchGAN logits layer (Cout = 1): GEMV-shaped SIMT kernels
+      if l.cout == 1:
+        gd = dY_view_override if (last and gout_is_dy) else dY.view(n0)
+        gin = self.gin[j]
+        w_row0 = st.kernel_bf16(l).data_ptr()
+        plan.add_d4_bwd(f"{tagj}.bwd{rng}", gd, self.inp[j].view(n0), w_row0,
+                        gin.view(n0) if need_dgrad else NULL_VIEW,
+                        st.gptr(l, "kernel") if wgrad else 0, st.gptr(l, "bias") if (wgrad and l.bias) else 0,
+                        self._pad_before(j), nimg, hi, wi, l.cin, bool(need_dgrad), bool(wgrad))
+        g1 = (gin.view(n0), 0)
+        continue
+
+      # ---- 2. wgrad
+      if wgrad:
+        self._wgrad(plan, j, n0, nimg, f"{tagj}.wgrad{rng}")
+      # ---- 3. dgrad
+      if need_dgrad:
+        g1 = self._dgrad(plan, j, n0, nimg, f"{tagj}.dgrad{rng}", input_grad_target if j == 0 else None)
+        if l.res == "a" and pending_skip is not None:
+          g2 = pending_skip
+          pending_skip = None
+
+  def _wgrad(self, plan, j: int, n0: int, nimg: int, name: str):
+    l = self.layers[j]
+    st = self.st
+    hi, wi = self.in_hw[j]
+    ho, wo = self.out_hw[j]
+    dY, src = self.dY[j], self.inp[j]
+    seg = st.seg(l, "kernel")
+    dw, ldw = st.gptr(l, "kernel"), seg.shape[1]
+    if l.kind == "convT":
+      kbw, kbh = nv.tile_shape(hi, wi, 64)
+      amap = src.tmap_interior(kbw, kbh, n0, nimg)
+      for a in (0, 1):
+        for b in (0, 1):
+          no.add_wgrad(plan, f"{name}.p{a}{b}", dY.tmap_parity(a, b, kbw, kbh, n0, nimg), [amap],
+                       no.taps_convT_phase(a, b, l.cin), wi // kbw, hi // kbh, kbw, kbh, nimg, l.cin,
+                       l.cout, dw, ldw)
+      return
+    if j in self.w_dgrad and not is_small_cin(l):
+      # small-Cout reflect conv (generator final layer): swapped operands in the flat domain.
+      #   dWT[ci][r*64 + jj*8 + co] = sum_u a_pad[u][ci] * dYz[u + (p - r) * P - p + jj][co]
+      P = src.wp
+      p = l.k // 2
+      rows = nimg * src.hp * src.wp
+      m_map = src.tmap_flat(n0, nimg, rows_box=64)
+      b_map = nv.tmap(dY.ptr(n0, padded=True), [64, rows, 1, 1], [8, rows * 8, rows * 8], [64, 64, 1, 1])
+      taps = [(0, 0, (p - r) * P - p, 0, r * 64) for r in range(l.k)]
+      scratch = self.wgrad_scratch[j]
+      plan.add_memset(f"{name}.zero", scratch.data_ptr(), scratch.numel() * 4)
+      no.add_wgrad(plan, name, m_map, [b_map], taps, (rows + 63) // 64, 1, 64, 1, 1, 64, l.cin,
+                   scratch.data_ptr(), scratch.shape[1])
+      _, idx = st.derived[f"{self.tag}.L{j}.dgradW"]
+      plan.add_scatter_add(f"{name}.scatter", st.g.data_ptr(), scratch.data_ptr(), idx.data_ptr(), idx.numel())
+      return
+    kbw, kbh = nv.tile_shape(ho, wo, 64)
+    dy_map = dY.tmap_interior(kbw, kbh, n0, nimg)
+    if is_small_cin(l):
+      maps, taps = self._small_cin_maps(j, n0, nimg, kbw, kbh)
+      cin = 64
+    elif l.pad == "reflect":
+      maps, taps, cin = [src.tmap_padded(kbw, kbh, n0, nimg)], no.taps_conv(l.k, l.cin), l.cin
+    elif l.stride == 2:
+      maps = [src.tmap_parity(a, b, kbw, kbh, n0, nimg) for a in (0, 1) for b in (0, 1)]
+      taps, cin = no.taps_conv_s2(l.k, l.cin, self._pad_before(j)), l.cin
+    else:
+      maps = [src.tmap_interior(kbw, kbh, n0, nimg)]
+      taps, cin = no.taps_conv(l.k, l.cin, origin=-self._pad_before(j)), l.cin
+    no.add_wgrad(plan, name, dy_map, maps, taps, wo // kbw, ho // kbh, kbw, kbh, nimg, cin, l.cout,
+                 dw, ldw)
+
+  def _dgrad(self, plan, j: int, n0: int, nimg: int, name: str, input_target):
+    """Returns (view, fold) of the gradient wrt the layer input."""
+    l = self.layers[j]
+    st = self.st
+    hi, wi = self.in_hw[j]
+    ho, wo = self.out_hw[j]
+    dY = self.dY[j]
+    w2 = st.kernel_bf16(l)
+    if l.kind == "convT":
+      gin = self.gin[j]
+      bw, bh = nv.tile_shape(hi, wi)
+      maps = [dY.tmap_parity(a, b, bw, bh, n0, nimg) for a in (0, 1) for b in (0, 1)]
+      no.add_conv(plan, name, maps, no.taps_conv_s2(l.k, l.cin, 0), l.cout, w2, gin.view(n0), hi, wi,
+                  nimg, l.cin, b_mn=True)
+      return (gin.view(n0), 0)
+    if l.pad == "reflect":
+      gin = self.gin[j]
+      p = l.k // 2
+      P = dY.wp
+      rows = nimg * dY.hp * dY.wp
+      if l.cout < 8:
+        amap = nv.tmap(dY.ptr(n0, padded=True), [64, rows, 1, 1], [8, rows * 8, rows * 8], [64, 128, 1, 1])
+        taps = [(0, 0, (p - r) * P - p, 0, r * 64) for r in range(l.k)]
+        no.add_conv_flat(plan, name, amap, taps, 64, self.w_dgrad[j], gin.ptr(n0, padded=True), l.cin,
+                         rows, l.cin, b_mn=False)
+      else:
+        taps = [(0, 0, (p - r) * P + (p - s), 0, (r * l.k + s) * l.cin)
+                for r in range(l.k) for s in range(l.k)]
+        no.add_conv_flat(plan, name, dY.tmap_flat(n0, nimg), taps, l.cout, w2, gin.ptr(n0, padded=True),
+                         l.cin, rows, l.cin, b_mn=True)
+      return (gin.view(n0), p)
+    pb = self._pad_before(j)
+    if l.stride == 2:
+      bw, bh = nv.tile_shape(ho, wo)
+      amap = dY.tmap_interior(bw, bh, n0, nimg)
+      if is_small_cin(l):
+        tgt, t0 = input_target
+        for a in (0, 1):
+          for b in (0, 1):
+            view = (tgt.ptr(t0, a, b), tgt.sn, 2 * tgt.sh, 2 * tgt.sw)
+            no.add_conv(plan, f"{name}.p{a}{b}", [amap], no.taps_convT_phase(a, b, l.cout, l.k, pb),
+                        l.cout, self.w_dgrad[j], view, ho, wo, nimg, l.cin, b_mn=False)
+        return (tgt.view(t0), 0)
+      gin = self.gin[j]
+      for a in (0, 1):
+        for b in (0, 1):
+          view = (gin.ptr(n0, a, b), gin.sn, 2 * gin.sh, 2 * gin.sw)
+          no.add_conv(plan, f"{name}.p{a}{b}", [amap], no.taps_convT_phase(a, b, l.cin, l.k, pb),
+                      l.cout, w2, view, ho, wo, nimg, l.cin, b_mn=True)
+      return (gin.view(n0), 0)
+    # stride-1 TF-SAME conv: dX[q] = sum dY[q + pb - (r, s)] W[r, s]
+    gin = self.gin[j]
+    bw, bh = nv.tile_shape(hi, wi)
+    taps = [(0, 0, pb - s, pb - r, (r * l.k + s) * l.cin) for r in range(l.k) for s in range(l.k)]
+    no.add_conv(plan, name, [dY.tmap_interior(bw, bh, n0, nimg)], taps, l.cout, w2, gin.view(n0), hi, wi,
+                nimg, l.cin, b_mn=True)
+    return (gin.view(n0), 0)

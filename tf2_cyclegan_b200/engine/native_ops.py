@@ -1,0 +1,123 @@
+"""Plan-op builders: translate one layer (conv / dgrad / wgrad / norm) into
+native kernel launches appended to a ``_C.Plan``.
+
+GEMM weight layout (shared by forward, dgrad (MN-major B) and wgrad output):
+``W2[cout_pad][tap * cin + ci]`` with ``tap = r * k + s``; from the TF layouts
+    Conv2D kernel [r, s, ci, co]           → permute(3, 0, 1, 2)
+    Conv2DTranspose kernel [r, s, co, ci]  → permute(2, 0, 1, 3)
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from ..ops import native as nv
+from ..ops.native import ACT, NULL_VIEW, Buf
+
+Tap = Tuple[int, int, int, int, int]   # (a-map index, dn, dw, dh, B column)
+
+
+def pack_conv_weight(kernel_tf: torch.Tensor, transpose_conv: bool = False,
+                     rows: Optional[int] = None) -> torch.Tensor:
+  """TF kernel → fp32 W2[rows >= cout][k*k*cin] (extra rows are zero)."""
+  if transpose_conv:
+    w2 = kernel_tf.permute(2, 0, 1, 3)
+  else:
+    w2 = kernel_tf.permute(3, 0, 1, 2)
+  cout = w2.shape[0]
+  w2 = w2.reshape(cout, -1).contiguous()
+  rows = max(cout, 16) if rows is None else rows
+  if rows > cout:
+    w2 = torch.cat([w2, w2.new_zeros(rows - cout, w2.shape[1])], 0)
+  return w2
+
+
+def unpack_conv_weight(w2: torch.Tensor, k: int, cin: int, cout: int,
+                       transpose_conv: bool = False) -> torch.Tensor:
+  w = w2[:cout].reshape(cout, k, k, cin)
+  return w.permute(1, 2, 0, 3).contiguous() if transpose_conv else w.permute(1, 2, 3, 0).contiguous()
+
+
+# --------------------------------------------------------------- tap tables
+def taps_conv(k: int, cin: int, origin: int = 0) -> List[Tap]:
+  """Stride-1 conv reading input pixel (oh + r + origin, ow + s + origin)."""
+  return [(0, 0, s + origin, r + origin, (r * k + s) * cin) for r in range(k) for s in range(k)]
+
+
+def taps_conv_s2(k: int, cin: int, pad_before: int) -> List[Tap]:
+  """Stride-2 conv over 4 parity views: input index 2*o + r - pad_before."""
+  taps = []
+  for r in range(k):
+    for s in range(k):
+      ir, ic = r - pad_before, s - pad_before
+      a, b = ir % 2, ic % 2
+      taps.append((a * 2 + b, 0, (ic - b) // 2, (ir - a) // 2, (r * k + s) * cin))
+  return taps
+
+
+def taps_convT_phase(a: int, b: int, cin: int, k: int = 3, pad_before: int = 0) -> List[Tap]:
+  """Transposed conv (stride 2) phase (a, b): out[2m+a, 2n+b] = sum x[m - dy, n - dx] K[ky, kx]
+  over taps with (ky - pad_before) ≡ a, (kx - pad_before) ≡ b (mod 2)."""
+  taps = []
+  for ky in range(k):
+    if (ky - pad_before - a) % 2:
+      continue
+    dy = (ky - pad_before - a) // 2
+    for kx in range(k):
+      if (kx - pad_before - b) % 2:
+        continue
+      dx = (kx - pad_before - b) // 2
+      taps.append((0, 0, -dx, -dy, (ky * k + kx) * cin))
+  return taps
+
+
+# ------------------------------------------------------------- op builders
+def add_conv(plan, name: str, a_maps: Sequence[bytes], taps: Sequence[Tap], k_channels: int,
+             w2_bf16: torch.Tensor, out_view, out_h: int, out_w: int, nimg: int, n_channels: int,
+             bias: int = 0, act: int = 0, stats: int = 0, b_mn: bool = False,
+             block_n: Optional[int] = None, tile: Optional[Tuple[int, int]] = None,
+             w_limit: Optional[int] = None):
+  """Box-mode implicit GEMM: out[n, h, w, :n_channels] over an out_h x out_w grid.
+
+  k_channels: channels of the A views (K per tap); n_channels: valid output channels."""
+  block_n = block_n or nv.pick_block_n(n_channels)
+  if b_mn:
+    block_n = max(block_n, 64)
+  bw, bh = tile or nv.tile_shape(out_h, out_w)
+  ptr, sn, sh, sw = out_view
+  return plan.add_conv_gemm(name, list(a_maps), nv.wmat_tmap(w2_bf16, block_n, b_mn),
+                            list(taps), k_channels // 64, out_w // bw, out_h // bh, bw, bh,
+                            out_w if w_limit is None else w_limit, ptr, sn, sh, sw, n_channels,
+                            bias, act, stats, block_n, b_mn, nimg)
+
+
+def add_conv_flat(plan, name: str, a_map: bytes, taps: Sequence[Tap], k_channels: int,
+                  w2_bf16: torch.Tensor, out_ptr: int, out_row_stride: int, rows: int,
+                  n_channels: int, b_mn: bool = False, block_n: Optional[int] = None):
+  """Flat-mode implicit GEMM over ``rows`` consecutive pixels of a zero-ringed domain
+  (taps are constant row offsets): out[row, :n_channels]."""
+  block_n = block_n or nv.pick_block_n(n_channels)
+  if b_mn:
+    block_n = max(block_n, 64)
+  tiles = (rows + 127) // 128
+  return plan.add_conv_gemm(name, [a_map], nv.wmat_tmap(w2_bf16, block_n, b_mn), list(taps),
+                            k_channels // 64, tiles, 1, 128, 1, rows, out_ptr, 0, 0,
+                            out_row_stride, n_channels, 0, 0, 0, block_n, b_mn, 1)
+
+
+def add_wgrad(plan, name: str, dy_map: bytes, a_maps: Sequence[bytes], taps: Sequence[Tap],
+              kt_w: int, kt_h: int, kbw: int, kbh: int, nimg: int, cin: int, cout: int,
+              dw_ptr: int, ldw: int, block_n: Optional[int] = None, target_ctas: int = 296):
+  block_n = block_n or max(64, nv.pick_block_n(cin))
+  m_tiles = (cout + 127) // 128
+  n_tiles = (cin + block_n - 1) // block_n
+  base = m_tiles * n_tiles * len(taps)
+  total_kt = kt_w * kt_h * nimg
+  ksplit = max(1, min(total_kt, (target_ctas + base - 1) // base))
+  return plan.add_wgrad(name, dy_map, list(a_maps), list(taps), kt_w, kt_h, kbw, kbh, nimg,
+                        cin, cout, dw_ptr, ldw, block_n, ksplit)
+
+
+def fptr(t: Optional[torch.Tensor]) -> int:
+  return 0 if t is None else t.data_ptr()
