@@ -1,0 +1,103 @@
+"""CPU stand-in for the native extension: records plan ops and validates every
+TMA descriptor / launch geometry the planner produces, so the (GPU-only)
+planning logic is exercised on the GPU-less pod."""
+from __future__ import annotations
+
+import struct
+
+
+class FakePlan:
+
+  def __init__(self):
+    self.ops = []
+
+  def size(self):
+    return len(self.ops)
+
+  def names(self):
+    return [o[1] for o in self.ops]
+
+  def run(self, *a, **k):
+    raise RuntimeError("fake plan cannot run")
+
+  def _add(self, kind, name, *args):
+    self.ops.append((kind, name, args))
+    return len(self.ops) - 1
+
+  def add_conv_gemm(self, name, a_maps, b_map, taps, cin_blocks, tiles_w, tiles_h, bw, bh, w_limit,
+                    out, sn, sh, sw, cout, bias, act, stats, block_n, b_mn, num_images):
+    assert bw * bh == 128 and 1 <= len(a_maps) <= 4 and 1 <= len(taps) <= 52
+    assert cin_blocks >= 1 and tiles_w >= 1 and tiles_h >= 1 and num_images >= 1
+    assert block_n in (16, 64, 128, 256) and (not b_mn or block_n >= 64)
+    for t in taps:
+      assert 0 <= t[0] < len(a_maps)
+    for m in a_maps:
+      d = decode(m)
+      assert d["box"][:3] == [64, bw, bh], (name, d["box"], bw, bh)
+    bd = decode(b_map)
+    assert bd["box"] == ([64, 64] if b_mn else [64, block_n]), (name, bd["box"])
+    if not b_mn:
+      assert bd["dims"][1] >= min(cout, block_n), (name, bd["dims"], cout)
+      for t in taps:
+        assert t[4] + cin_blocks * 64 <= bd["dims"][0], (name, t, bd["dims"])
+    else:
+      assert bd["dims"][1] >= cin_blocks * 64
+      for t in taps:
+        assert t[4] + cout <= bd["dims"][0] + 63, (name, t, bd["dims"], cout)
+    assert out % 16 == 0 or cout < 8
+    return self._add("conv_gemm", name, len(taps), cout, block_n, b_mn, num_images)
+
+  def add_wgrad(self, name, dy_map, a_maps, taps, ktw, kth, kbw, kbh, nimg, cin, cout, dw, ldw, block_n, ksplit):
+    assert kbw * kbh == 64 and ksplit >= 1 and block_n in (64, 128, 256)
+    assert decode(dy_map)["box"][:3] == [64, kbw, kbh]
+    for m in a_maps:
+      assert decode(m)["box"][:3] == [64, kbw, kbh]
+    for t in taps:
+      assert t[4] + cin <= ldw, (name, t, cin, ldw)
+    assert dw % 16 == 0 and ldw % 4 == 0
+    return self._add("wgrad", name, len(taps), cin, cout)
+
+  def __getattr__(self, item):
+    if item.startswith("add_"):
+      def f(name, *args):
+        return self._add(item[4:], name, *args)
+      return f
+    raise AttributeError(item)
+
+
+_MAPS = {}
+
+
+def decode(b: bytes):
+  return _MAPS[b]
+
+
+class FakeModule:
+  MAX_TAPS = 52
+  Plan = FakePlan
+  _counter = 0
+
+  @staticmethod
+  def encode_tmap(ptr, dtype, dims, strides_bytes, box, swizzle=3):
+    rank = len(dims)
+    assert 1 <= rank <= 5 and len(box) == rank and len(strides_bytes) == rank - 1
+    assert ptr % 16 == 0, "TMA base must be 16-byte aligned"
+    for s in strides_bytes:
+      assert s % 16 == 0 and 0 < s < (1 << 40), f"bad stride {s}"
+    for d in dims:
+      assert 1 <= d <= (1 << 32)
+    for b_ in box:
+      assert 1 <= b_ <= 256
+    esz = {0: 2, 1: 4, 2: 1}[dtype]
+    assert box[0] * esz == 128 or swizzle != 3, "SWIZZLE_128B needs a 128-byte inner box"
+    FakeModule._counter += 1
+    key = struct.pack("<Q", FakeModule._counter) + b"\0" * 120
+    _MAPS[key] = {"ptr": ptr, "dims": list(dims), "strides": list(strides_bytes), "box": list(box)}
+    return key
+
+
+def install(monkeypatch):
+  from tf2_cyclegan_b200.ops import native as nv
+  monkeypatch.setattr(nv, "_mod", FakeModule)
+  monkeypatch.setattr(nv, "available", lambda: True)
+  return FakeModule

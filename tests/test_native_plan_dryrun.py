@@ -1,0 +1,59 @@
+"""Dry-run of the native step planner on CPU against a validating fake extension."""
+import pytest
+import torch
+
+from tests import fake_native
+
+
+class A:
+  def __init__(self, nres):
+    self.num_residual_blocks = nres
+
+
+@pytest.mark.parametrize("size,b,nres", [(128, 2, 1), (256, 1, 9)])
+def test_step_plan_builds_and_is_well_formed(monkeypatch, size, b, nres):
+  fake_native.install(monkeypatch)
+  monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+  from tf2_cyclegan_b200.engine.cyclegan import build_specs
+  from tf2_cyclegan_b200.engine.native_backend import NETS, NativeBackend
+  from tf2_cyclegan_b200.parallel.strategy import Strategy
+  st = Strategy(device="cpu")
+  be = NativeBackend(build_specs(A(nres)), b, st, seed=1, image_size=size, local_batch=b)
+  sp = be.plan_for(b)
+  names = sp.names
+  assert sp.marks["cycle_end"] < sp.marks["test_end"] < sp.marks["G_bwd_end"] < sp.marks["end"]
+  # six generator forwards = 2 batched + 2 cycle passes per generator pair
+  assert sum(1 for n in names if n.startswith("G.stem.fwd")) == 2
+  assert sum(1 for n in names if n.startswith("X.conv0.fwd")) == 1      # fakes forwarded once
+  # gradient routing: no dgrad into a stem, adversarial pass has no wgrad
+  assert not any("stem.dgrad" in n for n in names)
+  adv = names[sp.marks["test_end"]:names.index("zero.X.bstats2")]
+  assert adv and not any("wgrad" in n for n in adv) and any("conv0.dgrad" in n for n in adv)
+  for n in NETS:
+    assert f"opt.{n}.adam" in names and f"opt.{n}.step" in names
+  # every conv layer of every network gets exactly one wgrad group in the full backward
+  full = names[names.index("zero.Y.bstats2"):]
+  for l in be.specs["G"].layers:
+    assert any(n.startswith(f"G.{l.name}.wgrad") for n in full), l.name
+  for l in be.specs["X"].layers:
+    assert any(n.startswith(f"X.{l.name}.wgrad") or n.startswith(f"X.{l.name}.bwd") for n in full), l.name
+
+
+def test_flat_layout_roundtrip_and_mask():
+  from tf2_cyclegan_b200.engine.native_params import FlatLayout
+  from tf2_cyclegan_b200.models import oracle_net
+  from tf2_cyclegan_b200.models.spec import discriminator_spec, generator_spec
+  for spec in (generator_spec(num_residual_blocks=1), discriminator_spec()):
+    lay = FlatLayout(spec)
+    params = oracle_net.init_params(spec, torch.Generator().manual_seed(0))
+    flat = lay.pack(params)
+    back = lay.unpack(flat)
+    for k, v in params.items():
+      assert torch.equal(back[k], v), k
+    mask = lay.mask()
+    assert int(mask.sum()) == spec.num_params()
+    assert (flat[mask == 0] == 0).all()
+    # index tensor addresses the same elements
+    l0 = spec.layers[0]
+    idx = lay.index_tensor(l0)
+    assert torch.equal(flat[idx], params[f"layer_with_weights-{l0.lw_index}/kernel"])

@@ -156,7 +156,22 @@ __global__ void gather_bf16_kernel(__nv_bfloat16* dst, const float* src, const i
   }
 }
 
+__global__ void scatter_add_kernel(float* dst, const float* src, const int* idx, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int j = idx[i];
+    if (j >= 0) atomicAdd(dst + j, src[i]);
+  }
+}
+
 }  // namespace
+
+void launch_scatter_add(float* dst, const float* src, const int* idx, long long n, cudaStream_t s) {
+  long long b = (n + 255) / 256;
+  if (b > 148 * 8) b = 148 * 8;
+  if (b < 1) b = 1;
+  scatter_add_kernel<<<static_cast<int>(b), 256, 0, s>>>(dst, src, idx, n);
+}
 
 void launch_allreduce_adam(const AllreduceAdamParams& p, int num_blocks, cudaStream_t s) {
   allreduce_adam_kernel<<<num_blocks, 512, 0, s>>>(p);

@@ -23,6 +23,7 @@ struct AllreduceAdamParams {
 };
 
 void launch_allreduce_adam(const AllreduceAdamParams& p, int num_blocks, cudaStream_t s);
+void launch_scatter_add(float* dst, const float* src, const int* idx, long long n, cudaStream_t s);
 void launch_gather_bf16(__nv_bfloat16* dst, const float* src, const int* idx, long long n,
                         cudaStream_t s);
 

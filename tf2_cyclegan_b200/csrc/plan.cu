@@ -145,6 +145,25 @@ class Plan {
     check(cudaGetLastError(), "plan launch");
   }
 
+  // per-op device time (ms) measured with CUDA events; ops stay back-to-back on the stream
+  std::vector<float> run_timed(int begin, int end, uint64_t stream) {
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (end < 0 || end > size()) end = size();
+    const int n = end - begin;
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& e : ev) check(cudaEventCreate(&e), "cudaEventCreate");
+    check(cudaEventRecord(ev[0], s), "cudaEventRecord");
+    for (int i = 0; i < n; ++i) {
+      ops_[begin + i].fn(s);
+      check(cudaEventRecord(ev[i + 1], s), "cudaEventRecord");
+    }
+    check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
+    std::vector<float> ms(n);
+    for (int i = 0; i < n; ++i) check(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]), "elapsed");
+    for (auto& e : ev) cudaEventDestroy(e);
+    return ms;
+  }
+
   // ------------------------------------------------------------- GEMM ops
   int add_conv_gemm(std::string name, std::vector<py::bytes> a_maps, py::bytes b_map,
                     std::vector<TapT> taps, int cin_blocks, int tiles_w, int tiles_h, int bw,
@@ -255,6 +274,11 @@ class Plan {
       launch_gather_bf16(P<__nv_bfloat16>(dst), P<const float>(src_f32), P<const int>(idx), n, s);
     });
   }
+  int add_scatter_add(std::string name, uint64_t dst, uint64_t src, uint64_t idx, long long n) {
+    return add(std::move(name), [dst, src, idx, n](cudaStream_t s) {
+      launch_scatter_add(P<float>(dst), P<const float>(src), P<const int>(idx), n, s);
+    });
+  }
   int add_memset(std::string name, uint64_t ptr, long long nbytes) {
     return add(std::move(name), [ptr, nbytes](cudaStream_t s) {
       check(cudaMemsetAsync(P<void>(ptr), 0, nbytes, s), "cudaMemsetAsync");
@@ -309,6 +333,8 @@ PYBIND11_MODULE(_C, m) {
       .def("names", &Plan::names)
       .def("run", &Plan::run, py::arg("begin") = 0, py::arg("end") = -1, py::arg("stream") = 0,
            py::arg("check_each") = false, py::call_guard<py::gil_scoped_release>())
+      .def("run_timed", &Plan::run_timed, py::arg("begin") = 0, py::arg("end") = -1,
+           py::arg("stream") = 0)
       .def("add_conv_gemm", &Plan::add_conv_gemm)
       .def("add_wgrad", &Plan::add_wgrad)
       .def("add_in_apply", &Plan::add_in_apply)
@@ -322,6 +348,7 @@ PYBIND11_MODULE(_C, m) {
       .def("add_step_increment", &Plan::add_step_increment)
       .def("add_mask_grad", &Plan::add_mask_grad)
       .def("add_gather_bf16", &Plan::add_gather_bf16)
+      .def("add_scatter_add", &Plan::add_scatter_add)
       .def("add_memset", &Plan::add_memset)
       .def("add_d4_bwd", &Plan::add_d4_bwd)
       .def("add_allreduce_adam", &Plan::add_allreduce_adam);

@@ -45,8 +45,12 @@ class CycleGAN:
     backend = getattr(args, "backend", "auto")
     dtype = getattr(args, "dtype", "fp32")
     seed = int(getattr(args, "seed", 1234))
+    size = int(getattr(args, "image_size", 256))
     if backend == "auto":
-      backend = "native" if strategy.device.type == "cuda" else "oracle"
+      native_ok = strategy.device.type == "cuda" and size >= 128 and size & (size - 1) == 0
+      backend = "native" if native_ok else "oracle"
+    if backend == "oracle" and dtype == "fp8":
+      dtype = "bf16"
     if backend == "native":
       from .native_backend import NativeBackend
       self.backend = NativeBackend(self.specs, self.global_batch_size, strategy, seed=seed,

@@ -1,0 +1,369 @@
+"""Native (sm_100a) backend: the whole CycleGAN train step as one pre-compiled
+Plan of hand-written kernels — no autograd, no cuDNN/cuBLAS, no per-step Python
+on the hot path (CUDA-graph replay).
+
+Schedule (exploits the reference's gradient routing):
+  * each generator holds three image slots: G: [G(x) | G(y) | G(fake_x)],
+    F: [F(y) | F(x) | F(fake_y)]. Slots 0-1 are ONE batched forward, slot 2 a second;
+    the backward (dgrad + InstanceNorm backward + wgrad) is ONE batched pass over 3b
+    images, so the three calls' weight gradients accumulate inside one split-K GEMM;
+  * discriminators see [D(fake) | D(real)] as one batch; the fakes are forwarded once
+    (the reference forwards them twice, main.py:213-214,241-242);
+  * the adversarial term reaches a generator through a dgrad-only pass of the
+    discriminator; no dgrad is ever computed into cycle inputs or past a stem;
+  * all four updates use pre-update weights; G's and F's optimizer steps are
+    issued right after their own backward.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, List, Optional
+
+import torch
+
+from ..models import oracle_net
+from ..models.spec import NetSpec
+from ..ops import native as nv
+from ..ops.native import NULL_VIEW, Buf
+from ..parallel.strategy import Strategy
+from .native_net import NetExec, NetState
+
+NETS = ("G", "F", "X", "Y")
+SLOT = {"G_loss": 0, "G_cycle": 1, "G_identity": 2, "F_loss": 3, "F_cycle": 4, "F_identity": 5,
+        "X_loss": 6, "Y_loss": 7, "err_x_cycle": 8, "err_y_cycle": 9, "err_x_same": 10,
+        "err_y_same": 11}
+NUM_SLOTS = 16
+ADAM = dict(lr=2e-4, b1=0.5, b2=0.9, eps=1e-7)   # main.py:134-145 (+ Keras default epsilon)
+
+
+class StepPlan:
+  """Everything that depends on the local batch size b."""
+
+  def __init__(self, be: "NativeBackend", b: int):
+    C = nv.load()
+    self.b = b
+    dev = be.device
+    S = be.image_size
+    self.x_in = torch.zeros(b, S, S, 3, device=dev)
+    self.y_in = torch.zeros(b, S, S, 3, device=dev)
+    self.slots = torch.zeros(NUM_SLOTS, device=dev)
+    self.ex: Dict[str, NetExec] = {
+        "G": NetExec(be.specs["G"], be.state["G"], 3 * b, S, dev, "G"),
+        "F": NetExec(be.specs["F"], be.state["F"], 3 * b, S, dev, "F"),
+        "X": NetExec(be.specs["X"], be.state["X"], 2 * b, S, dev, "X"),
+        "Y": NetExec(be.specs["Y"], be.state["Y"], 2 * b, S, dev, "Y"),
+    }
+    for e in self.ex.values():
+      e.enable_backward()
+    G, F, X, Y = (self.ex[n] for n in NETS)
+    hd, wd = X.out_hw[-1]
+    self.gd_adv = {"X": Buf(b, hd, wd, 8, device=dev), "Y": Buf(b, hd, wd, 8, device=dev)}
+    gbs = be.global_batch_size
+    plan = C.Plan()
+    self.plan = plan
+    self.marks: Dict[str, int] = {}
+    sl = lambda k: self.slots[SLOT[k]:].data_ptr()
+
+    # ---- P0: zero accumulators
+    plan.add_memset("zero.slots", self.slots.data_ptr(), NUM_SLOTS * 4)
+    for n in NETS:
+      e = self.ex[n]
+      plan.add_memset(f"zero.{n}.stats", e.stat_arena.data_ptr(), e.stat_arena.numel() * 4)
+      plan.add_memset(f"zero.{n}.bstats", e.bstat_arena.data_ptr(), e.bstat_arena.numel() * 4)
+    # ---- P1: inputs -> 8-channel padded bf16 layouts
+    xi, yi = self.x_in.data_ptr(), self.y_in.data_ptr()
+    plan.add_img_prep("prep.x->G0,X1", xi, NULL_VIEW, G.inp[0].view(0), 3, X.inp[0].view(b), b, S, S)
+    plan.add_img_prep("prep.x->F1", xi, NULL_VIEW, F.inp[0].view(b), 3, NULL_VIEW, b, S, S)
+    plan.add_img_prep("prep.y->F0,Y1", yi, NULL_VIEW, F.inp[0].view(0), 3, Y.inp[0].view(b), b, S, S)
+    plan.add_img_prep("prep.y->G1", yi, NULL_VIEW, G.inp[0].view(b), 3, NULL_VIEW, b, S, S)
+    # ---- P2: fake / identity generators (one batched pass each)
+    G.forward(plan, 0, 2 * b)
+    F.forward(plan, 0, 2 * b)
+    # ---- P3: fakes -> inputs of the cycle pass and of the discriminators
+    plan.add_img_prep("prep.fake_y->F2,Y0", 0, G.inp[-1].view(0), F.inp[0].view(2 * b), 3,
+                      Y.inp[0].view(0), b, S, S)
+    plan.add_img_prep("prep.fake_x->G2,X0", 0, F.inp[-1].view(0), G.inp[0].view(2 * b), 3,
+                      X.inp[0].view(0), b, S, S)
+    # ---- P4: cycle pass
+    G.forward(plan, 2 * b, b)
+    F.forward(plan, 2 * b, b)
+    self.marks["cycle_end"] = plan.size()
+    # ---- P5: discriminators on [fake | real]
+    X.forward(plan, 0, 2 * b)
+    Y.forward(plan, 0, 2 * b)
+    # ---- P6: losses (+ their gradients)
+    npx = S * S * 3
+    nd = hd * wd
+    plan.add_mse_loss("loss.G_adv", Y.inp[-1].view(0), 1.0, 1.0 / (nd * gbs), 2.0 / (nd * gbs),
+                      sl("G_loss"), self.gd_adv["Y"].view(0), b, hd, wd)
+    plan.add_mse_loss("loss.F_adv", X.inp[-1].view(0), 1.0, 1.0 / (nd * gbs), 2.0 / (nd * gbs),
+                      sl("F_loss"), self.gd_adv["X"].view(0), b, hd, wd)
+    lc, li = be.lambda_cycle, be.lambda_identity
+    plan.add_l1_loss("loss.G_cycle", G.inp[-1].view(2 * b), yi, lc / (npx * gbs), lc / (npx * gbs),
+                     sl("G_cycle"), sl("err_y_cycle"), 1.0 / (npx * gbs), G.gout_final.view(2 * b), b, S, S)
+    plan.add_l1_loss("loss.G_identity", G.inp[-1].view(b), yi, li / (npx * gbs), li / (npx * gbs),
+                     sl("G_identity"), sl("err_y_same"), 1.0 / (npx * gbs), G.gout_final.view(b), b, S, S)
+    plan.add_l1_loss("loss.F_cycle", F.inp[-1].view(2 * b), xi, lc / (npx * gbs), lc / (npx * gbs),
+                     sl("F_cycle"), sl("err_x_cycle"), 1.0 / (npx * gbs), F.gout_final.view(2 * b), b, S, S)
+    plan.add_l1_loss("loss.F_identity", F.inp[-1].view(b), xi, li / (npx * gbs), li / (npx * gbs),
+                     sl("F_identity"), sl("err_x_same"), 1.0 / (npx * gbs), F.gout_final.view(b), b, S, S)
+    for n in ("X", "Y"):
+      D = self.ex[n]
+      plan.add_mse_loss(f"loss.{n}_real", D.inp[-1].view(b), 1.0, 0.5 / (nd * gbs), 1.0 / (nd * gbs),
+                        sl(f"{n}_loss"), D.gout_final.view(b), b, hd, wd)
+      plan.add_mse_loss(f"loss.{n}_fake", D.inp[-1].view(0), 0.0, 0.5 / (nd * gbs), 1.0 / (nd * gbs),
+                        sl(f"{n}_loss"), D.gout_final.view(0), b, hd, wd)
+    self.marks["test_end"] = plan.size()
+    # ---- P7: adversarial gradient into the fakes (dgrad-only pass through Y / X)
+    Y.backward(plan, 0, b, wgrad=False, input_grad_target=(G.gout_final, 0),
+               gout_view=self.gd_adv["Y"].view(0), gout_is_dy=True)
+    X.backward(plan, 0, b, wgrad=False, input_grad_target=(F.gout_final, 0),
+               gout_view=self.gd_adv["X"].view(0), gout_is_dy=True)
+    for n in ("X", "Y"):
+      e = self.ex[n]
+      plan.add_memset(f"zero.{n}.bstats2", e.bstat_arena.data_ptr(), e.bstat_arena.numel() * 4)
+    # ---- P8/P9: backward + optimizer per network
+    for n in NETS:
+      e = self.ex[n]
+      if n in ("G", "F"):
+        e.backward(plan, 0, 3 * b, wgrad=True)
+      else:
+        e.backward(plan, 0, 2 * b, wgrad=True, gout_is_dy=True)
+      self.marks[f"{n}_bwd_end"] = plan.size()
+      be.emit_optimizer(plan, n)
+      self.marks[f"{n}_opt_end"] = plan.size()
+    self.marks["end"] = plan.size()
+    self.names = plan.names()
+    self.kernels_per_step = sum(1 for nm in self.names if not nm.startswith("zero.") and ".zero" not in nm)
+    self.graph: Optional[torch.cuda.CUDAGraph] = None
+
+
+class NativeBackend:
+  name = "native"
+
+  def __init__(self, specs: Dict[str, NetSpec], global_batch_size: int, strategy: Strategy,
+               seed: int = 1234, image_size: int = 256, local_batch: int = 1, dtype: str = "bf16",
+               fused_allreduce: str = "auto", use_graph: Optional[bool] = None):
+    if not nv.available():
+      raise RuntimeError("the native backend needs an sm_100 GPU (B200)")
+    if dtype not in ("bf16",):
+      raise NotImplementedError(f"native backend: dtype {dtype!r} is not available yet (bf16 only)")
+    if image_size < 128 or image_size & (image_size - 1):
+      raise ValueError("native backend: image_size must be a power of two >= 128 "
+                       "(every layer must tile into 128-pixel boxes); use --backend oracle")
+    nv.load()
+    self.specs = specs
+    self.strategy = strategy
+    self.device = strategy.device
+    self.global_batch_size = global_batch_size
+    self.image_size = image_size
+    self.lambda_cycle = 10.0
+    self.lambda_identity = 5.0
+    import os
+    self.use_graph = (os.environ.get("B2_NO_GRAPH", "0") != "1") if use_graph is None else use_graph
+    self.world = strategy.world_size
+    self.fused = (fused_allreduce in ("auto", "on")) and self.world > 1
+    gen = torch.Generator().manual_seed(seed)
+    self.state: Dict[str, NetState] = OrderedDict()
+    self.symm = None
+    if self.fused:
+      from ..parallel.fused_allreduce import SymmetricBuffers
+      try:
+        self.symm = SymmetricBuffers(strategy)
+      except Exception as e:  # pragma: no cover - depends on the box
+        if fused_allreduce == "on":
+          raise
+        print(f"[native] fused all-reduce unavailable ({type(e).__name__}: {e}); using NCCL path")
+        self.fused = False
+    for n in NETS:
+      logical = oracle_net.init_params(specs[n], generator=gen)
+      gbuf = wbuf = None
+      if self.fused:
+        from .native_params import FlatLayout
+        numel = FlatLayout(specs[n]).numel
+        gbuf, wbuf = self.symm.alloc(n, numel)
+      self.state[n] = NetState(specs[n], logical, self.device, grad_buffer=gbuf, wb_buffer=wbuf)
+    self._plans: Dict[int, StepPlan] = {}
+    self._launches = 0
+    torch.cuda.synchronize(self.device)
+    strategy.barrier()
+
+  # ------------------------------------------------------------ optimizer
+  def emit_optimizer(self, plan, n: str):
+    st = self.state[n]
+    plan.add_mask_grad(f"opt.{n}.mask", st.g.data_ptr(), st.mask.data_ptr(), st.n)
+    if self.fused:
+      self.symm.emit_allreduce_adam(plan, n, st, **ADAM)
+    else:
+      plan.add_adam(f"opt.{n}.adam", st.w.data_ptr(), st.m.data_ptr(), st.v.data_ptr(), st.g.data_ptr(),
+                    st.wb.data_ptr(), st.step.data_ptr(), ADAM["lr"], ADAM["b1"], ADAM["b2"], ADAM["eps"],
+                    1.0, st.n)
+      plan.add_memset(f"zero.{n}.grads", st.g.data_ptr(), st.n * 4)
+    plan.add_step_increment(f"opt.{n}.step", st.step.data_ptr())
+    st.refresh_derived_ops(plan, f"opt.{n}")
+
+  # ---------------------------------------------------------------- plans
+  def plan_for(self, b: int) -> StepPlan:
+    if b not in self._plans:
+      self._plans[b] = StepPlan(self, b)
+    return self._plans[b]
+
+  def kernel_launches(self) -> int:
+    return self._launches
+
+  def _stream(self) -> int:
+    return torch.cuda.current_stream(self.device).cuda_stream
+
+  def _results(self, sp: StepPlan, with_errors: bool) -> Dict[str, torch.Tensor]:
+    s = sp.slots.clone()
+    r = OrderedDict([
+        ("loss_G/loss", s[0]), ("loss_G/cycle", s[1]), ("loss_G/identity", s[2]),
+        ("loss_G/total", s[0:3].sum()),
+        ("loss_F/loss", s[3]), ("loss_F/cycle", s[4]), ("loss_F/identity", s[5]),
+        ("loss_F/total", s[3:6].sum()),
+        ("loss_X/loss", s[6]), ("loss_Y/loss", s[7])])
+    if with_errors:
+      r["error/MAE(X, F(G(X)))"] = s[8]
+      r["error/MAE(Y, G(F(Y)))"] = s[9]
+      r["error/MAE(X, F(X))"] = s[10]
+      r["error/MAE(Y, G(Y))"] = s[11]
+    return r
+
+  def _load_inputs(self, sp: StepPlan, x: torch.Tensor, y: torch.Tensor):
+    sp.x_in.copy_(x.to(torch.float32), non_blocking=True)
+    sp.y_in.copy_(y.to(torch.float32), non_blocking=True)
+
+  def _zero_results(self, with_errors: bool):
+    z = torch.zeros((), device=self.device)
+    keys = ["loss_G/loss", "loss_G/cycle", "loss_G/identity", "loss_G/total", "loss_F/loss",
+            "loss_F/cycle", "loss_F/identity", "loss_F/total", "loss_X/loss", "loss_Y/loss"]
+    if with_errors:
+      keys += ["error/MAE(X, F(G(X)))", "error/MAE(Y, G(F(Y)))", "error/MAE(X, F(X))", "error/MAE(Y, G(Y))"]
+    return OrderedDict((k, z.clone()) for k in keys)
+
+  # ----------------------------------------------------------------- steps
+  def train_step(self, x: torch.Tensor, y: torch.Tensor, debug: bool = False) -> Dict[str, torch.Tensor]:
+    b = x.shape[0]
+    if b == 0:
+      return self._empty_train_step()
+    sp = self.plan_for(b)
+    self._load_inputs(sp, x, y)
+    end = sp.marks["end"]
+    if self.world > 1 and not self.fused:
+      self._run_segmented(sp)
+    elif self.use_graph and not debug:
+      if sp.graph is None:
+        # the first step runs eagerly (also sets lazy kernel attributes); the graph is captured
+        # right after it — capture records the launches without executing them
+        sp.plan.run(0, end, self._stream(), False)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+          sp.plan.run(0, end, self._stream(), False)
+        sp.graph = g
+      else:
+        sp.graph.replay()
+    else:
+      sp.plan.run(0, end, self._stream(), debug)
+    self._launches += sp.kernels_per_step
+    return self._results(sp, with_errors=False)
+
+  def _run_segmented(self, sp: StepPlan):
+    """NCCL baseline path: plan segments with one packed all-reduce per network in between."""
+    s = self._stream()
+    pos = 0
+    for n in NETS:
+      sp.plan.run(pos, sp.marks[f"{n}_bwd_end"], s, False)
+      self.strategy.all_reduce_sum(self.state[n].g)
+      pos = sp.marks[f"{n}_bwd_end"]
+    sp.plan.run(pos, sp.marks["end"], s, False)
+
+  def _empty_train_step(self):
+    """A replica with an empty share of a partial batch still joins the collectives."""
+    for n in NETS:
+      st = self.state[n]
+      if self.world > 1 and not self.fused:
+        self.strategy.all_reduce_sum(st.g)
+      # run just the optimizer ops of any existing plan (gradients are zero locally)
+    sp = self.plan_for(max(self._plans.keys(), default=1))
+    s = self._stream()
+    for n in NETS:
+      sp.plan.run(sp.marks[f"{n}_bwd_end"], sp.marks[f"{n}_opt_end"], s, False)
+    return self._zero_results(False)
+
+  @torch.no_grad()
+  def test_step(self, x: torch.Tensor, y: torch.Tensor) -> Dict[str, torch.Tensor]:
+    b = x.shape[0]
+    if b == 0:
+      return self._zero_results(True)
+    sp = self.plan_for(b)
+    self._load_inputs(sp, x, y)
+    sp.plan.run(0, sp.marks["test_end"], self._stream(), False)
+    return self._results(sp, with_errors=True)
+
+  @torch.no_grad()
+  def cycle_step(self, x: torch.Tensor, y: torch.Tensor):
+    """(fake_x, fake_y, cycle_x, cycle_y) as fp32 NHWC3 tensors."""
+    b = x.shape[0]
+    sp = self.plan_for(b)
+    self._load_inputs(sp, x.to(self.device), y.to(self.device))
+    sp.plan.run(0, sp.marks["cycle_end"], self._stream(), False)
+    G, F = sp.ex["G"], sp.ex["F"]
+    img = lambda e, s0: e.inp[-1].t[s0:s0 + b, :, :, :3].float()
+    return img(F, 0), img(G, 0), img(F, 2 * b), img(G, 2 * b)
+
+  # ------------------------------------------------------------ checkpoint
+  def _full(self, n: str, t: torch.Tensor) -> torch.Tensor:
+    """fp32 master / moments are sharded across ranks on the fused path (ZeRO-1)."""
+    if self.fused:
+      return self.symm.gather_sharded(t)
+    return t
+
+  def state_dict(self) -> Dict[str, torch.Tensor]:
+    sd: Dict[str, torch.Tensor] = OrderedDict()
+    for n in NETS:
+      st = self.state[n]
+      w = st.layout.unpack(self._full(n, st.w))
+      m = st.layout.unpack(self._full(n, st.m))
+      v = st.layout.unpack(self._full(n, st.v))
+      for name, t in w.items():
+        sd[f"{n}/{name}/.ATTRIBUTES/VARIABLE_VALUE"] = t
+      hyper = {"iter": float(st.step.item()), "learning_rate": ADAM["lr"], "beta_1": ADAM["b1"],
+               "beta_2": ADAM["b2"], "decay": 0.0}
+      for hk, hv in hyper.items():
+        sd[f"{n}_optimizer/{hk}/.ATTRIBUTES/VARIABLE_VALUE"] = torch.tensor(hv, dtype=torch.float64)
+      for name in w:
+        sd[f"{n}/{name}/.OPTIMIZER_SLOT/{n}_optimizer/m/.ATTRIBUTES/VARIABLE_VALUE"] = m[name]
+        sd[f"{n}/{name}/.OPTIMIZER_SLOT/{n}_optimizer/v/.ATTRIBUTES/VARIABLE_VALUE"] = v[name]
+    return sd
+
+  def load_state_dict(self, sd: Dict[str, torch.Tensor], expect_partial: bool = False) -> None:
+    missing: List[str] = []
+    for n in NETS:
+      st = self.state[n]
+      cur_w = st.layout.unpack(self._full(n, st.w))
+      cur_m = st.layout.unpack(self._full(n, st.m))
+      cur_v = st.layout.unpack(self._full(n, st.v))
+      for name in cur_w:
+        for store, key in ((cur_w, f"{n}/{name}/.ATTRIBUTES/VARIABLE_VALUE"),
+                           (cur_m, f"{n}/{name}/.OPTIMIZER_SLOT/{n}_optimizer/m/.ATTRIBUTES/VARIABLE_VALUE"),
+                           (cur_v, f"{n}/{name}/.OPTIMIZER_SLOT/{n}_optimizer/v/.ATTRIBUTES/VARIABLE_VALUE")):
+          if key in sd:
+            store[name] = sd[key].float()
+          else:
+            missing.append(key)
+      st.w.copy_(st.layout.pack(cur_w).to(self.device))
+      st.m.copy_(st.layout.pack(cur_m).to(self.device))
+      st.v.copy_(st.layout.pack(cur_v).to(self.device))
+      st.wb.copy_(st.w.to(torch.bfloat16))
+      st.refresh_derived_now()
+      key = f"{n}_optimizer/iter/.ATTRIBUTES/VARIABLE_VALUE"
+      if key in sd:
+        st.step.fill_(int(sd[key]))
+      else:
+        missing.append(key)
+    torch.cuda.synchronize(self.device)
+    self.strategy.barrier()
+    if missing and not expect_partial:
+      raise KeyError(f"checkpoint is missing {len(missing)} keys, e.g. {missing[:3]} "
+                     f"(pass expect_partial=True to ignore)")

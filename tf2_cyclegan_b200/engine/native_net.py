@@ -65,6 +65,8 @@ class NetState:
 
   def add_derived(self, name: str, idx: torch.Tensor) -> torch.Tensor:
     """bf16 matrix gathered from the master weights through ``idx`` (-1 = zero)."""
+    if name in self.derived:      # shared by every plan (batch size) of this network
+      return self.derived[name][0]
     idx32 = idx.to(torch.int32).contiguous().to(self.w.device)
     dst = torch.zeros(idx.shape, dtype=torch.bfloat16, device=self.w.device)
     self.derived[name] = (dst, idx32)
@@ -117,15 +119,15 @@ class NetExec:
     self.stats: List[Optional[torch.Tensor]] = []
     self.bstats: List[Optional[torch.Tensor]] = []
     stat_sizes = [nb * l.cout * 2 if l.norm else 0 for l in self.layers]
-    self.stat_arena = torch.zeros(2 * sum(stat_sizes) + 8, device=dev)
+    self.stat_arena = torch.zeros(sum(stat_sizes) + 8, device=dev)     # zeroed every step
+    self.bstat_arena = torch.zeros(sum(stat_sizes) + 8, device=dev)    # zeroed before every backward pass
     off = 0
     for j, l in enumerate(self.layers):
       ho, wo = self.out_hw[j]
       if l.norm:
         self.raw.append(Buf(nb, ho, wo, l.cout, device=dev))
         self.stats.append(self.stat_arena[off:off + stat_sizes[j]].view(nb, l.cout, 2))
-        off += stat_sizes[j]
-        self.bstats.append(self.stat_arena[off:off + stat_sizes[j]].view(nb, l.cout, 2))
+        self.bstats.append(self.bstat_arena[off:off + stat_sizes[j]].view(nb, l.cout, 2))
         off += stat_sizes[j]
       else:
         self.raw.append(None)
