@@ -57,6 +57,15 @@ class FakePlan:
     assert dw % 16 == 0 and ldw % 4 == 0
     return self._add("wgrad", name, len(taps), cin, cout)
 
+  def set_lane(self, lane):
+    self.lane = lane
+
+  def add_fork(self, name):
+    return self._add("fork", name)
+
+  def add_join(self, name):
+    return self._add("join", name)
+
   def __getattr__(self, item):
     if item.startswith("add_"):
       def f(name, *args):

@@ -27,12 +27,13 @@ def test_step_plan_builds_and_is_well_formed(monkeypatch, size, b, nres):
   assert sum(1 for n in names if n.startswith("X.conv0.fwd")) == 1      # fakes forwarded once
   # gradient routing: no dgrad into a stem, adversarial pass has no wgrad
   assert not any("stem.dgrad" in n for n in names)
-  adv = names[sp.marks["test_end"]:names.index("zero.X.bstats2")]
+  adv = [n for n in names if n[0] in "XY" and n.endswith(f"[0:{b}]") or f"[0:{b}]." in n and n[0] in "XY"]
   assert adv and not any("wgrad" in n for n in adv) and any("conv0.dgrad" in n for n in adv)
+  assert any(n.startswith("sync.fork") for n in names) and any(n.startswith("sync.join") for n in names)
   for n in NETS:
     assert f"opt.{n}.adam" in names and f"opt.{n}.step" in names
   # every conv layer of every network gets exactly one wgrad group in the full backward
-  full = names[names.index("zero.Y.bstats2"):]
+  full = names[sp.marks["test_end"]:]
   for l in be.specs["G"].layers:
     assert any(n.startswith(f"G.{l.name}.wgrad") for n in full), l.name
   for l in be.specs["X"].layers:

@@ -1,19 +1,20 @@
-// Implicit-GEMM convolution for sm_100a: TMA (4-D tiled boxes, zero OOB fill) →
-// 128B-swizzled shared memory → tcgen05.mma (M=128, N=BLOCK_N, K=16, fp32
-// accumulators in TMEM) → tcgen05.ld epilogue with fused bias / activation /
-// InstanceNorm partial statistics.
+// Persistent implicit-GEMM convolution for sm_100a: TMA (4-D tiled boxes, zero OOB
+// fill) → 128B-swizzled shared memory ring → tcgen05.mma (M=128, N=BLOCK_N, K=16,
+// fp32 accumulators in TMEM, double-buffered) → tcgen05.ld epilogue with fused bias /
+// activation / InstanceNorm partial statistics, overlapped with the next tile's MMAs.
 //
 //   D[m, n] = sum_taps sum_c A_tap[m, c] * W[n, tap, c]
 //
-// One CTA computes one 128-pixel x BLOCK_N-channel output tile; the filter taps
-// are walked by shifting the TMA box coordinates, so no im2col buffer exists.
-// The same kernel serves forward convs (box mode over padded / parity views),
-// transposed-conv phases and dgrad (flat mode over zero-ringed gradients); the
-// weight operand may be K-major ([N][K]) or MN-major ([K][N], used by dgrad so
-// forward and backward share one weight copy).
+// One CTA per SM loops over 128-pixel x BLOCK_N-channel output tiles; filter taps are
+// walked by shifting the TMA box coordinates, so no im2col buffer exists. The same
+// kernel serves forward convs (box mode over padded / parity views), transposed-conv
+// phases and dgrad (flat mode over zero-ringed gradients); the weight operand may be
+// K-major ([N][K]) or MN-major ([K][N], used by dgrad so forward and backward share one
+// weight copy).
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer,
-// warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM lane quarter = warp % 4).
+// Warp roles (256 threads): warp 0 = TMA producer (runs ahead across tiles), warp 1 =
+// MMA issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM lane quarter = warp % 4).
+// Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty x2 (MMA <-> epilogue).
 #include "conv_gemm.cuh"
 
 namespace b2 {
@@ -24,40 +25,42 @@ struct GemmCfg {
   static constexpr int kBBytes = BLOCK_N * 128;    // BLOCK_N x 64 bf16
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
-  static constexpr int kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
-  static constexpr int kChunks = BLOCK_N / 8;      // 16-byte chunks per staged output row
-  static constexpr int kRowGroups = 128 / (kChunks > 128 ? 128 : kChunks);
-  static constexpr int kStagingBytes = 128 * BLOCK_N * 2;
-  static constexpr int kRedBytes = kRowGroups * BLOCK_N * 2 * 4;
-  static constexpr int kBarrierBytes = (2 * kStages + 1) * 8 + 16;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + 1024;  // +align slack
-  static_assert(kStagingBytes + kRedBytes <= kStages * kStageBytes, "epilogue aliases the pipeline");
+  static constexpr int kAccCols = BLOCK_N < 32 ? 32 : BLOCK_N;
+  static constexpr int kTmemCols = 2 * kAccCols;   // 64 .. 512, power of two
+  static constexpr int kChunkN = BLOCK_N < 64 ? BLOCK_N : 64;   // epilogue column chunk
+  static constexpr int kChunks16 = kChunkN / 8;    // 16-byte pieces per staged row
+  static constexpr int kRowGroups = 128 / kChunks16;
+  static constexpr int kStagingBytes = 128 * kChunkN * 2;
+  static constexpr int kRedBytes = kRowGroups * kChunkN * 2 * 4;
+  static constexpr int kBarrierBytes = (2 * kStages + 4) * 8 + 16;
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kStagingBytes + kRedBytes + kBarrierBytes + 1024;  // +align slack
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
 template <int BLOCK_N, bool B_MN>
 __global__ void __launch_bounds__(256, 1)
-conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, int num_images) {
   using Cfg = GemmCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* stage_buf = smem + Cfg::kStages * Cfg::kStageBytes;
+  float* red = reinterpret_cast<float*>(stage_buf + Cfg::kStagingBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_buf + Cfg::kStagingBytes + Cfg::kRedBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;    // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;          // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // tile -> (image, h0, w0)
   const int tiles_per_img = p.tiles_w * p.tiles_h;
-  const int img = blockIdx.x / tiles_per_img;
-  const int t_in = blockIdx.x - img * tiles_per_img;
-  const int th = t_in / p.tiles_w;
-  const int w0 = (t_in - th * p.tiles_w) * p.bw;
-  const int h0 = th * p.bh;
-  const int n0 = blockIdx.y * BLOCK_N;
+  const int m_tiles = tiles_per_img * num_images;
+  const int n_tiles = (p.cout + BLOCK_N - 1) / BLOCK_N;
+  const int total_tiles = m_tiles * n_tiles;
   const int num_kb = p.num_taps * p.cin_blocks;
 
   if (warp == 0 && lane == 0) {
@@ -68,7 +71,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 128);
+    }
     fence_barrier_init();
   } else if (warp == 2) {
     tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
@@ -81,24 +87,33 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   if (warp == 0) {
     // ============================ TMA producer ============================
     if (lane == 0) {
-      int kb = 0;
-      for (int t = 0; t < p.num_taps; ++t) {
-        const Tap tap = p.taps[t];
-        const CUtensorMap* amap = &p.tmA[tap.map];
-        for (int cb = 0; cb < p.cin_blocks; ++cb, ++kb) {
-          const int s = kb % Cfg::kStages;
-          const uint32_t ph = (kb / Cfg::kStages) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + s * Cfg::kStageBytes;
-          uint8_t* sb = sa + Cfg::kABytes;
-          mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-          tma_load_4d(sa, amap, &full_bar[s], cb * 64, w0 + tap.dw, h0 + tap.dh, img + tap.dn);
-          if constexpr (!B_MN) {
-            tma_load_2d(sb, &p.tmB, &full_bar[s], tap.bk + cb * 64, n0);
-          } else {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / n_tiles;
+        const int n0 = (tile - mt * n_tiles) * BLOCK_N;
+        const int img = mt / tiles_per_img;
+        const int t_in = mt - img * tiles_per_img;
+        const int th = t_in / p.tiles_w;
+        const int w0 = (t_in - th * p.tiles_w) * p.bw;
+        const int h0 = th * p.bh;
+        for (int t = 0; t < p.num_taps; ++t) {
+          const Tap tap = p.taps[t];
+          const CUtensorMap* amap = &p.tmA[tap.map];
+          for (int cb = 0; cb < p.cin_blocks; ++cb, ++it) {
+            const int s = it % Cfg::kStages;
+            const uint32_t ph = (it / Cfg::kStages) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* sa = smem + s * Cfg::kStageBytes;
+            uint8_t* sb = sa + Cfg::kABytes;
+            mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+            tma_load_4d(sa, amap, &full_bar[s], cb * 64, w0 + tap.dw, h0 + tap.dh, img + tap.dn);
+            if constexpr (!B_MN) {
+              tma_load_2d(sb, &p.tmB, &full_bar[s], tap.bk + cb * 64, n0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j)
-              tma_load_2d(sb + j * (64 * 128), &p.tmB, &full_bar[s], tap.bk + n0 + j * 64, cb * 64);
+              for (int j = 0; j < BLOCK_N / 64; ++j)
+                tma_load_2d(sb + j * (64 * 128), &p.tmB, &full_bar[s], tap.bk + n0 + j * 64, cb * 64);
+            }
           }
         }
       }
@@ -107,159 +122,184 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     // ============================= MMA issuer =============================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, B_MN ? 1 : 0);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % Cfg::kStages;
-        const uint32_t ph = (kb / Cfg::kStages) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, tile_i = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
+        const uint32_t acc = tile_i & 1;
+        const uint32_t acc_ph = (tile_i >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
-        const uint32_t sb = sa + Cfg::kABytes;
-        const uint64_t da = make_desc_kmajor(sa);
-        const uint64_t db = B_MN ? make_desc_mnmajor(sb, 64) : make_desc_kmajor(sb);
+        const uint32_t tmem_d = tmem_base + acc * Cfg::kAccCols;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+          const uint64_t da = make_desc_kmajor(sa);
+          const uint64_t db = B_MN ? make_desc_mnmajor(sb, 64) : make_desc_kmajor(sb);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // K advance of 16 elements: +32 B inside the swizzle row (K-major),
-          // +16 rows * 128 B (MN-major); descriptor address field is in 16-byte units
-          const uint64_t da_k = da + static_cast<uint64_t>(k * 2);
-          const uint64_t db_k = db + static_cast<uint64_t>(B_MN ? k * 128 : k * 2);
-          umma_bf16(tmem_base, da_k, db_k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            // K advance of 16 elements: +32 B inside the swizzle row (K-major),
+            // +16 rows * 128 B (MN-major); descriptor address field is in 16-byte units
+            const uint64_t da_k = da + static_cast<uint64_t>(k * 2);
+            const uint64_t db_k = db + static_cast<uint64_t>(B_MN ? k * 128 : k * 2);
+            umma_bf16(tmem_d, da_k, db_k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);        // frees the smem slot when these MMAs retire
         }
-        umma_commit(&empty_bar[s]);   // frees the smem slot when these MMAs retire
+        umma_commit(&tmem_full_bar[acc]);    // accumulator complete
       }
-      umma_commit(tmem_full_bar);     // accumulator complete
     }
   } else if (warp >= 4) {
     // ============================== epilogue ==============================
     const int e = threadIdx.x - 128;          // 0..127 == tile row == TMEM lane
     const int ew = warp - 4;                  // TMEM lane quarter
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    uint8_t* stage = smem;                    // aliases the (now idle) pipeline buffers
-    float* red = reinterpret_cast<float*>(smem + Cfg::kStagingBytes);
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
-    constexpr int ROW_BYTES = BLOCK_N * 2;
-
-    if constexpr (BLOCK_N >= 32) {
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c, r);
-        tmem_ld_wait();
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[j]);
-          if (p.bias != nullptr && n0 + c + j < p.cout) x += __ldg(p.bias + n0 + c + j);
-          v[j] = apply_act(x, p.act);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int ci = (c >> 3) + q;
-          const int phys = ci ^ (e & 7);
-          uint4 pk;
-          pk.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-          pk.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-          pk.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-          pk.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-          *reinterpret_cast<uint4*>(stage + e * ROW_BYTES + phys * 16) = pk;
-        }
-      }
-    } else {
-      uint32_t r[16];
-      tmem_ld_32x16(taddr, r);
-      tmem_ld_wait();
-      float v[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float x = __uint_as_float(r[j]);
-        if (p.bias != nullptr && n0 + j < p.cout) x += __ldg(p.bias + n0 + j);
-        v[j] = apply_act(x, p.act);
-      }
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        uint4 pk;
-        pk.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-        pk.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-        pk.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-        pk.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-        *reinterpret_cast<uint4*>(stage + e * ROW_BYTES + q * 16) = pk;
-      }
-    }
-    tc_fence_before();
-    named_bar_sync(1, 128);
-
-    constexpr int CH = Cfg::kChunks;
+    constexpr int CN = Cfg::kChunkN;
+    constexpr int CH = Cfg::kChunks16;
+    constexpr int RG = Cfg::kRowGroups;
     constexpr bool SWZ = (CH >= 8);
-    // ---- InstanceNorm partial statistics (sum, sum of squares per channel)
-    if (p.stats != nullptr) {
-      constexpr int RG = Cfg::kRowGroups;
-      const int ci = e % CH;
-      const int rg = e / CH;
-      float s[8], q[8];
+    constexpr int ROW_BYTES = CN * 2;
+    uint32_t tile_i = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
+      const int mt = tile / n_tiles;
+      const int n0 = (tile - mt * n_tiles) * BLOCK_N;
+      const int img = mt / tiles_per_img;
+      const int t_in = mt - img * tiles_per_img;
+      const int th = t_in / p.tiles_w;
+      const int w0 = (t_in - th * p.tiles_w) * p.bw;
+      const int h0 = th * p.bh;
+      const uint32_t acc = tile_i & 1;
+      const uint32_t acc_ph = (tile_i >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * Cfg::kAccCols + (static_cast<uint32_t>(ew * 32) << 16);
+
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += CN) {
+        // ---- TMEM -> registers -> bias / activation -> bf16 -> staging (swizzled rows)
+        if constexpr (CN >= 32) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
-      for (int r = rg; r < 128; r += RG) {
-        const int phys = SWZ ? (ci ^ (r & 7)) : ci;
-        const uint4 pk = *reinterpret_cast<const uint4*>(stage + r * ROW_BYTES + phys * 16);
-        const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+          for (int cc = 0; cc < CN; cc += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(taddr + c0 + cc, r);
+            tmem_ld_wait();
+            float v[32];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = unpack_bf16x2(w[j]);
-          s[2 * j] += f.x; q[2 * j] += f.x * f.x;
-          s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
+            for (int j = 0; j < 32; ++j) {
+              float x = __uint_as_float(r[j]);
+              if (p.bias != nullptr && n0 + c0 + cc + j < p.cout) x += __ldg(p.bias + n0 + c0 + cc + j);
+              v[j] = apply_act(x, p.act);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int ci = (cc >> 3) + q;
+              const int phys = SWZ ? (ci ^ (e & 7)) : ci;
+              uint4 pk;
+              pk.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+              pk.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+              pk.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+              pk.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+              *reinterpret_cast<uint4*>(stage_buf + e * ROW_BYTES + phys * 16) = pk;
+            }
+          }
+        } else {
+          uint32_t r[16];
+          tmem_ld_32x16(taddr + c0, r);
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float x = __uint_as_float(r[j]);
+            if (p.bias != nullptr && n0 + c0 + j < p.cout) x += __ldg(p.bias + n0 + c0 + j);
+            v[j] = apply_act(x, p.act);
+          }
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            uint4 pk;
+            pk.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+            pk.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+            pk.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+            pk.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+            *reinterpret_cast<uint4*>(stage_buf + e * ROW_BYTES + q * 16) = pk;
+          }
         }
-      }
+        if (c0 + CN >= BLOCK_N) {     // all TMEM reads of this tile are done: release the accumulator
+          tc_fence_before();
+          mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        named_bar_sync(1, 128);
+
+        // ---- InstanceNorm partial statistics (sum, sum of squares per channel)
+        if (p.stats != nullptr) {
+          const int ci = e % CH;
+          const int rg = e / CH;
+          float s[8], q[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        red[(rg * BLOCK_N + ci * 8 + j) * 2 + 0] = s[j];
-        red[(rg * BLOCK_N + ci * 8 + j) * 2 + 1] = q[j];
-      }
-      named_bar_sync(1, 128);
-      for (int col = e; col < BLOCK_N; col += 128) {
-        if (n0 + col < p.cout) {
-          float ss = 0.f, qq = 0.f;
+          for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
 #pragma unroll 4
-          for (int g = 0; g < RG; ++g) {
-            ss += red[(g * BLOCK_N + col) * 2 + 0];
-            qq += red[(g * BLOCK_N + col) * 2 + 1];
-          }
-          float* dst = p.stats + (static_cast<long long>(img) * p.cout + n0 + col) * 2;
-          atomicAdd(dst, ss);
-          atomicAdd(dst + 1, qq);
-        }
-      }
-    }
-    // ---- coalesced store of the staged tile
-    const int n_valid = min(BLOCK_N, p.cout - n0);
-    if (n_valid == BLOCK_N) {
-      constexpr int CPR = CH > 32 ? 32 : CH;     // chunks handled per row per pass
-      constexpr int RPI = 32 / CPR;              // rows per warp instruction
-      for (int it = 0; it < 32 / RPI; ++it) {
-        const int r = ew * 32 + it * RPI + lane / CPR;
-        const int wl = r % p.bw, hl = r / p.bw;
-        if (w0 + wl < p.w_limit) {
-          __nv_bfloat16* dst = p.out + img * p.out_sn + (h0 + hl) * p.out_sh +
-                               (w0 + wl) * p.out_sw + n0;
+          for (int r = rg; r < 128; r += RG) {
+            const int phys = SWZ ? (ci ^ (r & 7)) : ci;
+            const uint4 pk = *reinterpret_cast<const uint4*>(stage_buf + r * ROW_BYTES + phys * 16);
+            const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
 #pragma unroll
-          for (int cc = lane % CPR; cc < CH; cc += CPR) {
-            const int phys = SWZ ? (cc ^ (r & 7)) : cc;
-            const uint4 pk = *reinterpret_cast<const uint4*>(stage + r * ROW_BYTES + phys * 16);
-            *reinterpret_cast<uint4*>(dst + cc * 8) = pk;
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = unpack_bf16x2(w[j]);
+              s[2 * j] += f.x; q[2 * j] += f.x * f.x;
+              s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            red[(rg * CN + ci * 8 + j) * 2 + 0] = s[j];
+            red[(rg * CN + ci * 8 + j) * 2 + 1] = q[j];
+          }
+          named_bar_sync(2, 128);
+          if (e < CN && n0 + c0 + e < p.cout) {
+            float ss = 0.f, qq = 0.f;
+#pragma unroll 8
+            for (int g = 0; g < RG; ++g) {
+              ss += red[(g * CN + e) * 2 + 0];
+              qq += red[(g * CN + e) * 2 + 1];
+            }
+            float* dst = p.stats + (static_cast<long long>(img) * p.cout + n0 + c0 + e) * 2;
+            atomicAdd(dst, ss);
+            atomicAdd(dst + 1, qq);
           }
         }
-      }
-    } else {
-      const int r = e;
-      const int wl = r % p.bw, hl = r / p.bw;
-      if (w0 + wl < p.w_limit) {
-        __nv_bfloat16* dst = p.out + img * p.out_sn + (h0 + hl) * p.out_sh +
-                             (w0 + wl) * p.out_sw + n0;
-        for (int c = 0; c < n_valid; ++c) {
-          const int cc = c >> 3;
-          const int phys = SWZ ? (cc ^ (r & 7)) : cc;
-          dst[c] = *reinterpret_cast<const __nv_bfloat16*>(stage + r * ROW_BYTES + phys * 16 +
-                                                            (c & 7) * 2);
+
+        // ---- coalesced store of the staged chunk
+        const int n_valid = min(CN, p.cout - n0 - c0);
+        if (n_valid == CN) {
+          constexpr int RPI = 32 / CH;              // rows per warp instruction
+#pragma unroll 2
+          for (int itr = 0; itr < 32 / RPI; ++itr) {
+            const int r = ew * 32 + itr * RPI + lane / CH;
+            const int cc = lane % CH;
+            const int wl = r % p.bw, hl = r / p.bw;
+            if (w0 + wl < p.w_limit) {
+              __nv_bfloat16* dst = p.out + img * p.out_sn + (h0 + hl) * p.out_sh +
+                                   (w0 + wl) * p.out_sw + n0 + c0;
+              const int phys = SWZ ? (cc ^ (r & 7)) : cc;
+              const uint4 pk = *reinterpret_cast<const uint4*>(stage_buf + r * ROW_BYTES + phys * 16);
+              *reinterpret_cast<uint4*>(dst + cc * 8) = pk;
+            }
+          }
+        } else if (n_valid > 0) {
+          const int r = e;
+          const int wl = r % p.bw, hl = r / p.bw;
+          if (w0 + wl < p.w_limit) {
+            __nv_bfloat16* dst = p.out + img * p.out_sn + (h0 + hl) * p.out_sh +
+                                 (w0 + wl) * p.out_sw + n0 + c0;
+            for (int c = 0; c < n_valid; ++c) {
+              const int cc = c >> 3;
+              const int phys = SWZ ? (cc ^ (r & 7)) : cc;
+              dst[c] = *reinterpret_cast<const __nv_bfloat16*>(stage_buf + r * ROW_BYTES + phys * 16 +
+                                                                (c & 7) * 2);
+            }
+          }
         }
+        named_bar_sync(1, 128);   // staging / red buffers are reused by the next chunk
       }
     }
   }
@@ -267,6 +307,17 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
 }
 
 template <int BLOCK_N, bool B_MN>
@@ -278,8 +329,9 @@ static void launch_t(const ConvGemmParams& p, int num_images, cudaStream_t strea
                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     configured = true;
   }
-  dim3 grid(p.tiles_w * p.tiles_h * num_images, (p.cout + BLOCK_N - 1) / BLOCK_N);
-  conv_gemm_kernel<BLOCK_N, B_MN><<<grid, 256, Cfg::kSmemBytes, stream>>>(p);
+  const int total = p.tiles_w * p.tiles_h * num_images * ((p.cout + BLOCK_N - 1) / BLOCK_N);
+  const int grid = total < num_sms() ? total : num_sms();
+  conv_gemm_kernel<BLOCK_N, B_MN><<<grid, 256, Cfg::kSmemBytes, stream>>>(p, num_images);
 }
 
 void launch_conv_gemm(const ConvGemmParams& p, int block_n, bool b_mn_major, int num_images,

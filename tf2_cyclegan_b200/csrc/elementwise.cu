@@ -76,50 +76,83 @@ __device__ __forceinline__ void gather_g(const View& g1, int fold, const View& g
 }
 
 // ------------------------------------------------------------------ in_apply
-__global__ void __launch_bounds__(kThreads) in_apply_kernel(const InApplyParams p) {
+// grid: (pixel chunks, N). A thread owns one 8-channel group (coefficients live in
+// registers) and walks pixels, 4 at a time so that several 16-byte loads are in flight.
+__global__ void __launch_bounds__(kThreads, 2) in_apply_kernel(const InApplyParams p, int pix_per_block) {
   const int c8 = p.C >> 3;
-  const long long total = static_cast<long long>(p.N) * p.H * p.W * c8;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % c8) * 8;
-    long long r = i / c8;
-    const int w = static_cast<int>(r % p.W);
-    r /= p.W;
-    const int h = static_cast<int>(r % p.H);
-    const int n = static_cast<int>(r / p.H);
-    float v[8];
-    load8(vptr(p.x, n, h, w) + c, v);
-    if (p.stats != nullptr) {
-      const float* st = p.stats + (static_cast<long long>(n) * p.C + c) * 2;
+  const int lanes = kThreads / c8;
+  const int c = (threadIdx.x % c8) * 8;
+  const int ln = threadIdx.x / c8;
+  const int n = blockIdx.y;
+  const int HW = p.H * p.W;
+  const int pix0 = blockIdx.x * pix_per_block;
+  const int pix1 = min(HW, pix0 + pix_per_block);
+  float ca[8], cb[8];
+  if (p.stats != nullptr) {
+    const float* st = p.stats + (static_cast<long long>(n) * p.C + c) * 2;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float mean = st[2 * j] * p.inv_count;
-        const float var = fmaxf(st[2 * j + 1] * p.inv_count - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + p.eps);
-        v[j] = (v[j] - mean) * rstd * __ldg(p.gamma + c + j) + __ldg(p.beta + c + j);
+    for (int j = 0; j < 8; ++j) {
+      const float mean = st[2 * j] * p.inv_count;
+      const float var = fmaxf(st[2 * j + 1] * p.inv_count - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + p.eps);
+      ca[j] = rstd * __ldg(p.gamma + c + j);
+      cb[j] = __ldg(p.beta + c + j) - mean * ca[j];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ca[j] = 1.f; cb[j] = 0.f; }
+  }
+  const bool has_skip = p.skip.p != nullptr;
+  constexpr int U = 4;
+  for (int base = pix0 + ln; base < pix1; base += lanes * U) {
+    uint4 xv[U], sv[U];
+    int hh[U], ww[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pix = base + u * lanes;
+      if (pix < pix1) {
+        hh[u] = pix / p.W;
+        ww[u] = pix - hh[u] * p.W;
+        xv[u] = __ldg(reinterpret_cast<const uint4*>(vptr(p.x, n, hh[u], ww[u]) + c));
+        if (has_skip) sv[u] = __ldg(reinterpret_cast<const uint4*>(vptr(p.skip, n, hh[u], ww[u]) + c));
       }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], p.act);
-    if (p.skip.p != nullptr) {
-      float s[8];
-      load8(vptr(p.skip, n, h, w) + c, s);
+    for (int u = 0; u < U; ++u) {
+      const int pix = base + u * lanes;
+      if (pix >= pix1) continue;
+      const uint32_t xw[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+      const uint32_t sw[4] = {sv[u].x, sv[u].y, sv[u].z, sv[u].w};
+      float v[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] += s[j];
+      for (int j = 0; j < 4; ++j) {
+        const float2 t = unpack_bf16x2(xw[j]);
+        v[2 * j] = apply_act(fmaf(t.x, ca[2 * j], cb[2 * j]), p.act);
+        v[2 * j + 1] = apply_act(fmaf(t.y, ca[2 * j + 1], cb[2 * j + 1]), p.act);
+        if (has_skip) {
+          const float2 k = unpack_bf16x2(sw[j]);
+          v[2 * j] += k.x;
+          v[2 * j + 1] += k.y;
+        }
+      }
+      const uint4 pk = pack8(v);
+      *reinterpret_cast<uint4*>(vptr_mut(p.dst, n, hh[u], ww[u]) + c) = pk;
+      if (p.halo > 0) {
+        int hs[2], ws[2];
+        const int nh = reflect_set(hh[u], p.H, p.halo, hs);
+        const int nw = reflect_set(ww[u], p.W, p.halo, ws);
+        if (nh + nw > 2)
+          for (int a = 0; a < nh; ++a)
+            for (int b = 0; b < nw; ++b)
+              if (a + b > 0) *reinterpret_cast<uint4*>(vptr_mut(p.dst, n, hs[a], ws[b]) + c) = pk;
+      }
     }
-    const uint4 pk = pack8(v);
-    int hs[2], ws[2];
-    const int nh = reflect_set(h, p.H, p.halo, hs);
-    const int nw = reflect_set(w, p.W, p.halo, ws);
-    for (int a = 0; a < nh; ++a)
-      for (int b = 0; b < nw; ++b)
-        *reinterpret_cast<uint4*>(vptr_mut(p.dst, n, hs[a], ws[b]) + c) = pk;
   }
 }
 
 // ------------------------------------------------------------ in_bwd_reduce
 // grid: (pixel chunks, N). Threads: (C/8 channel groups) x (256 / (C/8) pixel lanes).
-__global__ void __launch_bounds__(kThreads) in_bwd_reduce_kernel(const InBwdReduceParams p,
+__global__ void __launch_bounds__(kThreads, 2) in_bwd_reduce_kernel(const InBwdReduceParams p,
                                                                  int pix_per_block) {
   extern __shared__ float red[];   // [lanes][C][2]
   const int c8 = p.C >> 3;
@@ -149,24 +182,72 @@ __global__ void __launch_bounds__(kThreads) in_bwd_reduce_kernel(const InBwdRedu
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
 
-  for (int pix = pix0 + ln; pix < pix1; pix += lanes) {
-    const int h = pix / p.W, w = pix - h * p.W;
-    float g[8], x[8];
-    gather_g(p.g1, p.fold1, p.g2, n, h, w, p.H, p.W, c, g);
-    if (has_in) {
-      load8(vptr(p.x, n, h, w) + c, x);
+  const bool has_g2 = p.g2.p != nullptr;
+  constexpr int U = 4;
+  for (int base = pix0 + ln; base < pix1; base += lanes * U) {
+    uint4 gv[U], g2v[U], xv[U];
+    int hh[U], ww[U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = (x[j] - mean[j]) * rstd[j];
-        const float y = xh * gam[j] + bet[j];
-        g[j] *= act_grad_from_pre(y, p.act);
-        // statistics of the value that is actually stored (bf16)
-        const float gq = __bfloat162float(__float2bfloat16(g[j]));
-        s1[j] += gq;
-        s2[j] += gq * xh;
+    for (int u = 0; u < U; ++u) {
+      const int pix = base + u * lanes;
+      if (pix < pix1) {
+        hh[u] = pix / p.W;
+        ww[u] = pix - hh[u] * p.W;
+        gv[u] = __ldg(reinterpret_cast<const uint4*>(vptr(p.g1, n, hh[u], ww[u]) + c));
+        if (has_g2) g2v[u] = __ldg(reinterpret_cast<const uint4*>(vptr(p.g2, n, hh[u], ww[u]) + c));
+        if (has_in) xv[u] = __ldg(reinterpret_cast<const uint4*>(vptr(p.x, n, hh[u], ww[u]) + c));
       }
     }
-    store8(vptr_mut(p.dy, n, h, w) + c, g);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pix = base + u * lanes;
+      if (pix >= pix1) continue;
+      const int h = hh[u], w = ww[u];
+      float g[8];
+      {
+        const uint32_t a[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
+        const uint32_t b[4] = {g2v[u].x, g2v[u].y, g2v[u].z, g2v[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 t = unpack_bf16x2(a[j]);
+          g[2 * j] = t.x; g[2 * j + 1] = t.y;
+          if (has_g2) { const float2 k = unpack_bf16x2(b[j]); g[2 * j] += k.x; g[2 * j + 1] += k.y; }
+        }
+      }
+      if (p.fold1 > 0) {   // rare: pixels whose mirror images live in the halo of g1
+        int hs[2], ws[2];
+        const int nh = reflect_set(h, p.H, p.fold1, hs);
+        const int nw = reflect_set(w, p.W, p.fold1, ws);
+        if (nh + nw > 2)
+          for (int a = 0; a < nh; ++a)
+            for (int b = 0; b < nw; ++b)
+              if (a + b > 0) {
+                float t[8];
+                load8(vptr(p.g1, n, hs[a], ws[b]) + c, t);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) g[j] += t[j];
+              }
+      }
+      if (has_in) {
+        const uint32_t xw[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 t = unpack_bf16x2(xw[j]);
+          const float xs[2] = {t.x, t.y};
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const int jj = 2 * j + q;
+            const float xh = (xs[q] - mean[jj]) * rstd[jj];
+            const float y = xh * gam[jj] + bet[jj];
+            g[jj] *= act_grad_from_pre(y, p.act);
+            const float gq = __bfloat162float(__float2bfloat16(g[jj]));   // stats of the stored value
+            s1[jj] += gq;
+            s2[jj] += gq * xh;
+          }
+        }
+      }
+      store8(vptr_mut(p.dy, n, h, w) + c, g);
+    }
   }
   if (!has_in || p.bstats == nullptr) return;
 #pragma unroll
@@ -183,32 +264,30 @@ __global__ void __launch_bounds__(kThreads) in_bwd_reduce_kernel(const InBwdRedu
 }
 
 // ------------------------------------------------------------- in_bwd_apply
-__global__ void __launch_bounds__(kThreads) in_bwd_apply_kernel(const InBwdApplyParams p) {
+// dx = A*dy + B*x + C per channel (A = gamma*rstd, B = -gamma*rstd^2*m2, C = gamma*rstd*(mean*rstd*m2 - m1))
+__global__ void __launch_bounds__(kThreads, 2) in_bwd_apply_kernel(const InBwdApplyParams p, int pix_per_block) {
   const int c8 = p.C >> 3;
-  const long long total = static_cast<long long>(p.N) * p.H * p.W * c8;
-  if (blockIdx.x == 0 && p.dgamma != nullptr) {   // parameter gradients: sum over images
-    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+  const int lanes = kThreads / c8;
+  const int c = (threadIdx.x % c8) * 8;
+  const int ln = threadIdx.x / c8;
+  const int n = blockIdx.y;
+  const int HW = p.H * p.W;
+  const int pix0 = blockIdx.x * pix_per_block;
+  const int pix1 = min(HW, pix0 + pix_per_block);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && p.dgamma != nullptr) {   // parameter gradients: sum over images
+    for (int cc = threadIdx.x; cc < p.C; cc += blockDim.x) {
       float dg = 0.f, db = 0.f;
-      for (int n = 0; n < p.N; ++n) {
-        const float* bs = p.bstats + (static_cast<long long>(n) * p.C + c) * 2;
+      for (int nn = 0; nn < p.N; ++nn) {
+        const float* bs = p.bstats + (static_cast<long long>(nn) * p.C + cc) * 2;
         db += bs[0];
         dg += bs[1];
       }
-      p.dgamma[c] += dg;
-      p.dbeta[c] += db;
+      p.dgamma[cc] += dg;
+      p.dbeta[cc] += db;
     }
   }
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % c8) * 8;
-    long long r = i / c8;
-    const int w = static_cast<int>(r % p.W);
-    r /= p.W;
-    const int h = static_cast<int>(r % p.H);
-    const int n = static_cast<int>(r / p.H);
-    float dy[8], x[8], out[8];
-    load8(vptr(p.dy, n, h, w) + c, dy);
-    load8(vptr(p.x, n, h, w) + c, x);
+  float kA[8], kB[8], kC[8];
+  {
     const float* st = p.stats + (static_cast<long long>(n) * p.C + c) * 2;
     const float* bs = p.bstats + (static_cast<long long>(n) * p.C + c) * 2;
 #pragma unroll
@@ -216,12 +295,44 @@ __global__ void __launch_bounds__(kThreads) in_bwd_apply_kernel(const InBwdApply
       const float mean = st[2 * j] * p.inv_count;
       const float var = fmaxf(st[2 * j + 1] * p.inv_count - mean * mean, 0.f);
       const float rstd = rsqrtf(var + p.eps);
-      const float xh = (x[j] - mean) * rstd;
       const float m1 = bs[2 * j] * p.inv_count;
       const float m2 = bs[2 * j + 1] * p.inv_count;
-      out[j] = __ldg(p.gamma + c + j) * rstd * (dy[j] - m1 - xh * m2);
+      const float gr = __ldg(p.gamma + c + j) * rstd;
+      kA[j] = gr;
+      kB[j] = -gr * rstd * m2;
+      kC[j] = gr * (mean * rstd * m2 - m1);
     }
-    store8(vptr_mut(p.dx, n, h, w) + c, out);
+  }
+  constexpr int U = 4;
+  for (int base = pix0 + ln; base < pix1; base += lanes * U) {
+    uint4 dv[U], xv[U];
+    int hh[U], ww[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pix = base + u * lanes;
+      if (pix < pix1) {
+        hh[u] = pix / p.W;
+        ww[u] = pix - hh[u] * p.W;
+        dv[u] = __ldg(reinterpret_cast<const uint4*>(vptr(p.dy, n, hh[u], ww[u]) + c));
+        xv[u] = __ldg(reinterpret_cast<const uint4*>(vptr(p.x, n, hh[u], ww[u]) + c));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pix = base + u * lanes;
+      if (pix >= pix1) continue;
+      const uint32_t dw[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+      const uint32_t xw[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+      float out[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 d = unpack_bf16x2(dw[j]);
+        const float2 x = unpack_bf16x2(xw[j]);
+        out[2 * j] = fmaf(kA[2 * j], d.x, fmaf(kB[2 * j], x.x, kC[2 * j]));
+        out[2 * j + 1] = fmaf(kA[2 * j + 1], d.y, fmaf(kB[2 * j + 1], x.y, kC[2 * j + 1]));
+      }
+      store8(vptr_mut(p.dx, n, hh[u], ww[u]) + c, out);
+    }
   }
 }
 
@@ -465,25 +576,38 @@ inline int grid_for_fixed_c(long long total, int c8) {
 
 }  // namespace
 
+static int pick_pix_per_block(int HW, int N, int lanes) {
+  // >= 4 pixels per thread per pass, and roughly >= 2 blocks per SM
+  int ppb = lanes * 16;
+  while (ppb > lanes * 4 && static_cast<long long>((HW + ppb - 1) / ppb) * N < 2 * 148) ppb /= 2;
+  if (ppb > HW) ppb = HW;
+  return ppb;
+}
+
 void launch_in_apply(const InApplyParams& p, cudaStream_t s) {
-  const long long total = static_cast<long long>(p.N) * p.H * p.W * (p.C / 8);
-  in_apply_kernel<<<grid_for(total), kThreads, 0, s>>>(p);
+  const int HW = p.H * p.W;
+  const int lanes = kThreads / (p.C / 8);
+  const int ppb = pick_pix_per_block(HW, p.N, lanes);
+  dim3 grid((HW + ppb - 1) / ppb, p.N);
+  in_apply_kernel<<<grid, kThreads, 0, s>>>(p, ppb);
 }
 
 void launch_in_bwd_reduce(const InBwdReduceParams& p, cudaStream_t s) {
   const int HW = p.H * p.W;
   const int c8 = p.C / 8;
   const int lanes = kThreads / c8;
-  int pix_per_block = lanes * 16;
-  if (pix_per_block > HW) pix_per_block = HW;
+  const int pix_per_block = pick_pix_per_block(HW, p.N, lanes);
   dim3 grid((HW + pix_per_block - 1) / pix_per_block, p.N);
   const size_t smem = static_cast<size_t>(lanes) * p.C * 2 * sizeof(float);
   in_bwd_reduce_kernel<<<grid, kThreads, smem, s>>>(p, pix_per_block);
 }
 
 void launch_in_bwd_apply(const InBwdApplyParams& p, cudaStream_t s) {
-  const long long total = static_cast<long long>(p.N) * p.H * p.W * (p.C / 8);
-  in_bwd_apply_kernel<<<grid_for(total), kThreads, 0, s>>>(p);
+  const int HW = p.H * p.W;
+  const int lanes = kThreads / (p.C / 8);
+  const int ppb = pick_pix_per_block(HW, p.N, lanes);
+  dim3 grid((HW + ppb - 1) / ppb, p.N);
+  in_bwd_apply_kernel<<<grid, kThreads, 0, s>>>(p, ppb);
 }
 
 void launch_act_bwd(const ActBwdParams& p, cudaStream_t s) {

@@ -113,15 +113,41 @@ void fill_taps(const std::vector<TapT>& taps, Tap* dst, int* n) {
 
 class Plan {
  public:
+  // lane 0 runs on the caller's stream, lane 1 on the plan's side stream; kind 1 = fork
+  // (side waits for main), kind 2 = join (main waits for side). Works under stream capture.
   struct Op {
     std::string name;
     std::function<void(cudaStream_t)> fn;
+    int lane = 0;
+    int kind = 0;
+    cudaEvent_t ev = nullptr;
   };
 
+  ~Plan() {
+    for (auto& o : ops_)
+      if (o.ev) cudaEventDestroy(o.ev);
+    if (side_) cudaStreamDestroy(side_);
+  }
+
   int add(std::string name, std::function<void(cudaStream_t)> fn) {
-    ops_.push_back({std::move(name), std::move(fn)});
+    Op o;
+    o.name = std::move(name);
+    o.fn = std::move(fn);
+    o.lane = lane_;
+    ops_.push_back(std::move(o));
     return static_cast<int>(ops_.size()) - 1;
   }
+  void set_lane(int lane) { lane_ = lane; }
+  int add_sync(std::string name, int kind) {
+    Op o;
+    o.name = std::move(name);
+    o.kind = kind;
+    check(cudaEventCreateWithFlags(&o.ev, cudaEventDisableTiming), "cudaEventCreate");
+    ops_.push_back(std::move(o));
+    return static_cast<int>(ops_.size()) - 1;
+  }
+  int add_fork(std::string name) { return add_sync(std::move(name), 1); }
+  int add_join(std::string name) { return add_sync(std::move(name), 2); }
   int size() const { return static_cast<int>(ops_.size()); }
   std::vector<std::string> names() const {
     std::vector<std::string> n;
@@ -132,8 +158,27 @@ class Plan {
   void run(int begin, int end, uint64_t stream, bool check_each) {
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (end < 0 || end > size()) end = size();
+    if (side_ == nullptr) check(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking), "side stream");
+    bool forked = false;
     for (int i = begin; i < end; ++i) {
-      ops_[i].fn(s);
+      Op& o = ops_[i];
+      if (o.kind == 1) {
+        if (!check_each) {
+          check(cudaEventRecord(o.ev, s), "fork record");
+          check(cudaStreamWaitEvent(side_, o.ev, 0), "fork wait");
+          forked = true;
+        }
+        continue;
+      }
+      if (o.kind == 2) {
+        if (forked) {
+          check(cudaEventRecord(o.ev, side_), "join record");
+          check(cudaStreamWaitEvent(s, o.ev, 0), "join wait");
+          forked = false;
+        }
+        continue;
+      }
+      o.fn((forked && o.lane == 1) ? side_ : s);
       if (check_each) {
         cudaError_t e = cudaStreamSynchronize(s);
         if (e == cudaSuccess) e = cudaGetLastError();
@@ -141,6 +186,13 @@ class Plan {
           throw std::runtime_error("plan op #" + std::to_string(i) + " (" + ops_[i].name +
                                    ") failed: " + cudaGetErrorString(e));
       }
+    }
+    if (forked) {   // range ended inside a forked region: always re-join
+      cudaEvent_t e;
+      check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
+      check(cudaEventRecord(e, side_), "join record");
+      check(cudaStreamWaitEvent(s, e, 0), "join wait");
+      cudaEventDestroy(e);
     }
     check(cudaGetLastError(), "plan launch");
   }
@@ -154,7 +206,7 @@ class Plan {
     for (auto& e : ev) check(cudaEventCreate(&e), "cudaEventCreate");
     check(cudaEventRecord(ev[0], s), "cudaEventRecord");
     for (int i = 0; i < n; ++i) {
-      ops_[begin + i].fn(s);
+      if (ops_[begin + i].kind == 0) ops_[begin + i].fn(s);
       check(cudaEventRecord(ev[i + 1], s), "cudaEventRecord");
     }
     check(cudaStreamSynchronize(s), "cudaStreamSynchronize");
@@ -317,6 +369,8 @@ class Plan {
 
  private:
   std::vector<Op> ops_;
+  int lane_ = 0;
+  cudaStream_t side_ = nullptr;
 };
 
 }  // namespace
@@ -333,6 +387,9 @@ PYBIND11_MODULE(_C, m) {
       .def("names", &Plan::names)
       .def("run", &Plan::run, py::arg("begin") = 0, py::arg("end") = -1, py::arg("stream") = 0,
            py::arg("check_each") = false, py::call_guard<py::gil_scoped_release>())
+      .def("set_lane", &Plan::set_lane)
+      .def("add_fork", &Plan::add_fork)
+      .def("add_join", &Plan::add_join)
       .def("run_timed", &Plan::run_timed, py::arg("begin") = 0, py::arg("end") = -1,
            py::arg("stream") = 0)
       .def("add_conv_gemm", &Plan::add_conv_gemm)

@@ -16,6 +16,7 @@ Schedule (exploits the reference's gradient routing):
 """
 from __future__ import annotations
 
+import os
 from collections import OrderedDict
 from typing import Dict, List, Optional
 
@@ -76,21 +77,43 @@ class StepPlan:
     plan.add_img_prep("prep.x->F1", xi, NULL_VIEW, F.inp[0].view(b), 3, NULL_VIEW, b, S, S)
     plan.add_img_prep("prep.y->F0,Y1", yi, NULL_VIEW, F.inp[0].view(0), 3, Y.inp[0].view(b), b, S, S)
     plan.add_img_prep("prep.y->G1", yi, NULL_VIEW, G.inp[0].view(b), 3, NULL_VIEW, b, S, S)
+    # Two lanes: lane 0 = {G, Y}, lane 1 = {F, X}. Inside a fork/join region the lanes run
+    # on two streams, so one network's tail wave overlaps the other's kernels.
+    two = be.two_lanes
+
+    def fork(tag):
+      if two:
+        plan.add_fork(f"sync.fork.{tag}")
+
+    def join(tag):
+      plan.set_lane(0)
+      if two:
+        plan.add_join(f"sync.join.{tag}")
+
+    def lane(k):
+      plan.set_lane(k if two else 0)
+
     # ---- P2: fake / identity generators (one batched pass each)
-    G.forward(plan, 0, 2 * b)
-    F.forward(plan, 0, 2 * b)
+    fork("fwd")
+    lane(0); G.forward(plan, 0, 2 * b)
+    lane(1); F.forward(plan, 0, 2 * b)
+    join("fwd")
     # ---- P3: fakes -> inputs of the cycle pass and of the discriminators
     plan.add_img_prep("prep.fake_y->F2,Y0", 0, G.inp[-1].view(0), F.inp[0].view(2 * b), 3,
                       Y.inp[0].view(0), b, S, S)
     plan.add_img_prep("prep.fake_x->G2,X0", 0, F.inp[-1].view(0), G.inp[0].view(2 * b), 3,
                       X.inp[0].view(0), b, S, S)
     # ---- P4: cycle pass
-    G.forward(plan, 2 * b, b)
-    F.forward(plan, 2 * b, b)
+    fork("cycle")
+    lane(0); G.forward(plan, 2 * b, b)
+    lane(1); F.forward(plan, 2 * b, b)
+    join("cycle")
     self.marks["cycle_end"] = plan.size()
     # ---- P5: discriminators on [fake | real]
-    X.forward(plan, 0, 2 * b)
-    Y.forward(plan, 0, 2 * b)
+    fork("dis")
+    lane(0); Y.forward(plan, 0, 2 * b)
+    lane(1); X.forward(plan, 0, 2 * b)
+    join("dis")
     # ---- P6: losses (+ their gradients)
     npx = S * S * 3
     nd = hd * wd
@@ -114,16 +137,17 @@ class StepPlan:
       plan.add_mse_loss(f"loss.{n}_fake", D.inp[-1].view(0), 0.0, 0.5 / (nd * gbs), 1.0 / (nd * gbs),
                         sl(f"{n}_loss"), D.gout_final.view(0), b, hd, wd)
     self.marks["test_end"] = plan.size()
-    # ---- P7: adversarial gradient into the fakes (dgrad-only pass through Y / X)
-    Y.backward(plan, 0, b, wgrad=False, input_grad_target=(G.gout_final, 0),
-               gout_view=self.gd_adv["Y"].view(0), gout_is_dy=True)
-    X.backward(plan, 0, b, wgrad=False, input_grad_target=(F.gout_final, 0),
-               gout_view=self.gd_adv["X"].view(0), gout_is_dy=True)
-    for n in ("X", "Y"):
-      e = self.ex[n]
-      plan.add_memset(f"zero.{n}.bstats2", e.bstat_arena.data_ptr(), e.bstat_arena.numel() * 4)
-    # ---- P8/P9: backward + optimizer per network
-    for n in NETS:
+
+    # ---- P7-P9: backward + optimizer. lane 0: Y adversarial dgrad -> G backward -> G update ->
+    # Y backward -> Y update; lane 1: the same for X / F. (sequential when lanes are off,
+    # which is what the NCCL baseline path needs: one all-reduce between bwd and optimizer)
+    def adv(D, gen):
+      e = self.ex[D]
+      e.backward(plan, 0, b, wgrad=False, input_grad_target=(self.ex[gen].gout_final, 0),
+                 gout_view=self.gd_adv[D].view(0), gout_is_dy=True)
+      plan.add_memset(f"zero.{D}.bstats2", e.bstat_arena.data_ptr(), e.bstat_arena.numel() * 4)
+
+    def full(n):
       e = self.ex[n]
       if n in ("G", "F"):
         e.backward(plan, 0, 3 * b, wgrad=True)
@@ -132,9 +156,20 @@ class StepPlan:
       self.marks[f"{n}_bwd_end"] = plan.size()
       be.emit_optimizer(plan, n)
       self.marks[f"{n}_opt_end"] = plan.size()
+
+    if two:
+      fork("bwd")
+      lane(0); adv("Y", "G"); full("G"); full("Y")
+      lane(1); adv("X", "F"); full("F"); full("X")
+      join("bwd")
+    else:
+      adv("Y", "G"); adv("X", "F")
+      for n in NETS:
+        full(n)
     self.marks["end"] = plan.size()
     self.names = plan.names()
-    self.kernels_per_step = sum(1 for nm in self.names if not nm.startswith("zero.") and ".zero" not in nm)
+    self.kernels_per_step = sum(1 for nm in self.names
+                                if not nm.startswith(("zero.", "sync.")) and ".zero" not in nm)
     self.graph: Optional[torch.cuda.CUDAGraph] = None
 
 
@@ -159,13 +194,15 @@ class NativeBackend:
     self.image_size = image_size
     self.lambda_cycle = 10.0
     self.lambda_identity = 5.0
-    import os
     self.use_graph = (os.environ.get("B2_NO_GRAPH", "0") != "1") if use_graph is None else use_graph
     self.world = strategy.world_size
     self.fused = (fused_allreduce in ("auto", "on")) and self.world > 1
+    self.two_lanes = os.environ.get("B2_ONE_STREAM", "0") != "1"
     gen = torch.Generator().manual_seed(seed)
     self.state: Dict[str, NetState] = OrderedDict()
     self.symm = None
+    if self.world > 1 and not (fused_allreduce in ("auto", "on")):
+      self.two_lanes = False   # NCCL baseline path runs plan segments sequentially
     if self.fused:
       from ..parallel.fused_allreduce import SymmetricBuffers
       try:
@@ -175,6 +212,7 @@ class NativeBackend:
           raise
         print(f"[native] fused all-reduce unavailable ({type(e).__name__}: {e}); using NCCL path")
         self.fused = False
+        self.two_lanes = False
     for n in NETS:
       logical = oracle_net.init_params(specs[n], generator=gen)
       gbuf = wbuf = None
