@@ -1,0 +1,89 @@
+"""Micro-benchmark of the hot GEMM kernels on the residual-block shape
+(3x3, 256->256 channels, 64x64, reflect pad): forward conv, flat dgrad (MN-major B),
+split-K wgrad. Device-timed with CUDA events, L2 flushed between iterations,
+reports TFLOP/s and the fraction of the measured cuBLAS bf16 peak (MEASURED_PEAKS.json).
+
+    python tools/kernel_bench.py [--images 12] [--iters 20] [--only fwd|dgrad|wgrad]
+"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from tf2_cyclegan_b200.engine import native_ops as no
+from tf2_cyclegan_b200.ops import native as nv
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--images", type=int, default=12)
+ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--only", default="")
+ap.add_argument("--no_flush", action="store_true")
+a = ap.parse_args()
+C = nv.load()
+n, h, c = a.images, 64, 256
+peaks = {}
+try:
+  peaks = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))
+except Exception:
+  pass
+peak = peaks.get("bf16_tflops", 1590.0)
+torch.manual_seed(0)
+x = nv.Buf(n, h, h, c, halo=1)
+x.t.copy_(torch.randn_like(x.t.float()).to(torch.bfloat16))
+w2 = (torch.randn(c, 9 * c, device="cuda") * 0.05).to(torch.bfloat16)
+out = nv.Buf(n, h, h, c)
+stats = torch.zeros(n, c, 2, device="cuda")
+dy = nv.Buf(n, h, h, c, halo=1)
+dy.interior().copy_(torch.randn(n, h, h, c, device="cuda").to(torch.bfloat16))
+dxp = nv.Buf(n, h, h, c, halo=1)
+dw = torch.zeros(c, 9 * c, device="cuda")
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+plans = {}
+bw, bh = nv.tile_shape(h, h)
+p = C.Plan()
+no.add_conv(p, "fwd", [x.tmap_padded(bw, bh)], no.taps_conv(3, c), c, w2, out.view(), h, h, n, c,
+            stats=stats.data_ptr())
+plans["fwd"] = (p, 2.0 * n * h * h * 9 * c * c)
+P = h + 2
+rows = n * P * P
+p = C.Plan()
+taps = [(0, 0, (1 - r) * P + (1 - s), 0, (r * 3 + s) * c) for r in range(3) for s in range(3)]
+no.add_conv_flat(p, "dgrad", dy.tmap_flat(), taps, c, w2, dxp.ptr(padded=True), c, rows, c, b_mn=True)
+plans["dgrad"] = (p, 2.0 * n * h * h * 9 * c * c)
+kbw, kbh = nv.tile_shape(h, h, 64)
+p = C.Plan()
+no.add_wgrad(p, "wgrad", dy.tmap_interior(kbw, kbh), [x.tmap_padded(kbw, kbh)], no.taps_conv(3, c),
+             h // kbw, h // kbh, kbw, kbh, n, c, c, dw.data_ptr(), 9 * c)
+plans["wgrad"] = (p, 2.0 * n * h * h * 9 * c * c)
+
+s = torch.cuda.current_stream().cuda_stream
+res = {}
+for name, (plan, flops) in plans.items():
+  if a.only and a.only != name:
+    continue
+  for _ in range(3):
+    plan.run(0, -1, s, False)
+  torch.cuda.synchronize()
+  ts = []
+  for _ in range(a.iters):
+    if not a.no_flush:
+      flush.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    plan.run(0, -1, s, False)
+    e1.record()
+    torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1))
+  ts.sort()
+  ms = ts[len(ts) // 2]
+  tf = flops / ms / 1e9
+  res[name] = {"ms_median": ms, "ms_min": ts[0], "tflops": tf, "frac_of_measured_bf16_peak": tf / peak}
+  print(f"{name:6s} images={n} median {ms * 1e3:8.1f} us  {tf:7.1f} TFLOP/s  "
+        f"{100 * tf / peak:5.1f}% of measured cuBLAS bf16 peak ({peak:.0f})")
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump({"shape": f"3x3 conv 256->256 @64x64 x{n} images", "l2_flush": not a.no_flush, "results": res},
+          open("gpurun_out/kernel_bench.json", "w"), indent=1)
