@@ -15,7 +15,9 @@
 // Warp roles (256 threads): warp 0 = TMA producer (runs ahead across tiles), warp 1 =
 // MMA issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM lane quarter = warp % 4).
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty x2 (MMA <-> epilogue).
-#include "conv_gemm.cuh"
+#include <stdlib.h>
+
+#include "conv_epilogue.cuh"
 
 namespace b2 {
 
@@ -155,11 +157,6 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, int num_images) {
     // ============================== epilogue ==============================
     const int e = threadIdx.x - 128;          // 0..127 == tile row == TMEM lane
     const int ew = warp - 4;                  // TMEM lane quarter
-    constexpr int CN = Cfg::kChunkN;
-    constexpr int CH = Cfg::kChunks16;
-    constexpr int RG = Cfg::kRowGroups;
-    constexpr bool SWZ = (CH >= 8);
-    constexpr int ROW_BYTES = CN * 2;
     uint32_t tile_i = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
       const int mt = tile / n_tiles;
@@ -175,132 +172,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, int num_images) {
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * Cfg::kAccCols + (static_cast<uint32_t>(ew * 32) << 16);
 
-#pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += CN) {
-        // ---- TMEM -> registers -> bias / activation -> bf16 -> staging (swizzled rows)
-        if constexpr (CN >= 32) {
-#pragma unroll
-          for (int cc = 0; cc < CN; cc += 32) {
-            uint32_t r[32];
-            tmem_ld_32x32(taddr + c0 + cc, r);
-            tmem_ld_wait();
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = __uint_as_float(r[j]);
-              if (p.bias != nullptr && n0 + c0 + cc + j < p.cout) x += __ldg(p.bias + n0 + c0 + cc + j);
-              v[j] = apply_act(x, p.act);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int ci = (cc >> 3) + q;
-              const int phys = SWZ ? (ci ^ (e & 7)) : ci;
-              uint4 pk;
-              pk.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-              pk.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-              pk.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-              pk.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-              *reinterpret_cast<uint4*>(stage_buf + e * ROW_BYTES + phys * 16) = pk;
-            }
-          }
-        } else {
-          uint32_t r[16];
-          tmem_ld_32x16(taddr + c0, r);
-          tmem_ld_wait();
-          float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float x = __uint_as_float(r[j]);
-            if (p.bias != nullptr && n0 + c0 + j < p.cout) x += __ldg(p.bias + n0 + c0 + j);
-            v[j] = apply_act(x, p.act);
-          }
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            uint4 pk;
-            pk.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-            pk.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-            pk.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-            pk.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-            *reinterpret_cast<uint4*>(stage_buf + e * ROW_BYTES + q * 16) = pk;
-          }
-        }
-        if (c0 + CN >= BLOCK_N) {     // all TMEM reads of this tile are done: release the accumulator
-          tc_fence_before();
-          mbar_arrive(&tmem_empty_bar[acc]);
-        }
-        named_bar_sync(1, 128);
-
-        // ---- InstanceNorm partial statistics (sum, sum of squares per channel)
-        if (p.stats != nullptr) {
-          const int ci = e % CH;
-          const int rg = e / CH;
-          float s[8], q[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
-#pragma unroll 4
-          for (int r = rg; r < 128; r += RG) {
-            const int phys = SWZ ? (ci ^ (r & 7)) : ci;
-            const uint4 pk = *reinterpret_cast<const uint4*>(stage_buf + r * ROW_BYTES + phys * 16);
-            const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = unpack_bf16x2(w[j]);
-              s[2 * j] += f.x; q[2 * j] += f.x * f.x;
-              s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            red[(rg * CN + ci * 8 + j) * 2 + 0] = s[j];
-            red[(rg * CN + ci * 8 + j) * 2 + 1] = q[j];
-          }
-          named_bar_sync(2, 128);
-          if (e < CN && n0 + c0 + e < p.cout) {
-            float ss = 0.f, qq = 0.f;
-#pragma unroll 8
-            for (int g = 0; g < RG; ++g) {
-              ss += red[(g * CN + e) * 2 + 0];
-              qq += red[(g * CN + e) * 2 + 1];
-            }
-            float* dst = p.stats + (static_cast<long long>(img) * p.cout + n0 + c0 + e) * 2;
-            atomicAdd(dst, ss);
-            atomicAdd(dst + 1, qq);
-          }
-        }
-
-        // ---- coalesced store of the staged chunk
-        const int n_valid = min(CN, p.cout - n0 - c0);
-        if (n_valid == CN) {
-          constexpr int RPI = 32 / CH;              // rows per warp instruction
-#pragma unroll 2
-          for (int itr = 0; itr < 32 / RPI; ++itr) {
-            const int r = ew * 32 + itr * RPI + lane / CH;
-            const int cc = lane % CH;
-            const int wl = r % p.bw, hl = r / p.bw;
-            if (w0 + wl < p.w_limit) {
-              __nv_bfloat16* dst = p.out + img * p.out_sn + (h0 + hl) * p.out_sh +
-                                   (w0 + wl) * p.out_sw + n0 + c0;
-              const int phys = SWZ ? (cc ^ (r & 7)) : cc;
-              const uint4 pk = *reinterpret_cast<const uint4*>(stage_buf + r * ROW_BYTES + phys * 16);
-              *reinterpret_cast<uint4*>(dst + cc * 8) = pk;
-            }
-          }
-        } else if (n_valid > 0) {
-          const int r = e;
-          const int wl = r % p.bw, hl = r / p.bw;
-          if (w0 + wl < p.w_limit) {
-            __nv_bfloat16* dst = p.out + img * p.out_sn + (h0 + hl) * p.out_sh +
-                                 (w0 + wl) * p.out_sw + n0 + c0;
-            for (int c = 0; c < n_valid; ++c) {
-              const int cc = c >> 3;
-              const int phys = SWZ ? (cc ^ (r & 7)) : cc;
-              dst[c] = *reinterpret_cast<const __nv_bfloat16*>(stage_buf + r * ROW_BYTES + phys * 16 +
-                                                                (c & 7) * 2);
-            }
-          }
-        }
-        named_bar_sync(1, 128);   // staging / red buffers are reused by the next chunk
-      }
+      conv_epilogue_tile<BLOCK_N>(p, stage_buf, red, taddr, img, h0, w0, n0, e, ew, lane, true,
+                                  [&]() { mbar_arrive(&tmem_empty_bar[acc]); });
     }
   }
 
@@ -334,8 +207,24 @@ static void launch_t(const ConvGemmParams& p, int num_images, cudaStream_t strea
   conv_gemm_kernel<BLOCK_N, B_MN><<<grid, 256, Cfg::kSmemBytes, stream>>>(p, num_images);
 }
 
+bool launch_conv_gemm_2cta(const ConvGemmParams& p, int block_n, bool b_mn_major, int num_images,
+                           cudaStream_t stream);
+
+static bool use_2cta() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2_2CTA");
+    v = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 void launch_conv_gemm(const ConvGemmParams& p, int block_n, bool b_mn_major, int num_images,
                       cudaStream_t stream) {
+  // wide layers: CTA pairs (cta_group::2) halve the weight-tile traffic per SM
+  if (block_n >= 128 && use_2cta() && p.tiles_w * p.tiles_h * num_images >= 2 &&
+      launch_conv_gemm_2cta(p, block_n, b_mn_major, num_images, stream))
+    return;
   if (!b_mn_major) {
     switch (block_n) {
       case 16: return launch_t<16, false>(p, num_images, stream);
