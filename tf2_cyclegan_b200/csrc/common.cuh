@@ -301,11 +301,15 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LEAKY = 2, ACT_TANH = 3 };
+// Negative-side slope of the piecewise-linear activations (none: 1, relu: 0, leaky: 0.2).
+// Hoist this out of element loops: a per-element switch compiles to an indirect branch.
+__device__ __forceinline__ float act_slope(int act) {
+  return act == ACT_RELU ? 0.f : (act == ACT_LEAKY ? 0.2f : 1.f);
+}
+__device__ __forceinline__ float apply_slope(float v, float slope) { return v > 0.f ? v : v * slope; }
 __device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == ACT_RELU) return fmaxf(v, 0.f);
-  if (act == ACT_LEAKY) return v > 0.f ? v : 0.2f * v;
   if (act == ACT_TANH) return tanhf(v);
-  return v;
+  return apply_slope(v, act_slope(act));
 }
 
 }  // namespace b2

@@ -27,6 +27,9 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, uint
   constexpr int RG = EpiCfg<BLOCK_N>::kRowGroups;
   constexpr bool SWZ = (CH >= 8);
   constexpr int ROW_BYTES = CN * 2;
+  const bool has_bias = p.bias != nullptr;
+  const bool is_tanh = p.act == ACT_TANH;
+  const float slope = act_slope(p.act);
 #pragma unroll 1
   for (int c0 = 0; c0 < BLOCK_N; c0 += CN) {
     // ---- TMEM -> registers -> bias / activation -> bf16 -> staging (swizzled rows)
@@ -38,10 +41,18 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, uint
         tmem_ld_wait();
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[j]);
-          if (p.bias != nullptr && n0 + c0 + cc + j < p.cout) x += __ldg(p.bias + n0 + c0 + cc + j);
-          v[j] = apply_act(x, p.act);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (has_bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + c0 + cc + j < p.cout) v[j] += __ldg(p.bias + n0 + c0 + cc + j);
+        }
+        if (is_tanh) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+        } else if (slope != 1.f) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_slope(v[j], slope);
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -61,10 +72,18 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, uint
       tmem_ld_wait();
       float v[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float x = __uint_as_float(r[j]);
-        if (p.bias != nullptr && n0 + c0 + j < p.cout) x += __ldg(p.bias + n0 + c0 + j);
-        v[j] = apply_act(x, p.act);
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+      if (has_bias) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (n0 + c0 + j < p.cout) v[j] += __ldg(p.bias + n0 + c0 + j);
+      }
+      if (is_tanh) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = tanhf(v[j]);
+      } else if (slope != 1.f) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = apply_slope(v[j], slope);
       }
 #pragma unroll
       for (int q = 0; q < 2; ++q) {

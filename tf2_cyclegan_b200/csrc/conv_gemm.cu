@@ -21,6 +21,8 @@
 
 namespace b2 {
 
+int dbg_flag();
+
 template <int BLOCK_N>
 struct GemmCfg {
   static constexpr int kABytes = 128 * 128;        // 128 pixels x 64 bf16
@@ -42,7 +44,7 @@ struct GemmCfg {
 
 template <int BLOCK_N, bool B_MN>
 __global__ void __launch_bounds__(256, 1)
-conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, int num_images) {
+conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int nstages, int dbg) {
   using Cfg = GemmCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms need 1024-byte alignment
@@ -102,15 +104,22 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, int num_images) {
           const Tap tap = p.taps[t];
           const CUtensorMap* amap = &p.tmA[tap.map];
           for (int cb = 0; cb < p.cin_blocks; ++cb, ++it) {
-            const int s = it % Cfg::kStages;
-            const uint32_t ph = (it / Cfg::kStages) & 1;
+            const int s = it % nstages;
+            const uint32_t ph = (it / nstages) & 1;
             mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* sa = smem + s * Cfg::kStageBytes;
             uint8_t* sb = sa + Cfg::kABytes;
+            if (dbg == 3) { mbar_arrive(&full_bar[s]); continue; }
             mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
             tma_load_4d(sa, amap, &full_bar[s], cb * 64, w0 + tap.dw, h0 + tap.dh, img + tap.dn);
             if constexpr (!B_MN) {
-              tma_load_2d(sb, &p.tmB, &full_bar[s], tap.bk + cb * 64, n0);
+              if constexpr (BLOCK_N >= 128) {   // the host encodes half-height boxes for wide tiles
+                tma_load_2d(sb, &p.tmB, &full_bar[s], tap.bk + cb * 64, n0);
+                tma_load_2d(sb + (BLOCK_N / 2) * 128, &p.tmB, &full_bar[s], tap.bk + cb * 64,
+                            n0 + BLOCK_N / 2);
+              } else {
+                tma_load_2d(sb, &p.tmB, &full_bar[s], tap.bk + cb * 64, n0);
+              }
             } else {
 #pragma unroll
               for (int j = 0; j < BLOCK_N / 64; ++j)
@@ -132,8 +141,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, int num_images) {
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * Cfg::kAccCols;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % Cfg::kStages;
-          const uint32_t ph = (it / Cfg::kStages) & 1;
+          const int s = it % nstages;
+          const uint32_t ph = (it / nstages) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
@@ -142,6 +151,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, int num_images) {
           const uint64_t db = B_MN ? make_desc_mnmajor(sb, 64) : make_desc_kmajor(sb);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
+            if (dbg == 2) break;
             // K advance of 16 elements: +32 B inside the swizzle row (K-major),
             // +16 rows * 128 B (MN-major); descriptor address field is in 16-byte units
             const uint64_t da_k = da + static_cast<uint64_t>(k * 2);
@@ -172,6 +182,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, int num_images) {
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * Cfg::kAccCols + (static_cast<uint32_t>(ew * 32) << 16);
 
+      if (dbg == 1) { tc_fence_before(); mbar_arrive(&tmem_empty_bar[acc]); continue; }
       conv_epilogue_tile<BLOCK_N>(p, stage_buf, red, taddr, img, h0, w0, n0, e, ew, lane, true,
                                   [&]() { mbar_arrive(&tmem_empty_bar[acc]); });
     }
@@ -203,12 +214,32 @@ static void launch_t(const ConvGemmParams& p, int num_images, cudaStream_t strea
     configured = true;
   }
   const int total = p.tiles_w * p.tiles_h * num_images * ((p.cout + BLOCK_N - 1) / BLOCK_N);
-  const int grid = total < num_sms() ? total : num_sms();
-  conv_gemm_kernel<BLOCK_N, B_MN><<<grid, 256, Cfg::kSmemBytes, stream>>>(p, num_images);
+  static int dbg_stages = -1, dbg_grid = -1;
+  if (dbg_stages < 0) {
+    const char* e = getenv("B2_STAGES");
+    dbg_stages = e ? atoi(e) : 0;
+    e = getenv("B2_GRID");
+    dbg_grid = e ? atoi(e) : 0;
+  }
+  int nst = Cfg::kStages;
+  if (dbg_stages > 0 && dbg_stages < nst) nst = dbg_stages;
+  int cap = num_sms();
+  if (dbg_grid > 0 && dbg_grid < cap) cap = dbg_grid;
+  const int grid = total < cap ? total : cap;
+  conv_gemm_kernel<BLOCK_N, B_MN><<<grid, 256, Cfg::kSmemBytes, stream>>>(p, num_images, nst, dbg_flag());
 }
 
 bool launch_conv_gemm_2cta(const ConvGemmParams& p, int block_n, bool b_mn_major, int num_images,
                            cudaStream_t stream);
+
+int dbg_flag() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2_DBG");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
 
 static bool use_2cta() {
   static int v = -1;

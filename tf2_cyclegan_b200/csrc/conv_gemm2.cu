@@ -15,6 +15,8 @@
 
 namespace b2 {
 
+int dbg_flag();
+
 template <int BLOCK_N>
 struct Gemm2Cfg {
   static constexpr int kHalfN = BLOCK_N / 2;
@@ -34,7 +36,7 @@ struct Gemm2Cfg {
 
 template <int BLOCK_N, bool B_MN>
 __global__ void __launch_bounds__(256, 1)
-conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p, int num_images) {
+conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int dbg) {
   using Cfg = Gemm2Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -146,6 +148,7 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p, int num_images) {
           const uint64_t db = B_MN ? make_desc_mnmajor(sb, 64) : make_desc_kmajor(sb);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
+            if (dbg == 2) break;
             const uint64_t da_k = da + static_cast<uint64_t>(k * 2);
             const uint64_t db_k = db + static_cast<uint64_t>(B_MN ? k * 128 : k * 2);
             umma_bf16_2sm(tmem_d, da_k, db_k, idesc, (kb | k) != 0 ? 1u : 0u);
@@ -168,6 +171,7 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p, int num_images) {
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * Cfg::kAccCols + (static_cast<uint32_t>(ew * 32) << 16);
+      if (dbg == 1) { tc_fence_before(); mbar_arrive_cluster(&tmem_empty_bar[acc], 0); continue; }
       conv_epilogue_tile<BLOCK_N>(p, stage_buf, red, taddr, img, h0, w0, n0, e, ew, lane, mt < m_tiles,
                                   [&]() { mbar_arrive_cluster(&tmem_empty_bar[acc], 0); });
     }
@@ -214,7 +218,7 @@ static void launch2_t(const ConvGemmParams& p, int num_images, cudaStream_t stre
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, conv_gemm2_kernel<BLOCK_N, B_MN>, p, num_images);
+  cudaLaunchKernelEx(&cfg, conv_gemm2_kernel<BLOCK_N, B_MN>, p, num_images, dbg_flag());
 }
 
 bool launch_conv_gemm_2cta(const ConvGemmParams& p, int block_n, bool b_mn_major, int num_images,

@@ -46,10 +46,8 @@ __device__ __forceinline__ int reflect_set(int i, int n, int p, int (&out)[2]) {
   return cnt;
 }
 
-__device__ __forceinline__ float act_grad_from_pre(float y, int act) {
-  if (act == ACT_RELU) return y > 0.f ? 1.f : 0.f;
-  if (act == ACT_LEAKY) return y > 0.f ? 1.f : 0.2f;
-  return 1.f;
+__device__ __forceinline__ float act_grad_from_pre(float y, float slope) {
+  return y > 0.f ? 1.f : slope;
 }
 
 // gradient gather with optional reflect-fold (sum of the halo positions that mirror (h, w))
@@ -103,6 +101,7 @@ __global__ void __launch_bounds__(kThreads, 2) in_apply_kernel(const InApplyPara
     for (int j = 0; j < 8; ++j) { ca[j] = 1.f; cb[j] = 0.f; }
   }
   const bool has_skip = p.skip.p != nullptr;
+  const float slope = act_slope(p.act);
   constexpr int U = 4;
   for (int base = pix0 + ln; base < pix1; base += lanes * U) {
     uint4 xv[U], sv[U];
@@ -127,8 +126,8 @@ __global__ void __launch_bounds__(kThreads, 2) in_apply_kernel(const InApplyPara
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 t = unpack_bf16x2(xw[j]);
-        v[2 * j] = apply_act(fmaf(t.x, ca[2 * j], cb[2 * j]), p.act);
-        v[2 * j + 1] = apply_act(fmaf(t.y, ca[2 * j + 1], cb[2 * j + 1]), p.act);
+        v[2 * j] = apply_slope(fmaf(t.x, ca[2 * j], cb[2 * j]), slope);
+        v[2 * j + 1] = apply_slope(fmaf(t.y, ca[2 * j + 1], cb[2 * j + 1]), slope);
         if (has_skip) {
           const float2 k = unpack_bf16x2(sw[j]);
           v[2 * j] += k.x;
@@ -183,6 +182,7 @@ __global__ void __launch_bounds__(kThreads, 2) in_bwd_reduce_kernel(const InBwdR
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
 
   const bool has_g2 = p.g2.p != nullptr;
+  const float slope = act_slope(p.act);
   constexpr int U = 4;
   for (int base = pix0 + ln; base < pix1; base += lanes * U) {
     uint4 gv[U], g2v[U], xv[U];
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kThreads, 2) in_bwd_reduce_kernel(const InBwdR
             const int jj = 2 * j + q;
             const float xh = (xs[q] - mean[jj]) * rstd[jj];
             const float y = xh * gam[jj] + bet[jj];
-            g[jj] *= act_grad_from_pre(y, p.act);
+            g[jj] *= act_grad_from_pre(y, slope);
             const float gq = __bfloat162float(__float2bfloat16(g[jj]));   // stats of the stored value
             s1[jj] += gq;
             s2[jj] += gq * xh;
@@ -347,6 +347,8 @@ __global__ void __launch_bounds__(kThreads) act_bwd_kernel(const ActBwdParams p)
 #pragma unroll
   for (int j = 0; j < 8; ++j) bacc[j] = 0.f;
   int my_c = -1;
+  const bool is_tanh = p.act == ACT_TANH;
+  const float slope = act_slope(p.act);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % c8) * 8;
@@ -360,10 +362,7 @@ __global__ void __launch_bounds__(kThreads) act_bwd_kernel(const ActBwdParams p)
     load8(vptr(p.out, n, h, w) + c, o);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float d = 1.f;
-      if (p.act == ACT_TANH) d = 1.f - o[j] * o[j];
-      else if (p.act == ACT_LEAKY) d = o[j] > 0.f ? 1.f : 0.2f;
-      else if (p.act == ACT_RELU) d = o[j] > 0.f ? 1.f : 0.f;
+      const float d = is_tanh ? 1.f - o[j] * o[j] : (o[j] > 0.f ? 1.f : slope);
       g[j] = (c + j < p.c_valid) ? g[j] * d : 0.f;
       bacc[j] += __bfloat162float(__float2bfloat16(g[j]));
     }

@@ -146,7 +146,9 @@ def wmat_tmap(w2: torch.Tensor, block_n: int, mn_major: bool) -> bytes:
   """Weights as a [rows, K] bf16 matrix. K-major: box {64, block_n};
   MN-major use (B[k][n] = w2[k, n]): box {64, 64}."""
   rows, k = w2.shape
-  box = [64, 64] if mn_major else [64, block_n]
+  # wide K-major tiles are fetched as two half-height boxes so that the same descriptor serves
+  # the 1-CTA kernel (two loads) and the cta_group::2 kernel (one half per CTA)
+  box = [64, 64] if mn_major else [64, block_n // 2 if block_n >= 128 else block_n]
   return tmap(w2.data_ptr(), [k, rows], [k], box)
 
 
