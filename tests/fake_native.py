@@ -25,8 +25,10 @@ class FakePlan:
     return len(self.ops) - 1
 
   def add_conv_gemm(self, name, a_maps, b_map, taps, cin_blocks, tiles_w, tiles_h, bw, bh, w_limit,
-                    out, sn, sh, sw, cout, bias, act, stats, block_n, b_mn, num_images):
-    assert bw * bh == 128 and 1 <= len(a_maps) <= 4 and 1 <= len(taps) <= 52
+                    out, sn, sh, sw, cout, bias, act, stats, block_n, b_mn, num_images, phases):
+    assert bw * bh == 128 and 1 <= len(a_maps) <= 4 and 1 <= len(taps) <= 52 and len(phases) <= 4
+    if phases:
+      assert sum(c for _, c, _ in phases) == len(taps) and all(c >= 1 for _, c, _ in phases)
     assert cin_blocks >= 1 and tiles_w >= 1 and tiles_h >= 1 and num_images >= 1
     assert block_n in (16, 64, 128, 256) and (not b_mn or block_n >= 64)
     for t in taps:
@@ -47,9 +49,12 @@ class FakePlan:
     assert out % 16 == 0 or cout < 8
     return self._add("conv_gemm", name, len(taps), cout, block_n, b_mn, num_images)
 
-  def add_wgrad(self, name, dy_map, a_maps, taps, ktw, kth, kbw, kbh, nimg, cin, cout, dw, ldw, block_n, ksplit):
+  def add_wgrad(self, name, dy_maps, a_maps, taps, ktw, kth, kbw, kbh, nimg, cin, cout, dw, ldw, block_n, ksplit):
     assert kbw * kbh == 64 and ksplit >= 1 and block_n in (64, 128, 256)
-    assert decode(dy_map)["box"][:3] == [64, kbw, kbh]
+    for m in dy_maps:
+      assert decode(m)["box"][:3] == [64, kbw, kbh]
+    for t in taps:
+      assert 0 <= t[1] < len(dy_maps) and 0 <= t[0] < len(a_maps)
     for m in a_maps:
       assert decode(m)["box"][:3] == [64, kbw, kbh]
     for t in taps:

@@ -126,11 +126,10 @@ def test_conv_transpose_phases():
   stats = torch.zeros(n, cout, 2, device="cuda")
   bw, bh = nv.tile_shape(h, h)
   plan = C.Plan()
-  for a in (0, 1):
-    for b in (0, 1):
-      view = (out.ptr(0, a, b), out.sn, 2 * out.sh, 2 * out.sw)
-      no.add_conv(plan, f"up{a}{b}", [xin.tmap_interior(bw, bh)], no.taps_convT_phase(a, b, cin), cin,
-                  w2, view, h, h, n, cout, stats=stats.data_ptr())
+  view = (out.ptr(0), out.sn, 2 * out.sh, 2 * out.sw)
+  phases = [(no.taps_convT_phase(a, b, cin), a * out.sh + b * out.sw) for a in (0, 1) for b in (0, 1)]
+  no.add_conv(plan, "up", [xin.tmap_interior(bw, bh)], [], cin, w2, view, h, h, n, cout,
+              stats=stats.data_ptr(), phases=phases)
   run(plan)
   ref = O.conv2d_transpose(x, kern, 2)
   assert rel_err(out.t, ref) < 1e-2

@@ -95,6 +95,18 @@ __device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, const void* 
       "r"(smem_u32(src)), "r"(c0), "r"(c1)
       : "memory");
 }
+// smem -> global bulk reduction (fp32 add) executed by the TMA engine at L2
+__device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const void* ssrc, uint32_t bytes) {
+  asm volatile(
+      "cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst),
+      "r"(smem_u32(ssrc)), "r"(bytes)
+      : "memory");
+}
+__device__ __forceinline__ float fast_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void tma_store_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }

@@ -18,7 +18,7 @@ struct EpiCfg {
 // Called by the 128 epilogue threads (e = TMEM lane = tile row). `release` is invoked once by
 // every thread right after its last TMEM read (arrive on the tmem-empty barrier).
 template <int BLOCK_N, class Release>
-__device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, uint8_t* stage_buf,
+__device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, __nv_bfloat16* out_base, uint8_t* stage_buf,
                                                    float* red, uint32_t taddr, int img, int h0,
                                                    int w0, int n0, int e, int ew, int lane,
                                                    bool tile_valid, Release release) {
@@ -49,7 +49,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, uint
         }
         if (is_tanh) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+          for (int j = 0; j < 32; ++j) v[j] = fast_tanh(v[j]);
         } else if (slope != 1.f) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = apply_slope(v[j], slope);
@@ -80,7 +80,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, uint
       }
       if (is_tanh) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = tanhf(v[j]);
+        for (int j = 0; j < 16; ++j) v[j] = fast_tanh(v[j]);
       } else if (slope != 1.f) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = apply_slope(v[j], slope);
@@ -149,7 +149,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, uint
         const int cc = lane % CH;
         const int wl = r % p.bw, hl = r / p.bw;
         if (w0 + wl < p.w_limit) {
-          __nv_bfloat16* dst = p.out + img * p.out_sn + (h0 + hl) * p.out_sh +
+          __nv_bfloat16* dst = out_base + img * p.out_sn + (h0 + hl) * p.out_sh +
                                (w0 + wl) * p.out_sw + n0 + c0;
           const int phys = SWZ ? (cc ^ (r & 7)) : cc;
           const uint4 pk = *reinterpret_cast<const uint4*>(stage_buf + r * ROW_BYTES + phys * 16);
@@ -160,7 +160,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, uint
       const int r = e;
       const int wl = r % p.bw, hl = r / p.bw;
       if (w0 + wl < p.w_limit) {
-        __nv_bfloat16* dst = p.out + img * p.out_sn + (h0 + hl) * p.out_sh +
+        __nv_bfloat16* dst = out_base + img * p.out_sn + (h0 + hl) * p.out_sh +
                              (w0 + wl) * p.out_sw + n0 + c0;
         for (int c = 0; c < n_valid; ++c) {
           const int cc = c >> 3;

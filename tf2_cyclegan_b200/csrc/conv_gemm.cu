@@ -64,8 +64,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int n
   const int tiles_per_img = p.tiles_w * p.tiles_h;
   const int m_tiles = tiles_per_img * num_images;
   const int n_tiles = (p.cout + BLOCK_N - 1) / BLOCK_N;
-  const int total_tiles = m_tiles * n_tiles;
-  const int num_kb = p.num_taps * p.cin_blocks;
+  const int tiles_per_phase = m_tiles * n_tiles;
+  const int total_tiles = tiles_per_phase * p.num_phases;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmB);
@@ -93,14 +93,17 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int n
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / n_tiles;
-        const int n0 = (tile - mt * n_tiles) * BLOCK_N;
+        const int phase = tile / tiles_per_phase;
+        const int tp = tile - phase * tiles_per_phase;
+        const int mt = tp / n_tiles;
+        const int n0 = (tp - mt * n_tiles) * BLOCK_N;
         const int img = mt / tiles_per_img;
         const int t_in = mt - img * tiles_per_img;
         const int th = t_in / p.tiles_w;
         const int w0 = (t_in - th * p.tiles_w) * p.bw;
         const int h0 = th * p.bh;
-        for (int t = 0; t < p.num_taps; ++t) {
+        const int t_begin = p.phase_tap_begin[phase], t_end = t_begin + p.phase_tap_count[phase];
+        for (int t = t_begin; t < t_end; ++t) {
           const Tap tap = p.taps[t];
           const CUtensorMap* amap = &p.tmA[tap.map];
           for (int cb = 0; cb < p.cin_blocks; ++cb, ++it) {
@@ -135,6 +138,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int n
       constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, B_MN ? 1 : 0);
       uint32_t it = 0, tile_i = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
+        const int num_kb = p.phase_tap_count[tile / tiles_per_phase] * p.cin_blocks;
         const uint32_t acc = tile_i & 1;
         const uint32_t acc_ph = (tile_i >> 1) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);   // epilogue has drained this accumulator
@@ -169,8 +173,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int n
     const int ew = warp - 4;                  // TMEM lane quarter
     uint32_t tile_i = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
-      const int mt = tile / n_tiles;
-      const int n0 = (tile - mt * n_tiles) * BLOCK_N;
+      const int phase = tile / tiles_per_phase;
+      const int tp = tile - phase * tiles_per_phase;
+      const int mt = tp / n_tiles;
+      const int n0 = (tp - mt * n_tiles) * BLOCK_N;
       const int img = mt / tiles_per_img;
       const int t_in = mt - img * tiles_per_img;
       const int th = t_in / p.tiles_w;
@@ -183,7 +189,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int n
       const uint32_t taddr = tmem_base + acc * Cfg::kAccCols + (static_cast<uint32_t>(ew * 32) << 16);
 
       if (dbg == 1) { tc_fence_before(); mbar_arrive(&tmem_empty_bar[acc]); continue; }
-      conv_epilogue_tile<BLOCK_N>(p, stage_buf, red, taddr, img, h0, w0, n0, e, ew, lane, true,
+      conv_epilogue_tile<BLOCK_N>(p, p.out + p.phase_out_off[phase], stage_buf, red, taddr, img, h0, w0, n0, e, ew, lane, true,
                                   [&]() { mbar_arrive(&tmem_empty_bar[acc]); });
     }
   }
@@ -213,7 +219,7 @@ static void launch_t(const ConvGemmParams& p, int num_images, cudaStream_t strea
                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     configured = true;
   }
-  const int total = p.tiles_w * p.tiles_h * num_images * ((p.cout + BLOCK_N - 1) / BLOCK_N);
+  const int total = p.tiles_w * p.tiles_h * num_images * ((p.cout + BLOCK_N - 1) / BLOCK_N) * p.num_phases;
   static int dbg_stages = -1, dbg_grid = -1;
   if (dbg_stages < 0) {
     const char* e = getenv("B2_STAGES");

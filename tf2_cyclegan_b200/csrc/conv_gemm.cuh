@@ -17,6 +17,8 @@ struct Tap {
   int32_t bk;
 };
 
+constexpr int kMaxPhases = 4;   // sub-pixel phases of a transposed conv share one launch
+
 struct ConvGemmParams {
   CUtensorMap tmA[kMaxAMaps];   // bf16 [.., C] views, box {64, bw, bh, 1}, SWIZZLE_128B
   CUtensorMap tmB;              // bf16 weights, box {64, BLOCK_N} (K-major) or {64, 64} (MN-major)
@@ -29,6 +31,10 @@ struct ConvGemmParams {
   __nv_bfloat16* out;           // NHWC-like: out[n*sn + h*sh + w*sw + c]
   long long out_sn, out_sh, out_sw;
   int cout;                     // valid output channels
+  int num_phases;               // >= 1; tile t belongs to phase t / (m_tiles * n_tiles)
+  int phase_tap_begin[kMaxPhases];
+  int phase_tap_count[kMaxPhases];
+  long long phase_out_off[kMaxPhases];   // element offset added to `out`
   const float* bias;            // [cout] or nullptr
   int act;                      // b2::Act, applied after bias
   float* stats;                 // [images][cout][2] (sum, sumsq) of the stored bf16 values, or nullptr

@@ -59,8 +59,8 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int 
   const int m_tiles = tiles_per_img * num_images;
   const int m_pairs = (m_tiles + 1) >> 1;
   const int n_tiles = (p.cout + BLOCK_N - 1) / BLOCK_N;
-  const int total_pairs = m_pairs * n_tiles;
-  const int num_kb = p.num_taps * p.cin_blocks;
+  const int pairs_per_phase = m_pairs * n_tiles;
+  const int total_pairs = pairs_per_phase * p.num_phases;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmB);
@@ -84,7 +84,8 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int 
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   // pair-tile -> this CTA's 128-pixel tile
-  auto decode = [&](int pt, int& mt, int& n0, int& img, int& h0, int& w0) {
+  auto decode = [&](int ptile, int& mt, int& n0, int& img, int& h0, int& w0) {
+    const int pt = ptile % pairs_per_phase;
     const int mp = pt / n_tiles;
     n0 = (pt - mp * n_tiles) * BLOCK_N;
     mt = 2 * mp + static_cast<int>(rank);
@@ -102,7 +103,9 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int 
       for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
         int mt, n0, img, h0, w0;
         decode(pt, mt, n0, img, h0, w0);
-        for (int t = 0; t < p.num_taps; ++t) {
+        const int phase = pt / pairs_per_phase;
+        const int t_begin = p.phase_tap_begin[phase], t_end = t_begin + p.phase_tap_count[phase];
+        for (int t = t_begin; t < t_end; ++t) {
           const Tap tap = p.taps[t];
           const CUtensorMap* amap = &p.tmA[tap.map];
           for (int cb = 0; cb < p.cin_blocks; ++cb, ++it) {
@@ -132,6 +135,7 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int 
       constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N, 0, B_MN ? 1 : 0);
       uint32_t it = 0, tile_i = 0;
       for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++tile_i) {
+        const int num_kb = p.phase_tap_count[pt / pairs_per_phase] * p.cin_blocks;
         const uint32_t acc = tile_i & 1;
         const uint32_t acc_ph = (tile_i >> 1) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
@@ -172,7 +176,7 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int 
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * Cfg::kAccCols + (static_cast<uint32_t>(ew * 32) << 16);
       if (dbg == 1) { tc_fence_before(); mbar_arrive_cluster(&tmem_empty_bar[acc], 0); continue; }
-      conv_epilogue_tile<BLOCK_N>(p, stage_buf, red, taddr, img, h0, w0, n0, e, ew, lane, mt < m_tiles,
+      conv_epilogue_tile<BLOCK_N>(p, p.out + p.phase_out_off[pt / pairs_per_phase], stage_buf, red, taddr, img, h0, w0, n0, e, ew, lane, mt < m_tiles,
                                   [&]() { mbar_arrive_cluster(&tmem_empty_bar[acc], 0); });
     }
   }
@@ -203,7 +207,7 @@ static void launch2_t(const ConvGemmParams& p, int num_images, cudaStream_t stre
     configured = true;
   }
   const int m_tiles = p.tiles_w * p.tiles_h * num_images;
-  const int pairs = ((m_tiles + 1) / 2) * ((p.cout + BLOCK_N - 1) / BLOCK_N);
+  const int pairs = ((m_tiles + 1) / 2) * ((p.cout + BLOCK_N - 1) / BLOCK_N) * p.num_phases;
   const int max_clusters = num_sms2() / 2;
   const int clusters = pairs < max_clusters ? pairs : max_clusters;
   cudaLaunchConfig_t cfg{};

@@ -85,21 +85,24 @@ __global__ void __launch_bounds__(kThreads, 2) in_apply_kernel(const InApplyPara
   const int HW = p.H * p.W;
   const int pix0 = blockIdx.x * pix_per_block;
   const int pix1 = min(HW, pix0 + pix_per_block);
-  float ca[8], cb[8];
-  if (p.stats != nullptr) {
-    const float* st = p.stats + (static_cast<long long>(n) * p.C + c) * 2;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float mean = st[2 * j] * p.inv_count;
-      const float var = fmaxf(st[2 * j + 1] * p.inv_count - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + p.eps);
-      ca[j] = rstd * __ldg(p.gamma + c + j);
-      cb[j] = __ldg(p.beta + c + j) - mean * ca[j];
+  // per-channel affine coefficients, computed once per block (thread t -> channel t)
+  extern __shared__ float coef[];   // [2][C]
+  for (int ch = threadIdx.x; ch < p.C; ch += kThreads) {
+    float a = 1.f, b = 0.f;
+    if (p.stats != nullptr) {
+      const float* st = p.stats + (static_cast<long long>(n) * p.C + ch) * 2;
+      const float mean = st[0] * p.inv_count;
+      const float var = fmaxf(st[1] * p.inv_count - mean * mean, 0.f);
+      a = rsqrtf(var + p.eps) * __ldg(p.gamma + ch);
+      b = __ldg(p.beta + ch) - mean * a;
     }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { ca[j] = 1.f; cb[j] = 0.f; }
+    coef[ch] = a;
+    coef[p.C + ch] = b;
   }
+  __syncthreads();
+  float ca[8], cb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { ca[j] = coef[c + j]; cb[j] = coef[p.C + c + j]; }
   const bool has_skip = p.skip.p != nullptr;
   const float slope = act_slope(p.act);
   constexpr int U = 4;
@@ -167,14 +170,23 @@ __global__ void __launch_bounds__(kThreads, 2) in_bwd_reduce_kernel(const InBwdR
   float mean[8], rstd[8], gam[8], bet[8];
   const bool has_in = p.stats != nullptr;
   if (has_in) {
-    const float* st = p.stats + (static_cast<long long>(n) * p.C + c) * 2;
+    float* coef = red + lanes * p.C * 2;   // [4][C]
+    for (int ch = threadIdx.x; ch < p.C; ch += kThreads) {
+      const float* st = p.stats + (static_cast<long long>(n) * p.C + ch) * 2;
+      const float mu = st[0] * p.inv_count;
+      const float var = fmaxf(st[1] * p.inv_count - mu * mu, 0.f);
+      coef[ch] = mu;
+      coef[p.C + ch] = rsqrtf(var + p.eps);
+      coef[2 * p.C + ch] = __ldg(p.gamma + ch);
+      coef[3 * p.C + ch] = __ldg(p.beta + ch);
+    }
+    __syncthreads();
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      mean[j] = st[2 * j] * p.inv_count;
-      const float var = fmaxf(st[2 * j + 1] * p.inv_count - mean[j] * mean[j], 0.f);
-      rstd[j] = rsqrtf(var + p.eps);
-      gam[j] = __ldg(p.gamma + c + j);
-      bet[j] = __ldg(p.beta + c + j);
+      mean[j] = coef[c + j];
+      rstd[j] = coef[p.C + c + j];
+      gam[j] = coef[2 * p.C + c + j];
+      bet[j] = coef[3 * p.C + c + j];
     }
   }
   float s1[8], s2[8];
@@ -286,22 +298,27 @@ __global__ void __launch_bounds__(kThreads, 2) in_bwd_apply_kernel(const InBwdAp
       p.dbeta[cc] += db;
     }
   }
+  extern __shared__ float coef[];   // [3][C]
+  for (int ch = threadIdx.x; ch < p.C; ch += kThreads) {
+    const float* st = p.stats + (static_cast<long long>(n) * p.C + ch) * 2;
+    const float* bs = p.bstats + (static_cast<long long>(n) * p.C + ch) * 2;
+    const float mean = st[0] * p.inv_count;
+    const float var = fmaxf(st[1] * p.inv_count - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + p.eps);
+    const float m1 = bs[0] * p.inv_count;
+    const float m2 = bs[1] * p.inv_count;
+    const float gr = __ldg(p.gamma + ch) * rstd;
+    coef[ch] = gr;
+    coef[p.C + ch] = -gr * rstd * m2;
+    coef[2 * p.C + ch] = gr * (mean * rstd * m2 - m1);
+  }
+  __syncthreads();
   float kA[8], kB[8], kC[8];
-  {
-    const float* st = p.stats + (static_cast<long long>(n) * p.C + c) * 2;
-    const float* bs = p.bstats + (static_cast<long long>(n) * p.C + c) * 2;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float mean = st[2 * j] * p.inv_count;
-      const float var = fmaxf(st[2 * j + 1] * p.inv_count - mean * mean, 0.f);
-      const float rstd = rsqrtf(var + p.eps);
-      const float m1 = bs[2 * j] * p.inv_count;
-      const float m2 = bs[2 * j + 1] * p.inv_count;
-      const float gr = __ldg(p.gamma + c + j) * rstd;
-      kA[j] = gr;
-      kB[j] = -gr * rstd * m2;
-      kC[j] = gr * (mean * rstd * m2 - m1);
-    }
+  for (int j = 0; j < 8; ++j) {
+    kA[j] = coef[c + j];
+    kB[j] = coef[p.C + c + j];
+    kC[j] = coef[2 * p.C + c + j];
   }
   constexpr int U = 4;
   for (int base = pix0 + ln; base < pix1; base += lanes * U) {
@@ -578,7 +595,7 @@ inline int grid_for_fixed_c(long long total, int c8) {
 static int pick_pix_per_block(int HW, int N, int lanes) {
   // >= 4 pixels per thread per pass, and roughly >= 2 blocks per SM
   int ppb = lanes * 16;
-  while (ppb > lanes * 4 && static_cast<long long>((HW + ppb - 1) / ppb) * N < 2 * 148) ppb /= 2;
+  while (ppb > lanes * 4 && static_cast<long long>((HW + ppb - 1) / ppb) * N < 4 * 148) ppb /= 2;
   if (ppb > HW) ppb = HW;
   return ppb;
 }
@@ -588,7 +605,7 @@ void launch_in_apply(const InApplyParams& p, cudaStream_t s) {
   const int lanes = kThreads / (p.C / 8);
   const int ppb = pick_pix_per_block(HW, p.N, lanes);
   dim3 grid((HW + ppb - 1) / ppb, p.N);
-  in_apply_kernel<<<grid, kThreads, 0, s>>>(p, ppb);
+  in_apply_kernel<<<grid, kThreads, 2 * p.C * sizeof(float), s>>>(p, ppb);
 }
 
 void launch_in_bwd_reduce(const InBwdReduceParams& p, cudaStream_t s) {
@@ -597,7 +614,7 @@ void launch_in_bwd_reduce(const InBwdReduceParams& p, cudaStream_t s) {
   const int lanes = kThreads / c8;
   const int pix_per_block = pick_pix_per_block(HW, p.N, lanes);
   dim3 grid((HW + pix_per_block - 1) / pix_per_block, p.N);
-  const size_t smem = static_cast<size_t>(lanes) * p.C * 2 * sizeof(float);
+  const size_t smem = (static_cast<size_t>(lanes) * p.C * 2 + 4 * p.C) * sizeof(float);
   in_bwd_reduce_kernel<<<grid, kThreads, smem, s>>>(p, pix_per_block);
 }
 
@@ -606,7 +623,7 @@ void launch_in_bwd_apply(const InBwdApplyParams& p, cudaStream_t s) {
   const int lanes = kThreads / (p.C / 8);
   const int ppb = pick_pix_per_block(HW, p.N, lanes);
   dim3 grid((HW + ppb - 1) / ppb, p.N);
-  in_bwd_apply_kernel<<<grid, kThreads, 0, s>>>(p, ppb);
+  in_bwd_apply_kernel<<<grid, kThreads, 3 * p.C * sizeof(float), s>>>(p, ppb);
 }
 
 void launch_act_bwd(const ActBwdParams& p, cudaStream_t s) {

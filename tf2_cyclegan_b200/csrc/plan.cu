@@ -221,7 +221,7 @@ class Plan {
                     std::vector<TapT> taps, int cin_blocks, int tiles_w, int tiles_h, int bw,
                     int bh, int w_limit, uint64_t out, long long sn, long long sh, long long sw,
                     int cout, uint64_t bias, int act, uint64_t stats, int block_n, bool b_mn,
-                    int num_images) {
+                    int num_images, std::vector<std::tuple<int, int, long long>> phases) {
     auto p = std::make_shared<ConvGemmParams>();
     memset(p.get(), 0, sizeof(ConvGemmParams));
     if (a_maps.empty() || a_maps.size() > kMaxAMaps) throw std::runtime_error("bad a_maps");
@@ -233,18 +233,27 @@ class Plan {
     p->bw = bw; p->bh = bh; p->w_limit = w_limit;
     p->out = P<__nv_bfloat16>(out); p->out_sn = sn; p->out_sh = sh; p->out_sw = sw;
     p->cout = cout; p->bias = P<const float>(bias); p->act = act; p->stats = P<float>(stats);
+    if (phases.empty()) phases.push_back({0, p->num_taps, 0});
+    if (phases.size() > kMaxPhases) throw std::runtime_error("too many phases");
+    p->num_phases = static_cast<int>(phases.size());
+    for (size_t i = 0; i < phases.size(); ++i) {
+      p->phase_tap_begin[i] = std::get<0>(phases[i]);
+      p->phase_tap_count[i] = std::get<1>(phases[i]);
+      p->phase_out_off[i] = std::get<2>(phases[i]);
+    }
     return add(std::move(name), [p, block_n, b_mn, num_images](cudaStream_t s) {
       launch_conv_gemm(*p, block_n, b_mn, num_images, s);
     });
   }
 
-  int add_wgrad(std::string name, py::bytes dy_map, std::vector<py::bytes> a_maps,
+  int add_wgrad(std::string name, std::vector<py::bytes> dy_maps, std::vector<py::bytes> a_maps,
                 std::vector<TapT> taps, int ktiles_w, int ktiles_h, int kbw, int kbh,
                 int num_images, int cin, int cout, uint64_t dw, long long ldw, int block_n,
                 int ksplit) {
     auto p = std::make_shared<WgradParams>();
     memset(p.get(), 0, sizeof(WgradParams));
-    p->tmDY = tmap_from(dy_map);
+    if (dy_maps.empty() || dy_maps.size() > kMaxAMaps) throw std::runtime_error("bad dy_maps");
+    for (size_t i = 0; i < dy_maps.size(); ++i) p->tmDY[i] = tmap_from(dy_maps[i]);
     if (a_maps.empty() || a_maps.size() > kMaxAMaps) throw std::runtime_error("bad a_maps");
     for (size_t i = 0; i < a_maps.size(); ++i) p->tmA[i] = tmap_from(a_maps[i]);
     fill_taps(taps, p->taps, &p->num_taps);

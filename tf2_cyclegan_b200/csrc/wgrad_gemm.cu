@@ -31,6 +31,34 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 
+
+// Epilogue shared by both wgrad kernels: TMEM row (one output channel) -> padded smem row ->
+// ONE bulk fp32 reduce-add per row into the gradient buffer (TMA engine, no per-thread atomics).
+// `stage` aliases the (idle) pipeline buffers; rows are padded by 16 B against bank conflicts.
+template <int BLOCK_N>
+__device__ __forceinline__ void wgrad_epilogue(const WgradParams& p, uint8_t* stage, uint32_t taddr,
+                                               int e, int co, int n0, int col0) {
+  constexpr int ROW_BYTES = BLOCK_N * 4 + 16;
+  float* srow = reinterpret_cast<float*>(stage + e * ROW_BYTES);
+#pragma unroll 1
+  for (int c = 0; c < BLOCK_N; c += 32) {
+    uint32_t r[32];
+    tmem_ld_32x32(taddr + c, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      *reinterpret_cast<uint4*>(srow + c + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+  }
+  fence_proxy_async_smem();            // generic-proxy smem writes -> visible to the bulk engine
+  const int n_valid = min(BLOCK_N, p.cin - n0);
+  if (co < p.cout && n_valid > 0) {
+    float* grow = p.dw + static_cast<long long>(co) * p.ldw + col0 + n0;
+    bulk_reduce_add_f32(grow, srow, static_cast<uint32_t>(n_valid) * 4u);
+    tma_store_commit();
+    tma_store_wait_all();              // smem row must stay intact until the engine has read it
+  }
+}
+
 template <int BLOCK_N>
 __global__ void __launch_bounds__(256, 1)
 wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
@@ -58,7 +86,7 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
   const int num_kb = kt_end - kt_begin;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmDY);
+    tma_prefetch_desc(&p.tmDY[tap.dn]);
     tma_prefetch_desc(&p.tmA[tap.map]);
   } else if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -95,11 +123,11 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
           // channels beyond the tensor extent are zero-filled by TMA (cout / cin < tile)
 #pragma unroll
           for (int j = 0; j < 2; ++j)
-            tma_load_4d(sa + j * (64 * 128), &p.tmDY, &full_bar[s], m0 + j * 64, w0, h0, img);
+            tma_load_4d(sa + j * (64 * 128), &p.tmDY[tap.dn], &full_bar[s], m0 + j * 64, w0, h0, img);
 #pragma unroll
           for (int j = 0; j < BLOCK_N / 64; ++j)
             tma_load_4d(sb + j * (64 * 128), amap, &full_bar[s], n0 + j * 64, w0 + tap.dw,
-                        h0 + tap.dh, img + tap.dn);
+                        h0 + tap.dh, img);
         }
       }
     } else if (warp == 1) {
@@ -128,22 +156,7 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
-      const int co = m0 + e;
-      float* row = p.dw + static_cast<long long>(co) * p.ldw + tap.bk + n0;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c, r);
-        tmem_ld_wait();
-        if (co < p.cout) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (n0 + c + j < p.cin)
-              red_add_v4(row + c + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                         __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-          }
-        }
-      }
+      wgrad_epilogue<BLOCK_N>(p, smem, taddr, e, m0 + e, n0, tap.bk);
     }
   }
   tc_fence_before();
@@ -212,7 +225,7 @@ wgrad_gemm2_kernel(const __grid_constant__ WgradParams p) {
   const int num_kb = kt_end - kt_begin;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmDY);
+    tma_prefetch_desc(&p.tmDY[tap.dn]);
     tma_prefetch_desc(&p.tmA[tap.map]);
   } else if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -248,12 +261,12 @@ wgrad_gemm2_kernel(const __grid_constant__ WgradParams p) {
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);
 #pragma unroll
           for (int j = 0; j < 2; ++j)
-            tma_load_4d_2sm(sa + j * (64 * 128), &p.tmDY, &full_bar[s], m0 + j * 64, w0, h0, img);
+            tma_load_4d_2sm(sa + j * (64 * 128), &p.tmDY[tap.dn], &full_bar[s], m0 + j * 64, w0, h0, img);
 #pragma unroll
           for (int j = 0; j < Cfg::kHalfN / 64; ++j)
             tma_load_4d_2sm(sb + j * (64 * 128), amap, &full_bar[s],
                             n0 + static_cast<int>(rank) * Cfg::kHalfN + j * 64, w0 + tap.dw, h0 + tap.dh,
-                            img + tap.dn);
+                            img);
           if (rank != 0) mbar_arrive_cluster(&full_bar[s], 0);
         }
       }
@@ -283,22 +296,7 @@ wgrad_gemm2_kernel(const __grid_constant__ WgradParams p) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
-      const int co = m0 + e;
-      float* row = p.dw + static_cast<long long>(co) * p.ldw + tap.bk + n0;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(taddr + c, r);
-        tmem_ld_wait();
-        if (co < p.cout) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (n0 + c + j < p.cin)
-              red_add_v4(row + c + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                         __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-          }
-        }
-      }
+      wgrad_epilogue<BLOCK_N>(p, smem, taddr, e, m0 + e, n0, tap.bk);
     }
   }
   tc_fence_before();

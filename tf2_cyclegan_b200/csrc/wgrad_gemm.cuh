@@ -5,7 +5,7 @@
 namespace b2 {
 
 struct WgradParams {
-  CUtensorMap tmDY;             // bf16 gradient view [.., Cout], box {64, kbw, kbh, 1}
+  CUtensorMap tmDY[kMaxAMaps];  // bf16 gradient views [.., Cout], box {64, kbw, kbh, 1}; tap.dn selects one
   CUtensorMap tmA[kMaxAMaps];   // bf16 activation views [.., Cin], box {64, kbw, kbh, 1}
   Tap taps[kMaxTaps];           // same tap table as the forward conv (bk = dW column)
   int num_taps;

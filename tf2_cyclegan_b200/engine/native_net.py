@@ -235,11 +235,10 @@ class NetExec:
       if l.kind == "convT":
         bw, bh = nv.tile_shape(hi, wi)
         amap = src.tmap_interior(bw, bh, n0, nimg)
-        for a in (0, 1):
-          for b in (0, 1):
-            view = (dst.ptr(n0, a, b), dst.sn, 2 * dst.sh, 2 * dst.sw)
-            no.add_conv(plan, f"{name}.p{a}{b}", [amap], no.taps_convT_phase(a, b, l.cin), l.cin, w2,
-                        view, hi, wi, nimg, l.cout, bias, act, stats)
+        view = (dst.ptr(n0), dst.sn, 2 * dst.sh, 2 * dst.sw)
+        phases = [(no.taps_convT_phase(a, b, l.cin), a * dst.sh + b * dst.sw) for a in (0, 1) for b in (0, 1)]
+        no.add_conv(plan, name, [amap], [], l.cin, w2, view, hi, wi, nimg, l.cout, bias, act, stats,
+                    phases=phases)
       else:
         bw, bh = nv.tile_shape(ho, wo)
         if is_small_cin(l):
@@ -345,11 +344,13 @@ class NetExec:
     if l.kind == "convT":
       kbw, kbh = nv.tile_shape(hi, wi, 64)
       amap = src.tmap_interior(kbw, kbh, n0, nimg)
+      dy_maps, taps = [], []
       for a in (0, 1):
         for b in (0, 1):
-          no.add_wgrad(plan, f"{name}.p{a}{b}", dY.tmap_parity(a, b, kbw, kbh, n0, nimg), [amap],
-                       no.taps_convT_phase(a, b, l.cin), wi // kbw, hi // kbh, kbw, kbh, nimg, l.cin,
-                       l.cout, dw, ldw)
+          dy_maps.append(dY.tmap_parity(a, b, kbw, kbh, n0, nimg))
+          taps += [(t[0], len(dy_maps) - 1, t[2], t[3], t[4]) for t in no.taps_convT_phase(a, b, l.cin)]
+      no.add_wgrad(plan, name, dy_maps, [amap], taps, wi // kbw, hi // kbh, kbw, kbh, nimg, l.cin,
+                   l.cout, dw, ldw)
       return
     if j in self.w_dgrad and not is_small_cin(l):
       # small-Cout reflect conv (generator final layer): swapped operands in the flat domain.
@@ -420,18 +421,17 @@ class NetExec:
       amap = dY.tmap_interior(bw, bh, n0, nimg)
       if is_small_cin(l):
         tgt, t0 = input_target
-        for a in (0, 1):
-          for b in (0, 1):
-            view = (tgt.ptr(t0, a, b), tgt.sn, 2 * tgt.sh, 2 * tgt.sw)
-            no.add_conv(plan, f"{name}.p{a}{b}", [amap], no.taps_convT_phase(a, b, l.cout, l.k, pb),
-                        l.cout, self.w_dgrad[j], view, ho, wo, nimg, l.cin, b_mn=False)
+        view = (tgt.ptr(t0), tgt.sn, 2 * tgt.sh, 2 * tgt.sw)
+        phases = [(no.taps_convT_phase(a, b, l.cout, l.k, pb), a * tgt.sh + b * tgt.sw)
+                  for a in (0, 1) for b in (0, 1)]
+        no.add_conv(plan, name, [amap], [], l.cout, self.w_dgrad[j], view, ho, wo, nimg, l.cin,
+                    b_mn=False, phases=phases)
         return (tgt.view(t0), 0)
       gin = self.gin[j]
-      for a in (0, 1):
-        for b in (0, 1):
-          view = (gin.ptr(n0, a, b), gin.sn, 2 * gin.sh, 2 * gin.sw)
-          no.add_conv(plan, f"{name}.p{a}{b}", [amap], no.taps_convT_phase(a, b, l.cin, l.k, pb),
-                      l.cout, w2, view, ho, wo, nimg, l.cin, b_mn=True)
+      view = (gin.ptr(n0), gin.sn, 2 * gin.sh, 2 * gin.sw)
+      phases = [(no.taps_convT_phase(a, b, l.cin, l.k, pb), a * gin.sh + b * gin.sw)
+                for a in (0, 1) for b in (0, 1)]
+      no.add_conv(plan, name, [amap], [], l.cout, w2, view, ho, wo, nimg, l.cin, b_mn=True, phases=phases)
       return (gin.view(n0), 0)
     # stride-1 TF-SAME conv: dX[q] = sum dY[q + pb - (r, s)] W[r, s]
     gin = self.gin[j]

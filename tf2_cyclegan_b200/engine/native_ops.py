@@ -77,7 +77,8 @@ def add_conv(plan, name: str, a_maps: Sequence[bytes], taps: Sequence[Tap], k_ch
              w2_bf16: torch.Tensor, out_view, out_h: int, out_w: int, nimg: int, n_channels: int,
              bias: int = 0, act: int = 0, stats: int = 0, b_mn: bool = False,
              block_n: Optional[int] = None, tile: Optional[Tuple[int, int]] = None,
-             w_limit: Optional[int] = None):
+             w_limit: Optional[int] = None,
+             phases: Optional[Sequence[Tuple[Sequence[Tap], int]]] = None):
   """Box-mode implicit GEMM: out[n, h, w, :n_channels] over an out_h x out_w grid.
 
   k_channels: channels of the A views (K per tap); n_channels: valid output channels."""
@@ -86,10 +87,16 @@ def add_conv(plan, name: str, a_maps: Sequence[bytes], taps: Sequence[Tap], k_ch
     block_n = max(block_n, 64)
   bw, bh = tile or nv.tile_shape(out_h, out_w)
   ptr, sn, sh, sw = out_view
+  ph = []
+  if phases is not None:   # several tap groups (sub-pixel phases) in ONE launch; out offsets in elements
+    taps = []
+    for ptaps, off in phases:
+      ph.append((len(taps), len(ptaps), int(off)))
+      taps.extend(ptaps)
   return plan.add_conv_gemm(name, list(a_maps), nv.wmat_tmap(w2_bf16, block_n, b_mn),
                             list(taps), k_channels // 64, out_w // bw, out_h // bh, bw, bh,
                             out_w if w_limit is None else w_limit, ptr, sn, sh, sw, n_channels,
-                            bias, act, stats, block_n, b_mn, nimg)
+                            bias, act, stats, block_n, b_mn, nimg, ph)
 
 
 def add_conv_flat(plan, name: str, a_map: bytes, taps: Sequence[Tap], k_channels: int,
@@ -103,19 +110,23 @@ def add_conv_flat(plan, name: str, a_map: bytes, taps: Sequence[Tap], k_channels
   tiles = (rows + 127) // 128
   return plan.add_conv_gemm(name, [a_map], nv.wmat_tmap(w2_bf16, block_n, b_mn), list(taps),
                             k_channels // 64, tiles, 1, 128, 1, rows, out_ptr, 0, 0,
-                            out_row_stride, n_channels, 0, 0, 0, block_n, b_mn, 1)
+                            out_row_stride, n_channels, 0, 0, 0, block_n, b_mn, 1, [])
 
 
-def add_wgrad(plan, name: str, dy_map: bytes, a_maps: Sequence[bytes], taps: Sequence[Tap],
+def add_wgrad(plan, name: str, dy_map, a_maps: Sequence[bytes], taps: Sequence[Tap],
               kt_w: int, kt_h: int, kbw: int, kbh: int, nimg: int, cin: int, cout: int,
-              dw_ptr: int, ldw: int, block_n: Optional[int] = None, target_ctas: int = 296):
+              dw_ptr: int, ldw: int, block_n: Optional[int] = None, target_ctas: Optional[int] = None):
+  import os
+  target_ctas = target_ctas or int(os.environ.get("B2_WGRAD_CTAS", "296"))
   block_n = block_n or max(64, nv.pick_block_n(cin))
   m_tiles = (cout + 127) // 128
   n_tiles = (cin + block_n - 1) // block_n
   base = m_tiles * n_tiles * len(taps)
   total_kt = kt_w * kt_h * nimg
   ksplit = max(1, min(total_kt, (target_ctas + base - 1) // base))
-  return plan.add_wgrad(name, dy_map, list(a_maps), list(taps), kt_w, kt_h, kbw, kbh, nimg,
+  # dy_map: one view, or a list of views selected per tap through tap[1] (phase-merged wgrad)
+  dy_maps = list(dy_map) if isinstance(dy_map, (list, tuple)) else [dy_map]
+  return plan.add_wgrad(name, dy_maps, list(a_maps), list(taps), kt_w, kt_h, kbw, kbh, nimg,
                         cin, cout, dw_ptr, ldw, block_n, ksplit)
 
 
