@@ -122,3 +122,28 @@ def test_cuda_graph_replay_matches_eager_plan():
   for k in ra:
     assert abs(ra[k].item() - rg[k].item()) < 2e-3 * max(1.0, abs(ra[k].item())), k
   assert g.kernel_launches() > 0
+
+
+def test_cli_end_to_end_native(tmp_path, capsys):
+  """runner + native backend: 2 epochs on synthetic data, checkpoint, plots, resume."""
+  from tf2_cyclegan_b200.cli import parse_args
+  from tf2_cyclegan_b200.runner import main
+  from tf2_cyclegan_b200.utils import checkpoint as ckpt
+  out = tmp_path / "runs"
+  argv = ["--output_dir", str(out), "--epochs", "2", "--image_size", "128", "--num_residual_blocks", "2",
+          "--synthetic_size", "6", "--batch_size", "2", "--backend", "native", "--verbose", "0"]
+  res = main(parse_args(argv))
+  assert len(res) == 14 and all(v == v for v in res.values())
+  prefix = str(out / "checkpoints" / "checkpoint")
+  assert ckpt.exists(prefix)
+  sd, extra = ckpt.load(prefix)
+  assert extra["epoch"] == 1 and sd["G_optimizer/iter/.ATTRIBUTES/VARIABLE_VALUE"].item() == 6
+  ea_mod = pytest.importorskip("tensorboard.backend.event_processing.event_accumulator")
+  te = ea_mod.EventAccumulator(str(out / "test"), size_guidance={"tensors": 0}); te.Reload()
+  tags = set(te.Tags()["tensors"])
+  assert "X_cycle/sample_#000" in tags and "error/MAE(X, F(G(X)))" in tags and "elapse" in tags
+  capsys.readouterr()
+  main(parse_args(argv[:3] + ["1"] + argv[4:]))
+  assert "loaded checkpoint from" in capsys.readouterr().out
+  sd2, _ = ckpt.load(prefix)
+  assert sd2["G_optimizer/iter/.ATTRIBUTES/VARIABLE_VALUE"].item() == 9
