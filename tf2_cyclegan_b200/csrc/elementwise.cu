@@ -1,4 +1,6 @@
 // Bandwidth-bound kernels around the GEMMs (see elementwise.cuh).
+#include <stdlib.h>
+
 #include "elementwise.cuh"
 
 namespace b2 {
@@ -547,7 +549,8 @@ __global__ void __launch_bounds__(kThreads) d4_dgrad_kernel(const D4BwdParams p)
   }
 }
 
-// dW[0][t][c] += sum_pix gd[pix] * a[pix + tap]; grid: (16 taps, pixel chunks)
+// dW[0][t][c] += sum_pix gd[pix] * a[pix + tap]; grid: (16 taps, pixel chunks).
+// A thread owns 2 channels; pixels are walked 4 at a time so the loads overlap.
 __global__ void __launch_bounds__(kThreads) d4_wgrad_kernel(const D4BwdParams p, int chunks) {
   const int t = blockIdx.x;
   const int kr = t >> 2, ks = t & 3;
@@ -555,23 +558,38 @@ __global__ void __launch_bounds__(kThreads) d4_wgrad_kernel(const D4BwdParams p,
   const long long per = (npix + chunks - 1) / chunks;
   const long long i0 = blockIdx.y * per, i1 = min(npix, i0 + per);
   float gsum = 0.f;
-  // each thread owns channels threadIdx.x*2 .. (C <= 512 => 2 channels per thread)
   const int c = threadIdx.x * 2;
+  const bool c_ok = c < p.C;
   float a0 = 0.f, a1 = 0.f;
-  for (long long i = i0; i < i1; ++i) {
-    const int w = static_cast<int>(i % p.W);
-    long long r = i / p.W;
-    const int h = static_cast<int>(r % p.H);
-    const int n = static_cast<int>(r / p.H);
-    const float g = __bfloat162float(*vptr(p.gd, n, h, w));
-    gsum += g;
-    const int ih = h + kr - p.pad_before, iw = w + ks - p.pad_before;
-    if (ih < 0 || ih >= p.H || iw < 0 || iw >= p.W || c >= p.C) continue;
-    const float2 av = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vptr(p.a, n, ih, iw) + c));
-    a0 += g * av.x;
-    a1 += g * av.y;
+  constexpr int U = 4;
+  for (long long base = i0; base < i1; base += U) {
+    float g[U];
+    uint32_t av[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = base + u;
+      g[u] = 0.f;
+      av[u] = 0u;
+      if (i < i1) {
+        const int w = static_cast<int>(i % p.W);
+        long long r = i / p.W;
+        const int h = static_cast<int>(r % p.H);
+        const int n = static_cast<int>(r / p.H);
+        g[u] = __bfloat162float(*vptr(p.gd, n, h, w));
+        const int ih = h + kr - p.pad_before, iw = w + ks - p.pad_before;
+        if (c_ok && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W)
+          av[u] = __ldg(reinterpret_cast<const uint32_t*>(vptr(p.a, n, ih, iw) + c));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const float2 f = unpack_bf16x2(av[u]);
+      gsum += g[u];
+      a0 += g[u] * f.x;
+      a1 += g[u] * f.y;
+    }
   }
-  if (c < p.C) {
+  if (c_ok) {
     atomicAdd(p.dw + static_cast<long long>(t) * p.C + c, a0);
     atomicAdd(p.dw + static_cast<long long>(t) * p.C + c + 1, a1);
   }
@@ -592,10 +610,19 @@ inline int grid_for_fixed_c(long long total, int c8) {
 
 }  // namespace
 
+static int ew_target_blocks() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2_EW_BLOCKS");
+    v = e ? atoi(e) : 592;
+  }
+  return v;
+}
+
 static int pick_pix_per_block(int HW, int N, int lanes) {
-  // >= 4 pixels per thread per pass, and roughly >= 2 blocks per SM
-  int ppb = lanes * 16;
-  while (ppb > lanes * 4 && static_cast<long long>((HW + ppb - 1) / ppb) * N < 4 * 148) ppb /= 2;
+  // >= 4 pixels per thread per pass; enough blocks to fill the machine
+  int ppb = lanes * 32;
+  while (ppb > lanes * 4 && static_cast<long long>((HW + ppb - 1) / ppb) * N < ew_target_blocks()) ppb /= 2;
   if (ppb > HW) ppb = HW;
   return ppb;
 }
@@ -660,7 +687,10 @@ void launch_d4_dgrad(const D4BwdParams& p, cudaStream_t s) {
   d4_dgrad_kernel<<<grid_for(total), kThreads, 0, s>>>(p);
 }
 void launch_d4_wgrad(const D4BwdParams& p, cudaStream_t s) {
-  const int chunks = 32;
+  const long long npix = static_cast<long long>(p.N) * p.H * p.W;
+  int chunks = static_cast<int>(npix / 32);   // ~32 pixels per block
+  if (chunks < 1) chunks = 1;
+  if (chunks > 256) chunks = 256;
   d4_wgrad_kernel<<<dim3(16, chunks), kThreads, 0, s>>>(p, chunks);
 }
 
