@@ -30,7 +30,7 @@ class FakePlan:
     if phases:
       assert sum(c for _, c, _ in phases) == len(taps) and all(c >= 1 for _, c, _ in phases)
     assert cin_blocks >= 1 and tiles_w >= 1 and tiles_h >= 1 and num_images >= 1
-    assert block_n in (16, 64, 128, 256) and (not b_mn or block_n >= 64)
+    assert block_n in (16, 32, 64, 128, 256) and (not b_mn or block_n >= 64)
     for t in taps:
       assert 0 <= t[0] < len(a_maps)
     for m in a_maps:
@@ -70,6 +70,14 @@ class FakePlan:
 
   def add_join(self, name):
     return self._add("join", name)
+
+  def add_event_record(self, name, lane):
+    assert 0 <= lane < 4
+    return self._add("record", name, lane)
+
+  def add_event_wait(self, name, lane, ref):
+    assert 0 <= lane < 4 and self.ops[ref][0] == "record"
+    return self._add("wait", name, lane, ref)
 
   def __getattr__(self, item):
     if item.startswith("add_"):

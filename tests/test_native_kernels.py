@@ -309,3 +309,33 @@ def test_losses_adam_imgprep():
     opt.apply_gradients(ref, {"w": gr})
   assert torch.allclose(w, ref["w"], atol=1e-6) and step.item() == 2
   assert torch.allclose(wb.float(), w, atol=1e-2)
+
+
+def test_output_conv_row_gemm_and_gather():
+  """7x7 reflect conv 64 -> 3 (+bias, tanh) as one GEMM tap per kernel row over the flat padded
+  domain followed by the 7-tap horizontal gather."""
+  nv, no, O = _mods()
+  C = nv.load()
+  torch.manual_seed(9)
+  n, h, cin, cout, k = 2, 64, 64, 3, 7
+  x = bf(torch.randn(n, h, h, cin, device="cuda"))
+  kern = bf(torch.randn(k, k, cin, cout, device="cuda") * 0.05)
+  bias = torch.randn(cout, device="cuda") * 0.1
+  xin = nv.Buf(n, h, h, cin, halo=3)
+  fill_reflect(xin, x)
+  wq = torch.zeros(32, k, cin, device="cuda")
+  for s in range(k):
+    wq[s * 4:s * 4 + cout] = kern[:, s].permute(2, 0, 1)      # [co, r, ci]
+  wq = wq.reshape(32, k * cin).to(torch.bfloat16)
+  rows = n * xin.hp * xin.wp
+  q = torch.zeros((rows + 256) * 32, dtype=torch.bfloat16, device="cuda")
+  out = nv.Buf(n, h, h, 8)
+  plan = C.Plan()
+  taps = [(0, 0, r * xin.wp, 0, r * cin) for r in range(k)]
+  no.add_conv_flat(plan, "rowgemm", xin.tmap_flat(), taps, cin, wq, q.data_ptr(), 32, rows, 32, block_n=32)
+  plan.add_tap_gather("gather", q.data_ptr(), bias.data_ptr(), out.view(), nv.ACT["tanh"], k, xin.hp, xin.wp,
+                      n, h, h)
+  run(plan)
+  ref = torch.tanh(O.conv2d(O.reflect_pad(x, 3), kern, 1, "valid", bias))
+  assert (out.t[..., :cout].float() - ref).abs().max().item() < 3e-2
+  assert out.t[..., cout:].abs().max() == 0

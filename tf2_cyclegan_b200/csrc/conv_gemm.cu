@@ -265,6 +265,7 @@ void launch_conv_gemm(const ConvGemmParams& p, int block_n, bool b_mn_major, int
   if (!b_mn_major) {
     switch (block_n) {
       case 16: return launch_t<16, false>(p, num_images, stream);
+      case 32: return launch_t<32, false>(p, num_images, stream);
       case 64: return launch_t<64, false>(p, num_images, stream);
       case 128: return launch_t<128, false>(p, num_images, stream);
       case 256: return launch_t<256, false>(p, num_images, stream);

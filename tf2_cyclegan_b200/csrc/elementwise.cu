@@ -490,6 +490,31 @@ __global__ void __launch_bounds__(kThreads) mse_loss_kernel(const MseLossParams 
   if (threadIdx.x == 0) atomicAdd(p.loss_slot, tot * p.loss_scale);
 }
 
+// --------------------------------------------------------------- tap gather
+__global__ void __launch_bounds__(kThreads) tap_gather_kernel(const TapGatherParams p) {
+  const long long total = static_cast<long long>(p.N) * p.H * p.W;
+  const bool is_tanh = p.act == ACT_TANH;
+  const float b0 = p.bias ? p.bias[0] : 0.f, b1 = p.bias ? p.bias[1] : 0.f, b2 = p.bias ? p.bias[2] : 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int w = static_cast<int>(i % p.W);
+    long long r = i / p.W;
+    const int h = static_cast<int>(r % p.H);
+    const int n = static_cast<int>(r / p.H);
+    const long long row0 = (static_cast<long long>(n) * p.Hp + h) * p.Wp + w;
+    float a0 = b0, a1 = b1, a2 = b2;
+#pragma unroll 7
+    for (int s = 0; s < p.k; ++s) {
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(p.q + (row0 + s) * 32 + s * 4));
+      const float2 lo = unpack_bf16x2(u.x), hi = unpack_bf16x2(u.y);
+      a0 += lo.x; a1 += lo.y; a2 += hi.x;
+    }
+    float v[8] = {a0, a1, a2, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (is_tanh) { v[0] = fast_tanh(v[0]); v[1] = fast_tanh(v[1]); v[2] = fast_tanh(v[2]); }
+    store8(vptr_mut(p.out, n, h, w), v);
+  }
+}
+
 // --------------------------------------------------------------------- adam
 __global__ void __launch_bounds__(kThreads) adam_kernel(const AdamParams p) {
   const int t = *p.step + 1;
@@ -671,6 +696,11 @@ void launch_l1_loss(const L1LossParams& p, cudaStream_t s) {
 void launch_mse_loss(const MseLossParams& p, cudaStream_t s) {
   const long long total = static_cast<long long>(p.N) * p.H * p.W;
   mse_loss_kernel<<<grid_for(total, 148), kThreads, 0, s>>>(p);
+}
+
+void launch_tap_gather(const TapGatherParams& p, cudaStream_t s) {
+  const long long total = static_cast<long long>(p.N) * p.H * p.W;
+  tap_gather_kernel<<<grid_for(total), kThreads, 0, s>>>(p);
 }
 
 void launch_adam(const AdamParams& p, cudaStream_t s) {

@@ -130,6 +130,19 @@ void launch_step_increment(int* step, cudaStream_t s);
 // out[i] = 0 where mask[i] == 0 (zero the gradients of structural padding weights)
 void launch_mask_grad(float* g, const uint8_t* mask, long long n, cudaStream_t s);
 
+// Horizontal tap gather of the row-GEMM form of the generator's 7x7 output conv:
+//   out[n,h,w,co] = act(bias[co] + sum_s Q[flat(n,h,w) + s][s*4 + co]),  Q = [rows][32] bf16
+struct TapGatherParams {
+  const __nv_bfloat16* q;   // row-GEMM output, row = padded flat pixel, 32 columns (k*4 used)
+  const float* bias;        // [3]
+  View out;                 // bf16 8-channel image
+  int act;
+  int k;                    // taps per row (7)
+  int Hp, Wp;               // padded dims of the flat domain
+  int N, H, W;
+};
+void launch_tap_gather(const TapGatherParams& p, cudaStream_t s);
+
 // PatchGAN output layer (512 -> 1) backward: SIMT kernels (GEMV-shaped).
 struct D4BwdParams {
   View gd;              // bf16 gradient of the logits, 1 valid channel

@@ -22,6 +22,10 @@
 namespace py = pybind11;
 using namespace b2;
 
+namespace b2 {
+void launch_shift_probe(const CUtensorMap& tmA, const CUtensorMap& tmB, float* out, cudaStream_t s);
+}
+
 namespace {
 
 void check(cudaError_t e, const char* what) {
@@ -113,20 +117,29 @@ void fill_taps(const std::vector<TapT>& taps, Tap* dst, int* n) {
 
 class Plan {
  public:
-  // lane 0 runs on the caller's stream, lane 1 on the plan's side stream; kind 1 = fork
-  // (side waits for main), kind 2 = join (main waits for side). Works under stream capture.
+  // Lanes: lane 0 runs on the caller's stream, lanes 1..3 on the plan's side streams. Sync ops:
+  //   kind 1 fork  : every side lane waits for lane 0
+  //   kind 2 join  : lane 0 waits for every side lane that ran something since the last join
+  //   kind 3 record: record event `ev` on lane `lane`
+  //   kind 4 wait  : lane `lane` waits for the event recorded by op `ref`
+  // All of it is plain event record / wait, so it also works under stream capture (CUDA graph).
+  static constexpr int kLanes = 4;
   struct Op {
     std::string name;
     std::function<void(cudaStream_t)> fn;
     int lane = 0;
     int kind = 0;
+    int ref = -1;
     cudaEvent_t ev = nullptr;
   };
 
   ~Plan() {
     for (auto& o : ops_)
       if (o.ev) cudaEventDestroy(o.ev);
-    if (side_) cudaStreamDestroy(side_);
+    for (auto& s : side_)
+      if (s) cudaStreamDestroy(s);
+    for (auto& e : lane_ev_)
+      if (e) cudaEventDestroy(e);
   }
 
   int add(std::string name, std::function<void(cudaStream_t)> fn) {
@@ -137,17 +150,27 @@ class Plan {
     ops_.push_back(std::move(o));
     return static_cast<int>(ops_.size()) - 1;
   }
-  void set_lane(int lane) { lane_ = lane; }
-  int add_sync(std::string name, int kind) {
+  void set_lane(int lane) {
+    if (lane < 0 || lane >= kLanes) throw std::runtime_error("bad lane");
+    lane_ = lane;
+  }
+  int add_sync(std::string name, int kind, int lane = 0, int ref = -1) {
     Op o;
     o.name = std::move(name);
     o.kind = kind;
-    check(cudaEventCreateWithFlags(&o.ev, cudaEventDisableTiming), "cudaEventCreate");
+    o.lane = lane;
+    o.ref = ref;
+    if (kind != 4) check(cudaEventCreateWithFlags(&o.ev, cudaEventDisableTiming), "cudaEventCreate");
     ops_.push_back(std::move(o));
     return static_cast<int>(ops_.size()) - 1;
   }
   int add_fork(std::string name) { return add_sync(std::move(name), 1); }
   int add_join(std::string name) { return add_sync(std::move(name), 2); }
+  int add_event_record(std::string name, int lane) { return add_sync(std::move(name), 3, lane); }
+  int add_event_wait(std::string name, int lane, int ref) {
+    if (ref < 0 || ref >= size() || ops_[ref].kind != 3) throw std::runtime_error("bad event ref");
+    return add_sync(std::move(name), 4, lane, ref);
+  }
   int size() const { return static_cast<int>(ops_.size()); }
   std::vector<std::string> names() const {
     std::vector<std::string> n;
@@ -155,30 +178,53 @@ class Plan {
     return n;
   }
 
+  cudaStream_t lane_stream(int lane, cudaStream_t main) {
+    if (lane == 0) return main;
+    if (side_[lane] == nullptr)
+      check(cudaStreamCreateWithFlags(&side_[lane], cudaStreamNonBlocking), "side stream");
+    return side_[lane];
+  }
+
+  void join_dirty(cudaStream_t s, bool* dirty) {
+    for (int l = 1; l < kLanes; ++l) {
+      if (!dirty[l]) continue;
+      if (lane_ev_[l] == nullptr)
+        check(cudaEventCreateWithFlags(&lane_ev_[l], cudaEventDisableTiming), "cudaEventCreate");
+      check(cudaEventRecord(lane_ev_[l], side_[l]), "join record");
+      check(cudaStreamWaitEvent(s, lane_ev_[l], 0), "join wait");
+      dirty[l] = false;
+    }
+  }
+
   void run(int begin, int end, uint64_t stream, bool check_each) {
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (end < 0 || end > size()) end = size();
-    if (side_ == nullptr) check(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking), "side stream");
     bool forked = false;
+    bool dirty[kLanes] = {false, false, false, false};
     for (int i = begin; i < end; ++i) {
       Op& o = ops_[i];
-      if (o.kind == 1) {
-        if (!check_each) {
+      if (o.kind != 0) {
+        if (check_each) continue;          // debug mode: everything serial on the caller's stream
+        if (o.kind == 1) {
           check(cudaEventRecord(o.ev, s), "fork record");
-          check(cudaStreamWaitEvent(side_, o.ev, 0), "fork wait");
+          for (int l = 1; l < kLanes; ++l)
+            check(cudaStreamWaitEvent(lane_stream(l, s), o.ev, 0), "fork wait");
           forked = true;
-        }
-        continue;
-      }
-      if (o.kind == 2) {
-        if (forked) {
-          check(cudaEventRecord(o.ev, side_), "join record");
-          check(cudaStreamWaitEvent(s, o.ev, 0), "join wait");
+        } else if (o.kind == 2) {
+          join_dirty(s, dirty);
           forked = false;
+        } else if (o.kind == 3) {
+          if (forked || o.lane == 0) check(cudaEventRecord(o.ev, lane_stream(forked ? o.lane : 0, s)), "record");
+        } else if (o.kind == 4) {
+          // a wait whose record op lies outside [begin, end) (partial ranges) is skipped
+          if (forked && o.ref >= begin)
+            check(cudaStreamWaitEvent(lane_stream(o.lane, s), ops_[o.ref].ev, 0), "wait");
         }
         continue;
       }
-      o.fn((forked && o.lane == 1) ? side_ : s);
+      const int lane = forked ? o.lane : 0;
+      if (lane != 0) dirty[lane] = true;
+      o.fn(lane_stream(lane, s));
       if (check_each) {
         cudaError_t e = cudaStreamSynchronize(s);
         if (e == cudaSuccess) e = cudaGetLastError();
@@ -187,13 +233,7 @@ class Plan {
                                    ") failed: " + cudaGetErrorString(e));
       }
     }
-    if (forked) {   // range ended inside a forked region: always re-join
-      cudaEvent_t e;
-      check(cudaEventCreateWithFlags(&e, cudaEventDisableTiming), "cudaEventCreate");
-      check(cudaEventRecord(e, side_), "join record");
-      check(cudaStreamWaitEvent(s, e, 0), "join wait");
-      cudaEventDestroy(e);
-    }
+    join_dirty(s, dirty);   // a range that ends inside a forked region always re-joins
     check(cudaGetLastError(), "plan launch");
   }
 
@@ -316,6 +356,12 @@ class Plan {
                     view_from(g), N, H, W};
     return add(std::move(name), [p](cudaStream_t s) { launch_mse_loss(p, s); });
   }
+  int add_tap_gather(std::string name, uint64_t q, uint64_t bias, ViewT out, int act, int k, int Hp,
+                     int Wp, int N, int H, int W) {
+    TapGatherParams p{P<const __nv_bfloat16>(q), P<const float>(bias), view_from(out), act, k, Hp, Wp,
+                      N, H, W};
+    return add(std::move(name), [p](cudaStream_t s) { launch_tap_gather(p, s); });
+  }
   int add_adam(std::string name, uint64_t w, uint64_t m, uint64_t v, uint64_t g, uint64_t w_bf16,
                uint64_t step, float lr, float b1, float b2, float eps, float grad_scale,
                long long n) {
@@ -379,7 +425,8 @@ class Plan {
  private:
   std::vector<Op> ops_;
   int lane_ = 0;
-  cudaStream_t side_ = nullptr;
+  cudaStream_t side_[kLanes] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t lane_ev_[kLanes] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 }  // namespace
@@ -388,6 +435,10 @@ PYBIND11_MODULE(_C, m) {
   m.doc() = "b200-cyclegan native runtime (sm_100a kernels + plan executor)";
   m.def("encode_tmap", &encode_tmap, py::arg("ptr"), py::arg("dtype"), py::arg("dims"),
         py::arg("strides_bytes"), py::arg("box"), py::arg("swizzle") = 3);
+  m.def("shift_probe", [](py::bytes a, py::bytes b, uint64_t out) {
+    b2::launch_shift_probe(tmap_from(a), tmap_from(b), P<float>(out), nullptr);
+    check(cudaDeviceSynchronize(), "shift_probe");
+  });
   m.def("device_sync", []() { check(cudaDeviceSynchronize(), "cudaDeviceSynchronize"); });
   m.attr("MAX_TAPS") = kMaxTaps;
   py::class_<Plan>(m, "Plan")
@@ -399,6 +450,8 @@ PYBIND11_MODULE(_C, m) {
       .def("set_lane", &Plan::set_lane)
       .def("add_fork", &Plan::add_fork)
       .def("add_join", &Plan::add_join)
+      .def("add_event_record", &Plan::add_event_record)
+      .def("add_event_wait", &Plan::add_event_wait)
       .def("run_timed", &Plan::run_timed, py::arg("begin") = 0, py::arg("end") = -1,
            py::arg("stream") = 0)
       .def("add_conv_gemm", &Plan::add_conv_gemm)
@@ -410,6 +463,7 @@ PYBIND11_MODULE(_C, m) {
       .def("add_img_prep", &Plan::add_img_prep)
       .def("add_l1_loss", &Plan::add_l1_loss)
       .def("add_mse_loss", &Plan::add_mse_loss)
+      .def("add_tap_gather", &Plan::add_tap_gather)
       .def("add_adam", &Plan::add_adam)
       .def("add_step_increment", &Plan::add_step_increment)
       .def("add_mask_grad", &Plan::add_mask_grad)

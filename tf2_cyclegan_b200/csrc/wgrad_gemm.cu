@@ -14,6 +14,8 @@
 
 namespace b2 {
 
+int dbg_flag();
+
 template <int BLOCK_N>
 struct WgradCfg {
   static constexpr int kABytes = 2 * 64 * 128;          // 128 co x 64 pixels (2 MN atoms)
@@ -61,7 +63,7 @@ __device__ __forceinline__ void wgrad_epilogue(const WgradParams& p, uint8_t* st
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(256, 1)
-wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
+wgrad_gemm_kernel(const __grid_constant__ WgradParams p, int dbg) {
   using Cfg = WgradCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -144,7 +146,7 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
           const uint64_t db = make_desc_mnmajor(sb, 64);
 #pragma unroll
           for (int k = 0; k < 4; ++k)   // 16 pixels per MMA = 16 rows x 128 B = 128 x 16-byte units
-            umma_bf16(tmem_base, da + static_cast<uint64_t>(k * 128),
+            if (dbg != 2) umma_bf16(tmem_base, da + static_cast<uint64_t>(k * 128),
                       db + static_cast<uint64_t>(k * 128), idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[s]);
         }
@@ -156,7 +158,7 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
-      wgrad_epilogue<BLOCK_N>(p, smem, taddr, e, m0 + e, n0, tap.bk);
+      if (dbg != 1) wgrad_epilogue<BLOCK_N>(p, smem, taddr, e, m0 + e, n0, tap.bk);
     }
   }
   tc_fence_before();
@@ -176,7 +178,7 @@ static void launch_t(const WgradParams& p, int ksplit, cudaStream_t stream) {
   const int m_tiles = (p.cout + 127) / 128;
   const int n_tiles = (p.cin + BLOCK_N - 1) / BLOCK_N;
   dim3 grid(m_tiles * n_tiles, p.num_taps, ksplit);
-  wgrad_gemm_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(p);
+  wgrad_gemm_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(p, dbg_flag());
 }
 
 
@@ -199,7 +201,7 @@ struct Wgrad2Cfg {
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(256, 1)
-wgrad_gemm2_kernel(const __grid_constant__ WgradParams p) {
+wgrad_gemm2_kernel(const __grid_constant__ WgradParams p, int dbg) {
   using Cfg = Wgrad2Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -284,7 +286,7 @@ wgrad_gemm2_kernel(const __grid_constant__ WgradParams p) {
           const uint64_t db = make_desc_mnmajor(sb, 64);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16_2sm(tmem_base, da + static_cast<uint64_t>(k * 128),
+            if (dbg != 2) umma_bf16_2sm(tmem_base, da + static_cast<uint64_t>(k * 128),
                           db + static_cast<uint64_t>(k * 128), idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit_2sm(&empty_bar[s]);
         }
@@ -296,7 +298,7 @@ wgrad_gemm2_kernel(const __grid_constant__ WgradParams p) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
-      wgrad_epilogue<BLOCK_N>(p, smem, taddr, e, m0 + e, n0, tap.bk);
+      if (dbg != 1) wgrad_epilogue<BLOCK_N>(p, smem, taddr, e, m0 + e, n0, tap.bk);
     }
   }
   tc_fence_before();
@@ -327,7 +329,7 @@ static void launch2_t(const WgradParams& p, int ksplit, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, wgrad_gemm2_kernel<BLOCK_N>, p);
+  cudaLaunchKernelEx(&cfg, wgrad_gemm2_kernel<BLOCK_N>, p, dbg_flag());
 }
 
 static bool wgrad_use_2cta() {

@@ -147,20 +147,21 @@ class StepPlan:
                  gout_view=self.gd_adv[D].view(0), gout_is_dy=True)
       plan.add_memset(f"zero.{D}.bstats2", e.bstat_arena.data_ptr(), e.bstat_arena.numel() * 4)
 
-    def full(n):
+    def full(n, lanes=None):
       e = self.ex[n]
       if n in ("G", "F"):
-        e.backward(plan, 0, 3 * b, wgrad=True)
+        e.backward(plan, 0, 3 * b, wgrad=True, lanes=lanes)
       else:
-        e.backward(plan, 0, 2 * b, wgrad=True, gout_is_dy=True)
+        e.backward(plan, 0, 2 * b, wgrad=True, gout_is_dy=True, lanes=lanes)
       self.marks[f"{n}_bwd_end"] = plan.size()
       be.emit_optimizer(plan, n)
       self.marks[f"{n}_opt_end"] = plan.size()
 
     if two:
       fork("bwd")
-      lane(0); adv("Y", "G"); full("G"); full("Y")
-      lane(1); adv("X", "F"); full("F"); full("X")
+      wl = be.wgrad_lanes
+      lane(0); adv("Y", "G"); full("G", (0, 2) if wl else None); full("Y", (0, 2) if wl else None)
+      lane(1); adv("X", "F"); full("F", (1, 3) if wl else None); full("X", (1, 3) if wl else None)
       join("bwd")
     else:
       adv("Y", "G"); adv("X", "F")
@@ -198,6 +199,7 @@ class NativeBackend:
     self.world = strategy.world_size
     self.fused = (fused_allreduce in ("auto", "on")) and self.world > 1
     self.two_lanes = os.environ.get("B2_ONE_STREAM", "0") != "1"
+    self.wgrad_lanes = os.environ.get("B2_WGRAD_LANES", "1") != "0"
     gen = torch.Generator().manual_seed(seed)
     self.state: Dict[str, NetState] = OrderedDict()
     self.symm = None

@@ -147,6 +147,8 @@ class NetExec:
     """Derived weight matrices for the small-channel layers' dgrad."""
     st = self.st
     self.w_dgrad: Dict[int, torch.Tensor] = {}
+    self.w_rowgemm: Dict[int, torch.Tensor] = {}
+    self.q_buf: Dict[int, torch.Tensor] = {}
     for j, l in enumerate(self.layers):
       if l.kind == "conv" and l.cout < 8 and l.cout > 1:
         # generator final conv (Cout = 3): dgrad B (K-major) Wfd[ci][r*64 + jj*8 + co] = K[r][k-1-jj][ci][co]
@@ -155,6 +157,11 @@ class NetExec:
         for jj in range(l.k):
           d[:, :, jj, :l.cout] = idx_tf[:, l.k - 1 - jj, :, :].permute(1, 0, 2)
         self.w_dgrad[j] = st.add_derived(f"{self.tag}.L{j}.dgradW", d.reshape(l.cin, l.k * 64))
+        # forward as a row-GEMM: Q[q][s*4 + co] = sum_{r,ci} a_pad[q + r*P][ci] K[r][s][ci][co]
+        q = torch.full((32, l.k, l.cin), -1, dtype=torch.int64)
+        for ss in range(l.k):
+          q[ss * 4:ss * 4 + l.cout] = idx_tf[:, ss, :, :].permute(2, 0, 1)        # [co, r, ci]
+        self.w_rowgemm[j] = st.add_derived(f"{self.tag}.L{j}.rowW", q.reshape(32, l.k * l.cin))
       elif is_small_cin(l) and l.stride == 2:
         # PatchGAN conv0 (Cin = 3): dgrad B (K-major) W[c(16)][(r*k+s)*cout + co] = K[r][s][c][co]
         idx_tf = st.layout.index_tensor(l)                       # [k, k, cin, cout]
@@ -239,6 +246,20 @@ class NetExec:
         phases = [(no.taps_convT_phase(a, b, l.cin), a * dst.sh + b * dst.sw) for a in (0, 1) for b in (0, 1)]
         no.add_conv(plan, name, [amap], [], l.cin, w2, view, hi, wi, nimg, l.cout, bias, act, stats,
                     phases=phases)
+      elif j in self.w_rowgemm:
+        # small-Cout reflect conv (generator output layer): one GEMM tap per kernel ROW over the flat
+        # padded domain (A traffic / k), then a k-tap horizontal gather fused with bias + tanh
+        if j not in self.q_buf:
+          self.q_buf[j] = torch.zeros((self.nb * src.hp * src.wp + 256) * 32, dtype=torch.bfloat16,
+                                      device=src.t.device)
+        qb = self.q_buf[j]
+        rows = nimg * src.hp * src.wp
+        qptr = qb.data_ptr() + 2 * 32 * n0 * src.hp * src.wp
+        taps = [(0, 0, r * src.wp, 0, r * l.cin) for r in range(l.k)]
+        no.add_conv_flat(plan, name, src.tmap_flat(n0, nimg), taps, l.cin, self.w_rowgemm[j], qptr, 32,
+                         rows, 32, block_n=32)
+        plan.add_tap_gather(f"{self.tag}.{l.name}.gather[{n0}:{n0 + nimg}]", qptr, bias, dst.view(n0), act,
+                            l.k, src.hp, src.wp, nimg, ho, wo)
       else:
         bw, bh = nv.tile_shape(ho, wo)
         if is_small_cin(l):
@@ -263,7 +284,8 @@ class NetExec:
   # -------------------------------------------------------------- backward
   def backward(self, plan, n0: int, nimg: int, wgrad: bool, stop_layer: int = 0,
                input_grad_target: Optional[Tuple[Buf, int]] = None,
-               gout_view=None, gout_is_dy: bool = False):
+               gout_view=None, gout_is_dy: bool = False,
+               lanes: Optional[Tuple[int, int]] = None):
     """Emit the backward pass for images [n0, n0 + nimg).
 
     ``gout_view``: view of the gradient wrt the network output (default: self.gout_final).
@@ -271,7 +293,11 @@ class NetExec:
     ``wgrad``: accumulate parameter gradients into the flat fp32 gradient buffer.
     ``input_grad_target``: (Buf, image offset) receiving the gradient wrt the input image
     (only for the adversarial pass through a discriminator); otherwise the first layer
-    has no dgrad. Layers below ``stop_layer`` are skipped entirely."""
+    has no dgrad. Layers below ``stop_layer`` are skipped entirely.
+    ``lanes``: (main lane, wgrad lane): weight-gradient GEMMs are issued on their own stream —
+    nothing downstream of a layer depends on its wgrad — so they fill the tail waves of the
+    dgrad / normalisation chain; the caller joins the wgrad lane before the optimizer."""
+    main_lane, wg_lane = lanes if lanes is not None else (None, None)
     self.enable_backward()
     st = self.st
     L = len(self.layers)
@@ -325,13 +351,23 @@ class NetExec:
 
       # ---- 2. wgrad
       if wgrad:
-        self._wgrad(plan, j, n0, nimg, f"{tagj}.wgrad{rng}")
+        if wg_lane is not None:
+          ev = plan.add_event_record(f"sync.rec.{tagj}.dY", main_lane)
+          plan.set_lane(wg_lane)
+          plan.add_event_wait(f"sync.wait.{tagj}.dY", wg_lane, ev)
+          self._wgrad(plan, j, n0, nimg, f"{tagj}.wgrad{rng}")
+          plan.set_lane(main_lane)
+        else:
+          self._wgrad(plan, j, n0, nimg, f"{tagj}.wgrad{rng}")
       # ---- 3. dgrad
       if need_dgrad:
         g1 = self._dgrad(plan, j, n0, nimg, f"{tagj}.dgrad{rng}", input_grad_target if j == 0 else None)
         if l.res == "a" and pending_skip is not None:
           g2 = pending_skip
           pending_skip = None
+    if wgrad and wg_lane is not None:
+      ev = plan.add_event_record(f"sync.rec.{self.tag}.wgrad_done", wg_lane)
+      plan.add_event_wait(f"sync.wait.{self.tag}.wgrad_done", main_lane, ev)
 
   def _wgrad(self, plan, j: int, n0: int, nimg: int, name: str):
     l = self.layers[j]

@@ -154,6 +154,7 @@ def wmat_tmap(w2: torch.Tensor, block_n: int, mn_major: bool) -> bytes:
 
 def pick_block_n(cout: int) -> int:
   if cout <= 16: return 16
+  if cout <= 32: return 32
   if cout <= 64: return 64
   if cout <= 128: return 128
   return 256
