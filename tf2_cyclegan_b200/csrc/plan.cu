@@ -306,6 +306,18 @@ class Plan {
     });
   }
 
+  int add_wgrad_row(std::string name, py::bytes dy_map, py::bytes a_map, int tiles_w, int H,
+                    int num_images, int cin, int cout, uint64_t dw, long long ldw, int ksplit) {
+    auto p = std::make_shared<WgradRowParams>();
+    memset(p.get(), 0, sizeof(WgradRowParams));
+    p->tmDY = tmap_from(dy_map);
+    p->tmA = tmap_from(a_map);
+    if (cin % 128 || cout % 256) throw std::runtime_error("wgrad_row: cin % 128 / cout % 256");
+    p->tiles_w = tiles_w; p->H = H; p->num_images = num_images; p->cin = cin; p->cout = cout;
+    p->dw = P<float>(dw); p->ldw = ldw;
+    return add(std::move(name), [p, ksplit](cudaStream_t s) { launch_wgrad_row(*p, ksplit, s); });
+  }
+
   // ------------------------------------------------------ elementwise ops
   int add_in_apply(std::string name, ViewT x, uint64_t stats, uint64_t gamma, uint64_t beta,
                    float inv_count, float eps, int act, ViewT skip, ViewT dst, int halo, int N,
@@ -456,6 +468,7 @@ PYBIND11_MODULE(_C, m) {
            py::arg("stream") = 0)
       .def("add_conv_gemm", &Plan::add_conv_gemm)
       .def("add_wgrad", &Plan::add_wgrad)
+      .def("add_wgrad_row", &Plan::add_wgrad_row)
       .def("add_in_apply", &Plan::add_in_apply)
       .def("add_in_bwd_reduce", &Plan::add_in_bwd_reduce)
       .def("add_in_bwd_apply", &Plan::add_in_bwd_apply)
