@@ -148,5 +148,7 @@ def add_wgrad_row(plan, name: str, dY: Buf, src: Buf, n0: int, nimg: int, cin: i
 
 def wgrad_row_ok(l, wo: int) -> bool:
   import os
-  return (os.environ.get("B2_WGRAD_ROW", "1") != "0" and l.kind == "conv" and l.k == 3 and l.stride == 1
+  # measured on B200 (profiles/): correct, but ~8% slower than the generic 2-CTA kernel because both
+  # are bound by shared-memory operand bandwidth, not by L2 bytes -> opt-in only
+  return (os.environ.get("B2_WGRAD_ROW", "0") == "1" and l.kind == "conv" and l.k == 3 and l.stride == 1
           and l.pad == "reflect" and l.cin % 128 == 0 and l.cout % 256 == 0 and wo % 64 == 0)
