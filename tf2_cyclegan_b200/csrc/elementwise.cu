@@ -78,7 +78,7 @@ __device__ __forceinline__ void gather_g(const View& g1, int fold, const View& g
 // ------------------------------------------------------------------ in_apply
 // grid: (pixel chunks, N). A thread owns one 8-channel group (coefficients live in
 // registers) and walks pixels, 4 at a time so that several 16-byte loads are in flight.
-__global__ void __launch_bounds__(kThreads, 2) in_apply_kernel(const InApplyParams p, int pix_per_block) {
+__global__ void __launch_bounds__(kThreads, 4) in_apply_kernel(const InApplyParams p, int pix_per_block) {
   const int c8 = p.C >> 3;
   const int lanes = kThreads / c8;
   const int c = (threadIdx.x % c8) * 8;
@@ -87,8 +87,10 @@ __global__ void __launch_bounds__(kThreads, 2) in_apply_kernel(const InApplyPara
   const int HW = p.H * p.W;
   const int pix0 = blockIdx.x * pix_per_block;
   const int pix1 = min(HW, pix0 + pix_per_block);
-  // per-channel affine coefficients, computed once per block (thread t -> channel t)
-  extern __shared__ float coef[];   // [2][C]
+  // per-channel affine coefficients (a, b), computed once per block (thread t -> channel t) and
+  // read back from shared memory at use: few registers -> 4 blocks / SM -> more loads in flight
+  extern __shared__ float coef[];   // float2[C]
+  float2* ab = reinterpret_cast<float2*>(coef);
   for (int ch = threadIdx.x; ch < p.C; ch += kThreads) {
     float a = 1.f, b = 0.f;
     if (p.stats != nullptr) {
@@ -98,13 +100,9 @@ __global__ void __launch_bounds__(kThreads, 2) in_apply_kernel(const InApplyPara
       a = rsqrtf(var + p.eps) * __ldg(p.gamma + ch);
       b = __ldg(p.beta + ch) - mean * a;
     }
-    coef[ch] = a;
-    coef[p.C + ch] = b;
+    ab[((ch & 7) >> 1) * 2 * c8 + (ch >> 3) * 2 + (ch & 1)] = make_float2(a, b);
   }
   __syncthreads();
-  float ca[8], cb[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { ca[j] = coef[c + j]; cb[j] = coef[p.C + c + j]; }
   const bool has_skip = p.skip.p != nullptr;
   const float slope = act_slope(p.act);
   constexpr int U = 4;
@@ -127,19 +125,21 @@ __global__ void __launch_bounds__(kThreads, 2) in_apply_kernel(const InApplyPara
       if (pix >= pix1) continue;
       const uint32_t xw[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
       const uint32_t sw[4] = {sv[u].x, sv[u].y, sv[u].z, sv[u].w};
-      float v[8];
+      uint32_t ow[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 t = unpack_bf16x2(xw[j]);
-        v[2 * j] = apply_slope(fmaf(t.x, ca[2 * j], cb[2 * j]), slope);
-        v[2 * j + 1] = apply_slope(fmaf(t.y, ca[2 * j + 1], cb[2 * j + 1]), slope);
+        const float4 k = *reinterpret_cast<const float4*>(&ab[(j * c8 + (c >> 3)) * 2]);   // (a0, b0, a1, b1)
+        float v0 = apply_slope(fmaf(t.x, k.x, k.y), slope);
+        float v1 = apply_slope(fmaf(t.y, k.z, k.w), slope);
         if (has_skip) {
-          const float2 k = unpack_bf16x2(sw[j]);
-          v[2 * j] += k.x;
-          v[2 * j + 1] += k.y;
+          const float2 q = unpack_bf16x2(sw[j]);
+          v0 += q.x;
+          v1 += q.y;
         }
+        ow[j] = pack_bf16x2(v0, v1);
       }
-      const uint4 pk = pack8(v);
+      const uint4 pk = make_uint4(ow[0], ow[1], ow[2], ow[3]);
       *reinterpret_cast<uint4*>(vptr_mut(p.dst, n, hh[u], ww[u]) + c) = pk;
       if (p.halo > 0) {
         int hs[2], ws[2];
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(kThreads, 2) in_apply_kernel(const InApplyPara
 
 // ------------------------------------------------------------ in_bwd_reduce
 // grid: (pixel chunks, N). Threads: (C/8 channel groups) x (256 / (C/8) pixel lanes).
-__global__ void __launch_bounds__(kThreads, 2) in_bwd_reduce_kernel(const InBwdReduceParams p,
+__global__ void __launch_bounds__(kThreads, 3) in_bwd_reduce_kernel(const InBwdReduceParams p,
                                                                  int pix_per_block) {
   extern __shared__ float red[];   // [lanes][C][2]
   const int c8 = p.C >> 3;
@@ -169,27 +169,16 @@ __global__ void __launch_bounds__(kThreads, 2) in_bwd_reduce_kernel(const InBwdR
   const int pix0 = blockIdx.x * pix_per_block;
   const int pix1 = min(HW, pix0 + pix_per_block);
 
-  float mean[8], rstd[8], gam[8], bet[8];
   const bool has_in = p.stats != nullptr;
+  float4* mrgb = reinterpret_cast<float4*>(red + lanes * p.C * 2);   // float4[C] = (mean, rstd, gamma, beta)
   if (has_in) {
-    float* coef = red + lanes * p.C * 2;   // [4][C]
     for (int ch = threadIdx.x; ch < p.C; ch += kThreads) {
       const float* st = p.stats + (static_cast<long long>(n) * p.C + ch) * 2;
       const float mu = st[0] * p.inv_count;
       const float var = fmaxf(st[1] * p.inv_count - mu * mu, 0.f);
-      coef[ch] = mu;
-      coef[p.C + ch] = rsqrtf(var + p.eps);
-      coef[2 * p.C + ch] = __ldg(p.gamma + ch);
-      coef[3 * p.C + ch] = __ldg(p.beta + ch);
+      mrgb[(ch & 7) * c8 + (ch >> 3)] = make_float4(mu, rsqrtf(var + p.eps), __ldg(p.gamma + ch), __ldg(p.beta + ch));
     }
     __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      mean[j] = coef[c + j];
-      rstd[j] = coef[p.C + c + j];
-      gam[j] = coef[2 * p.C + c + j];
-      bet[j] = coef[3 * p.C + c + j];
-    }
   }
   float s1[8], s2[8];
 #pragma unroll
@@ -197,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 2) in_bwd_reduce_kernel(const InBwdR
 
   const bool has_g2 = p.g2.p != nullptr;
   const float slope = act_slope(p.act);
-  constexpr int U = 4;
+  constexpr int U = 2;
   for (int base = pix0 + ln; base < pix1; base += lanes * U) {
     uint4 gv[U], g2v[U], xv[U];
     int hh[U], ww[U];
@@ -251,8 +240,9 @@ __global__ void __launch_bounds__(kThreads, 2) in_bwd_reduce_kernel(const InBwdR
 #pragma unroll
           for (int q = 0; q < 2; ++q) {
             const int jj = 2 * j + q;
-            const float xh = (xs[q] - mean[jj]) * rstd[jj];
-            const float y = xh * gam[jj] + bet[jj];
+            const float4 k = mrgb[jj * c8 + (c >> 3)];
+            const float xh = (xs[q] - k.x) * k.y;
+            const float y = xh * k.z + k.w;
             g[jj] *= act_grad_from_pre(y, slope);
             const float gq = __bfloat162float(__float2bfloat16(g[jj]));   // stats of the stored value
             s1[jj] += gq;
@@ -279,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, 2) in_bwd_reduce_kernel(const InBwdR
 
 // ------------------------------------------------------------- in_bwd_apply
 // dx = A*dy + B*x + C per channel (A = gamma*rstd, B = -gamma*rstd^2*m2, C = gamma*rstd*(mean*rstd*m2 - m1))
-__global__ void __launch_bounds__(kThreads, 2) in_bwd_apply_kernel(const InBwdApplyParams p, int pix_per_block) {
+__global__ void __launch_bounds__(kThreads, 4) in_bwd_apply_kernel(const InBwdApplyParams p, int pix_per_block) {
   const int c8 = p.C >> 3;
   const int lanes = kThreads / c8;
   const int c = (threadIdx.x % c8) * 8;
@@ -300,7 +290,8 @@ __global__ void __launch_bounds__(kThreads, 2) in_bwd_apply_kernel(const InBwdAp
       p.dbeta[cc] += db;
     }
   }
-  extern __shared__ float coef[];   // [3][C]
+  extern __shared__ float coef[];   // float4[C] = (A, B, C, -)
+  float4* abc = reinterpret_cast<float4*>(coef);
   for (int ch = threadIdx.x; ch < p.C; ch += kThreads) {
     const float* st = p.stats + (static_cast<long long>(n) * p.C + ch) * 2;
     const float* bs = p.bstats + (static_cast<long long>(n) * p.C + ch) * 2;
@@ -310,18 +301,9 @@ __global__ void __launch_bounds__(kThreads, 2) in_bwd_apply_kernel(const InBwdAp
     const float m1 = bs[0] * p.inv_count;
     const float m2 = bs[1] * p.inv_count;
     const float gr = __ldg(p.gamma + ch) * rstd;
-    coef[ch] = gr;
-    coef[p.C + ch] = -gr * rstd * m2;
-    coef[2 * p.C + ch] = gr * (mean * rstd * m2 - m1);
+    abc[(ch & 7) * c8 + (ch >> 3)] = make_float4(gr, -gr * rstd * m2, gr * (mean * rstd * m2 - m1), 0.f);
   }
   __syncthreads();
-  float kA[8], kB[8], kC[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    kA[j] = coef[c + j];
-    kB[j] = coef[p.C + c + j];
-    kC[j] = coef[2 * p.C + c + j];
-  }
   constexpr int U = 4;
   for (int base = pix0 + ln; base < pix1; base += lanes * U) {
     uint4 dv[U], xv[U];
@@ -342,15 +324,15 @@ __global__ void __launch_bounds__(kThreads, 2) in_bwd_apply_kernel(const InBwdAp
       if (pix >= pix1) continue;
       const uint32_t dw[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
       const uint32_t xw[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
-      float out[8];
+      uint32_t ow[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 d = unpack_bf16x2(dw[j]);
         const float2 x = unpack_bf16x2(xw[j]);
-        out[2 * j] = fmaf(kA[2 * j], d.x, fmaf(kB[2 * j], x.x, kC[2 * j]));
-        out[2 * j + 1] = fmaf(kA[2 * j + 1], d.y, fmaf(kB[2 * j + 1], x.y, kC[2 * j + 1]));
+        const float4 k0 = abc[(2 * j) * c8 + (c >> 3)], k1 = abc[(2 * j + 1) * c8 + (c >> 3)];
+        ow[j] = pack_bf16x2(fmaf(k0.x, d.x, fmaf(k0.y, x.x, k0.z)), fmaf(k1.x, d.y, fmaf(k1.y, x.y, k1.z)));
       }
-      store8(vptr_mut(p.dx, n, hh[u], ww[u]) + c, out);
+      *reinterpret_cast<uint4*>(vptr_mut(p.dx, n, hh[u], ww[u]) + c) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
   }
 }
@@ -675,7 +657,7 @@ void launch_in_bwd_apply(const InBwdApplyParams& p, cudaStream_t s) {
   const int lanes = kThreads / (p.C / 8);
   const int ppb = pick_pix_per_block(HW, p.N, lanes);
   dim3 grid((HW + ppb - 1) / ppb, p.N);
-  in_bwd_apply_kernel<<<grid, kThreads, 3 * p.C * sizeof(float), s>>>(p, ppb);
+  in_bwd_apply_kernel<<<grid, kThreads, 4 * p.C * sizeof(float), s>>>(p, ppb);
 }
 
 void launch_act_bwd(const ActBwdParams& p, cudaStream_t s) {
