@@ -50,7 +50,9 @@ class FakePlan:
     return self._add("conv_gemm", name, len(taps), cout, block_n, b_mn, num_images)
 
   def add_wgrad(self, name, dy_maps, a_maps, taps, ktw, kth, kbw, kbh, nimg, cin, cout, dw, ldw, block_n, ksplit):
-    assert kbw * kbh == 64 and ksplit >= 1 and block_n in (64, 128, 256)
+    assert kbw * kbh == 64 and ksplit != 0 and block_n in (64, 128, 256)
+    if ksplit < 0:   # multi-tap kernel
+      assert cin == 64 and 2 <= len(taps) <= 7 and len(dy_maps) == 1
     for m in dy_maps:
       assert decode(m)["box"][:3] == [64, kbw, kbh]
     for t in taps:

@@ -1,0 +1,77 @@
+"""Data-parallel native training (fused peer-memory reduce + Adam inside the CUDA graph) vs the
+single-process autograd oracle on the full global batch. Needs >= 2 GPUs."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+
+WORKER = r'''
+import os, sys, types, torch
+sys.path.insert(0, os.environ["B2_ROOT"])
+from tf2_cyclegan_b200.engine.cyclegan import build_specs
+from tf2_cyclegan_b200.engine.native_backend import NativeBackend
+from tf2_cyclegan_b200.engine.oracle_backend import OracleBackend
+from tf2_cyclegan_b200.parallel.strategy import Strategy
+st = Strategy(device="cuda")
+specs = build_specs(types.SimpleNamespace(num_residual_blocks=1))
+gbs = 2 * st.world_size
+nb = NativeBackend(specs, gbs, st, seed=21, image_size=128, local_batch=2,
+                   fused_allreduce=os.environ.get("B2_FUSED", "auto"))
+torch.manual_seed(5)
+x = torch.rand(gbs, 128, 128, 3, device="cuda") * 2 - 1
+y = torch.rand(gbs, 128, 128, 3, device="cuda") * 2 - 1
+for _ in range(3):
+  res = st.reduce_dict(nb.train_step(st.shard(x), st.shard(y)))
+sd = nb.state_dict()          # collective (gathers the ZeRO-1 shards)
+ok = True
+if st.rank == 0:
+  one = types.SimpleNamespace(world_size=1, rank=0, device=st.device,
+                              all_reduce_sum=lambda t: t)
+  ob = OracleBackend(specs, gbs, one, seed=21)
+  for n in ob.params:
+    for p in ob.params[n].values():
+      p.data.copy_(p.data.to(torch.bfloat16).float())
+  for _ in range(3):
+    ro = ob.train_step(x, y)
+  for k in ro:
+    a, b = float(res[k]), float(ro[k])
+    if abs(a - b) > 5e-2 * max(abs(b), 0.05):
+      ok = False; print("loss mismatch", k, a, b)
+  osd = ob.state_dict()
+  for k in ("G/layer_with_weights-2/kernel/.ATTRIBUTES/VARIABLE_VALUE",
+            "X/layer_with_weights-1/kernel/.ATTRIBUTES/VARIABLE_VALUE",
+            "F/layer_with_weights-3/gamma/.ATTRIBUTES/VARIABLE_VALUE"):
+    d = (sd[k] - osd[k]).abs().max().item()
+    if d > 2e-3:
+      ok = False; print("weight mismatch", k, d)
+  print("fused =", nb.fused, "multicast =", bool(nb.symm and nb.symm.multicast_ptrs("G")[0]), "ok =", ok)
+flag = torch.tensor([1 if ok else 0], device="cuda")
+st.broadcast(flag, 0)
+st.barrier(); st.shutdown()
+sys.exit(0 if flag.item() == 1 else 1)
+'''
+
+
+def _free_port():
+  with socket.socket() as s:
+    s.bind(("127.0.0.1", 0))
+    return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("fused", ["auto", "off"])
+def test_native_dp_matches_oracle(tmp_path, fused):
+  if torch.cuda.device_count() < 2:
+    pytest.skip("needs >= 2 GPUs")
+  script = tmp_path / "worker.py"
+  script.write_text(WORKER)
+  env = dict(os.environ, B2_ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), B2_FUSED=fused)
+  cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+         "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)]
+  r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+  print(r.stdout[-3000:], r.stderr[-3000:])
+  assert r.returncode == 0

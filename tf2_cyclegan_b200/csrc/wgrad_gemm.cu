@@ -341,7 +341,13 @@ static bool wgrad_use_2cta() {
   return v == 1;
 }
 
+bool launch_wgrad_multi(const WgradParams& p, int ksplit, cudaStream_t stream);
+
 void launch_wgrad_gemm(const WgradParams& p, int block_n, int ksplit, cudaStream_t stream) {
+  if (ksplit < 0) {   // negative ksplit: caller asks for the multi-tap kernel (all taps in one CTA)
+    if (launch_wgrad_multi(p, -ksplit, stream)) return;
+    ksplit = -ksplit;
+  }
   if (wgrad_use_2cta() && p.cout >= 256 && p.cout % 256 == 0 && block_n >= 128) {
     // keep the CTA count: a pair does the work of two single CTAs
     if (block_n == 256) return launch2_t<256>(p, ksplit, stream);

@@ -124,6 +124,10 @@ def add_wgrad(plan, name: str, dy_map, a_maps: Sequence[bytes], taps: Sequence[T
   base = m_tiles * n_tiles * len(taps)
   total_kt = kt_w * kt_h * nimg
   ksplit = max(1, min(total_kt, (target_ctas + base - 1) // base))
+  multi = (cin == 64 and 2 <= len(taps) <= 7 and not isinstance(dy_map, (list, tuple))
+           and os.environ.get("B2_WGRAD_MULTI", "1") != "0")
+  if multi:   # narrow layers: one CTA accumulates all taps (dY tile loaded once per K tile)
+    ksplit = -max(1, min(total_kt, (target_ctas + m_tiles - 1) // m_tiles))
   # dy_map: one view, or a list of views selected per tap through tap[1] (phase-merged wgrad)
   dy_maps = list(dy_map) if isinstance(dy_map, (list, tuple)) else [dy_map]
   return plan.add_wgrad(name, dy_maps, list(a_maps), list(taps), kt_w, kt_h, kbw, kbh, nimg,
