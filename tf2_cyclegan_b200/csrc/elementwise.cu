@@ -106,15 +106,21 @@ __global__ void __launch_bounds__(kThreads, 4) in_apply_kernel(const InApplyPara
   const bool has_skip = p.skip.p != nullptr;
   const float slope = act_slope(p.act);
   constexpr int U = 4;
-  for (int base = pix0 + ln; base < pix1; base += lanes * U) {
+  int hh[U], ww[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {   // one division per slot, then incremental (h, w) updates
+    const int pix = pix0 + ln + u * lanes;
+    hh[u] = pix / p.W;
+    ww[u] = pix - hh[u] * p.W;
+  }
+  const int step = lanes * U;
+  const int step_h = step / p.W, step_w = step - step_h * p.W;
+  for (int base = pix0 + ln; base < pix1; base += step) {
     uint4 xv[U], sv[U];
-    int hh[U], ww[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int pix = base + u * lanes;
       if (pix < pix1) {
-        hh[u] = pix / p.W;
-        ww[u] = pix - hh[u] * p.W;
         xv[u] = __ldg(reinterpret_cast<const uint4*>(vptr(p.x, n, hh[u], ww[u]) + c));
         if (has_skip) sv[u] = __ldg(reinterpret_cast<const uint4*>(vptr(p.skip, n, hh[u], ww[u]) + c));
       }
@@ -141,7 +147,8 @@ __global__ void __launch_bounds__(kThreads, 4) in_apply_kernel(const InApplyPara
       }
       const uint4 pk = make_uint4(ow[0], ow[1], ow[2], ow[3]);
       *reinterpret_cast<uint4*>(vptr_mut(p.dst, n, hh[u], ww[u]) + c) = pk;
-      if (p.halo > 0) {
+      if (p.halo > 0 && (hh[u] <= p.halo || hh[u] >= p.H - 1 - p.halo || ww[u] <= p.halo ||
+                         ww[u] >= p.W - 1 - p.halo)) {   // only border pixels have mirror images
         int hs[2], ws[2];
         const int nh = reflect_set(hh[u], p.H, p.halo, hs);
         const int nw = reflect_set(ww[u], p.W, p.halo, ws);
@@ -150,6 +157,12 @@ __global__ void __launch_bounds__(kThreads, 4) in_apply_kernel(const InApplyPara
             for (int b = 0; b < nw; ++b)
               if (a + b > 0) *reinterpret_cast<uint4*>(vptr_mut(p.dst, n, hs[a], ws[b]) + c) = pk;
       }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      hh[u] += step_h;
+      ww[u] += step_w;
+      if (ww[u] >= p.W) { ww[u] -= p.W; ++hh[u]; }
     }
   }
 }
@@ -187,15 +200,21 @@ __global__ void __launch_bounds__(kThreads, 3) in_bwd_reduce_kernel(const InBwdR
   const bool has_g2 = p.g2.p != nullptr;
   const float slope = act_slope(p.act);
   constexpr int U = 2;
-  for (int base = pix0 + ln; base < pix1; base += lanes * U) {
+  int hh[U], ww[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int pix = pix0 + ln + u * lanes;
+    hh[u] = pix / p.W;
+    ww[u] = pix - hh[u] * p.W;
+  }
+  const int step = lanes * U;
+  const int step_h = step / p.W, step_w = step - step_h * p.W;
+  for (int base = pix0 + ln; base < pix1; base += step) {
     uint4 gv[U], g2v[U], xv[U];
-    int hh[U], ww[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int pix = base + u * lanes;
       if (pix < pix1) {
-        hh[u] = pix / p.W;
-        ww[u] = pix - hh[u] * p.W;
         gv[u] = __ldg(reinterpret_cast<const uint4*>(vptr(p.g1, n, hh[u], ww[u]) + c));
         if (has_g2) g2v[u] = __ldg(reinterpret_cast<const uint4*>(vptr(p.g2, n, hh[u], ww[u]) + c));
         if (has_in) xv[u] = __ldg(reinterpret_cast<const uint4*>(vptr(p.x, n, hh[u], ww[u]) + c));
@@ -217,7 +236,8 @@ __global__ void __launch_bounds__(kThreads, 3) in_bwd_reduce_kernel(const InBwdR
           if (has_g2) { const float2 k = unpack_bf16x2(b[j]); g[2 * j] += k.x; g[2 * j + 1] += k.y; }
         }
       }
-      if (p.fold1 > 0) {   // rare: pixels whose mirror images live in the halo of g1
+      if (p.fold1 > 0 && (h <= p.fold1 || h >= p.H - 1 - p.fold1 || w <= p.fold1 ||
+                          w >= p.W - 1 - p.fold1)) {   // rare: pixels whose mirror images live in the halo of g1
         int hs[2], ws[2];
         const int nh = reflect_set(h, p.H, p.fold1, hs);
         const int nw = reflect_set(w, p.W, p.fold1, ws);
@@ -251,6 +271,12 @@ __global__ void __launch_bounds__(kThreads, 3) in_bwd_reduce_kernel(const InBwdR
         }
       }
       store8(vptr_mut(p.dy, n, h, w) + c, g);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      hh[u] += step_h;
+      ww[u] += step_w;
+      if (ww[u] >= p.W) { ww[u] -= p.W; ++hh[u]; }
     }
   }
   if (!has_in || p.bstats == nullptr) return;
@@ -305,15 +331,21 @@ __global__ void __launch_bounds__(kThreads, 4) in_bwd_apply_kernel(const InBwdAp
   }
   __syncthreads();
   constexpr int U = 4;
-  for (int base = pix0 + ln; base < pix1; base += lanes * U) {
+  int hh[U], ww[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int pix = pix0 + ln + u * lanes;
+    hh[u] = pix / p.W;
+    ww[u] = pix - hh[u] * p.W;
+  }
+  const int step = lanes * U;
+  const int step_h = step / p.W, step_w = step - step_h * p.W;
+  for (int base = pix0 + ln; base < pix1; base += step) {
     uint4 dv[U], xv[U];
-    int hh[U], ww[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int pix = base + u * lanes;
       if (pix < pix1) {
-        hh[u] = pix / p.W;
-        ww[u] = pix - hh[u] * p.W;
         dv[u] = __ldg(reinterpret_cast<const uint4*>(vptr(p.dy, n, hh[u], ww[u]) + c));
         xv[u] = __ldg(reinterpret_cast<const uint4*>(vptr(p.x, n, hh[u], ww[u]) + c));
       }
@@ -333,6 +365,12 @@ __global__ void __launch_bounds__(kThreads, 4) in_bwd_apply_kernel(const InBwdAp
         ow[j] = pack_bf16x2(fmaf(k0.x, d.x, fmaf(k0.y, x.x, k0.z)), fmaf(k1.x, d.y, fmaf(k1.y, x.y, k1.z)));
       }
       *reinterpret_cast<uint4*>(vptr_mut(p.dx, n, hh[u], ww[u]) + c) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      hh[u] += step_h;
+      ww[u] += step_w;
+      if (ww[u] >= p.W) { ww[u] -= p.W; ++hh[u]; }
     }
   }
 }
