@@ -25,7 +25,7 @@ class FakePlan:
     return len(self.ops) - 1
 
   def add_conv_gemm(self, name, a_maps, b_map, taps, cin_blocks, tiles_w, tiles_h, bw, bh, w_limit,
-                    out, sn, sh, sw, cout, bias, act, stats, block_n, b_mn, num_images, phases):
+                    out, sn, sh, sw, cout, bias, act, stats, block_n, b_mn, num_images, phases, out_scale=0, fp8=False):
     assert bw * bh == 128 and 1 <= len(a_maps) <= 4 and 1 <= len(taps) <= 52 and len(phases) <= 4
     if phases:
       assert sum(c for _, c, _ in phases) == len(taps) and all(c >= 1 for _, c, _ in phases)
@@ -33,10 +33,14 @@ class FakePlan:
     assert block_n in (16, 32, 64, 128, 256) and (not b_mn or block_n >= 64)
     for t in taps:
       assert 0 <= t[0] < len(a_maps)
+    kb = 128 if fp8 else 64
     for m in a_maps:
       d = decode(m)
-      assert d["box"][:3] == [64, bw, bh], (name, d["box"], bw, bh)
+      assert d["box"][:3] == [kb, bw, bh], (name, d["box"], bw, bh)
     bd = decode(b_map)
+    if fp8:
+      assert block_n == 256 and not b_mn and out_scale != 0 and bd["box"] == [128, 128]
+      return self._add("conv_gemm_fp8", name, len(taps), cout, block_n, b_mn, num_images)
     assert bd["box"] == ([64, 64] if b_mn else [64, block_n // 2 if block_n >= 128 else block_n]), (name, bd["box"])
     if not b_mn:
       assert bd["dims"][1] >= min(cout, block_n), (name, bd["dims"], cout)
@@ -118,6 +122,7 @@ class FakeModule:
     for b_ in box:
       assert 1 <= b_ <= 256
     esz = {0: 2, 1: 4, 2: 1}[dtype]
+    elem = esz
     assert box[0] * esz == 128 or swizzle != 3, "SWIZZLE_128B needs a 128-byte inner box"
     FakeModule._counter += 1
     key = struct.pack("<Q", FakeModule._counter) + b"\0" * 120

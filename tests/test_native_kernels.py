@@ -362,3 +362,41 @@ def test_wgrad_row_tap_shared():
   run(plan)
   got = no.unpack_conv_weight(dw, 3, cin, cout)
   assert rel_err(got, gk) < 1e-2
+
+
+def test_fp8_conv_and_in_apply_quantisation():
+  """E4M3 x E4M3 conv (kind::f8f6f4, cta_group::2) with epilogue de-scaling, fed by the FP8 side
+  output of the IN-apply kernel; oracle = fp32 conv of the de-quantised operands."""
+  nv, no, O = _mods()
+  C = nv.load()
+  torch.manual_seed(11)
+  n, h, c, cout = 2, 64, 256, 256
+  x = bf(torch.randn(n, h, h, c, device="cuda"))
+  kern = bf(torch.randn(3, 3, c, cout, device="cuda") * 0.05)
+  sa, sb = 32.0, 1024.0
+  # producer: identity IN-apply (no stats) writing bf16 + E4M3 reflect-padded copies
+  xb = nv.Buf(n, h, h, c); xb.t.copy_(x.to(torch.bfloat16))
+  dst = nv.Buf(n, h, h, c, halo=1)
+  dst8 = nv.Buf8(n, h, h, c, halo=1)
+  scale = torch.tensor([sa], device="cuda"); amax = torch.zeros(1, device="cuda")
+  oscale = torch.tensor([1.0 / (sa * sb)], device="cuda")
+  w2 = no.pack_conv_weight(kern)
+  w8 = (w2 * sb).to(torch.float8_e4m3fn).view(torch.uint8).contiguous()
+  out = nv.Buf(n, h, h, cout)
+  stats = torch.zeros(n, cout, 2, device="cuda")
+  plan = C.Plan()
+  plan.add_in_apply("q", xb.view(), 0, 0, 0, 1.0, 1e-3, 0, nv.NULL_VIEW, dst.view(), 1, n, h, h, c,
+                    dst8.view(), scale.data_ptr(), amax.data_ptr())
+  bw, bh = nv.tile_shape(h, h)
+  no.add_conv(plan, "conv.fp8", [dst8.tmap_padded(bw, bh)], no.taps_conv(3, c), c, w8, out.view(), h, h, n,
+              cout, stats=stats.data_ptr(), fp8=True, out_scale=oscale.data_ptr())
+  run(plan)
+  assert abs(amax.item() - x.abs().max().item()) < 1e-2
+  xq = (O.reflect_pad(x, 1) * sa).to(torch.float8_e4m3fn).float() / sa
+  got8 = dst8.t.view(torch.float8_e4m3fn).float() / sa
+  assert (got8 - xq).abs().max().item() == 0
+  wq = no.unpack_conv_weight((w2 * sb).to(torch.float8_e4m3fn).float() / sb, 3, c, cout)
+  ref = O.conv2d(xq, wq, 1, "valid")
+  assert rel_err(out.t, ref) < 1e-2
+  full = O.conv2d(O.reflect_pad(x, 1), kern, 1, "valid")
+  assert rel_err(out.t, full) < 8e-2          # quantisation error of E4M3 operands

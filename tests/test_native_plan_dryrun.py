@@ -58,3 +58,20 @@ def test_flat_layout_roundtrip_and_mask():
     l0 = spec.layers[0]
     idx = lay.index_tensor(l0)
     assert torch.equal(flat[idx], params[f"layer_with_weights-{l0.lw_index}/kernel"])
+
+
+def test_fp8_plan_builds(monkeypatch):
+  fake_native.install(monkeypatch)
+  monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+  from tf2_cyclegan_b200.engine.cyclegan import build_specs
+  from tf2_cyclegan_b200.engine.native_backend import NativeBackend
+  from tf2_cyclegan_b200.parallel.strategy import Strategy
+  be = NativeBackend(build_specs(A(2)), 2, Strategy(device="cpu"), seed=1, image_size=128, local_batch=2,
+                     dtype="fp8")
+  sp = be.plan_for(2)
+  fp8_convs = [n for n in sp.names if n.endswith(".fp8")]
+  # 2 generators x 2 residual blocks x 2 convs x 2 forward passes
+  assert len(fp8_convs) == 16 and all(".res" in n for n in fp8_convs)
+  assert "fp8.G.w_quant" in sp.names and "fp8.F.scales" in sp.names
+  # backward stays bf16: same wgrad / dgrad op names as the bf16 plan
+  assert any(n.startswith("G.res0a.wgrad") for n in sp.names)

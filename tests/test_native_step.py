@@ -147,3 +147,25 @@ def test_cli_end_to_end_native(tmp_path, capsys):
   assert "loaded checkpoint from" in capsys.readouterr().out
   sd2, _ = ckpt.load(prefix)
   assert sd2["G_optimizer/iter/.ATTRIBUTES/VARIABLE_VALUE"].item() == 9
+
+
+def test_fp8_forward_tracks_bf16():
+  """--dtype fp8: residual-block forward convs in E4M3; losses stay close to the bf16 path."""
+  from tf2_cyclegan_b200.engine.cyclegan import build_specs
+  from tf2_cyclegan_b200.engine.native_backend import NativeBackend
+  from tf2_cyclegan_b200.parallel.strategy import Strategy
+  st = Strategy(device="cuda")
+  specs = build_specs(A(2))
+  a = NativeBackend(specs, 2, st, seed=5, image_size=128, local_batch=2, dtype="bf16")
+  f = NativeBackend(specs, 2, st, seed=5, image_size=128, local_batch=2, dtype="fp8")
+  torch.manual_seed(0)
+  x = torch.rand(2, 128, 128, 3, device="cuda") * 2 - 1
+  y = torch.rand(2, 128, 128, 3, device="cuda") * 2 - 1
+  for _ in range(4):
+    ra = a.train_step(x, y)
+    rf = f.train_step(x, y)
+  for k in ra:
+    va, vf = ra[k].item(), rf[k].item()
+    assert vf == vf and abs(va - vf) < 8e-2 * max(abs(va), 0.05), (k, va, vf)
+  s = f.state["G"]
+  assert s.act_scale.min().item() > 0 and (s.w8 != 0).any()

@@ -30,6 +30,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, __nv
   const bool has_bias = p.bias != nullptr;
   const bool is_tanh = p.act == ACT_TANH;
   const float slope = act_slope(p.act);
+  const float oscale = p.out_scale != nullptr ? __ldg(p.out_scale) : 1.f;
 #pragma unroll 1
   for (int c0 = 0; c0 < BLOCK_N; c0 += CN) {
     // ---- TMEM -> registers -> bias / activation -> bf16 -> staging (swizzled rows)
@@ -41,7 +42,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, __nv
         tmem_ld_wait();
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * oscale;
         if (has_bias) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -72,7 +73,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, __nv
       tmem_ld_wait();
       float v[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * oscale;
       if (has_bias) {
 #pragma unroll
         for (int j = 0; j < 16; ++j)

@@ -259,6 +259,13 @@ static bool use_2cta() {
 void launch_conv_gemm(const ConvGemmParams& p, int block_n, bool b_mn_major, int num_images,
                       cudaStream_t stream) {
   // wide layers: CTA pairs (cta_group::2) halve the weight-tile traffic per SM
+  if (p.fp8) {
+    if (!launch_conv_gemm_2cta(p, block_n, b_mn_major, num_images, stream)) {
+      fprintf(stderr, "launch_conv_gemm: fp8 needs block_n == 256, K-major B\n");
+      abort();
+    }
+    return;
+  }
   if (block_n >= 128 && use_2cta() && p.tiles_w * p.tiles_h * num_images >= 2 &&
       launch_conv_gemm_2cta(p, block_n, b_mn_major, num_images, stream))
     return;

@@ -38,6 +38,8 @@ struct ConvGemmParams {
   const float* bias;            // [cout] or nullptr
   int act;                      // b2::Act, applied after bias
   float* stats;                 // [images][cout][2] (sum, sumsq) of the stored bf16 values, or nullptr
+  const float* out_scale;       // device scalar multiplied into the accumulators (FP8 de-scaling), or nullptr
+  int fp8;                      // operands are E4M3 bytes (128 channels per 128-byte K block)
 };
 
 void launch_conv_gemm(const ConvGemmParams& p, int block_n, bool b_mn_major, int num_images,

@@ -34,7 +34,7 @@ struct Gemm2Cfg {
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
-template <int BLOCK_N, bool B_MN>
+template <int BLOCK_N, bool B_MN, bool FP8>
 __global__ void __launch_bounds__(256, 1)
 conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int dbg) {
   using Cfg = Gemm2Cfg<BLOCK_N>;
@@ -132,7 +132,7 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int 
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N, 0, B_MN ? 1 : 0);
+      constexpr uint32_t idesc = FP8 ? make_idesc_e4m3(256, BLOCK_N) : make_idesc_bf16(256, BLOCK_N, 0, B_MN ? 1 : 0);
       uint32_t it = 0, tile_i = 0;
       for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++tile_i) {
         const int num_kb = p.phase_tap_count[pt / pairs_per_phase] * p.cin_blocks;
@@ -155,7 +155,8 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int 
             if (dbg == 2) break;
             const uint64_t da_k = da + static_cast<uint64_t>(k * 2);
             const uint64_t db_k = db + static_cast<uint64_t>(B_MN ? k * 128 : k * 2);
-            umma_bf16_2sm(tmem_d, da_k, db_k, idesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (FP8) umma_f8_2sm(tmem_d, da_k, db_k, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16_2sm(tmem_d, da_k, db_k, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit_2sm(&empty_bar[s]);
         }
@@ -197,12 +198,12 @@ static int num_sms2() {
   return n;
 }
 
-template <int BLOCK_N, bool B_MN>
+template <int BLOCK_N, bool B_MN, bool FP8 = false>
 static void launch2_t(const ConvGemmParams& p, int num_images, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BLOCK_N>;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(conv_gemm2_kernel<BLOCK_N, B_MN>,
+    cudaFuncSetAttribute(conv_gemm2_kernel<BLOCK_N, B_MN, FP8>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     configured = true;
   }
@@ -222,11 +223,16 @@ static void launch2_t(const ConvGemmParams& p, int num_images, cudaStream_t stre
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, conv_gemm2_kernel<BLOCK_N, B_MN>, p, num_images, dbg_flag());
+  cudaLaunchKernelEx(&cfg, conv_gemm2_kernel<BLOCK_N, B_MN, FP8>, p, num_images, dbg_flag());
 }
 
 bool launch_conv_gemm_2cta(const ConvGemmParams& p, int block_n, bool b_mn_major, int num_images,
                            cudaStream_t stream) {
+  if (p.fp8) {
+    if (block_n != 256 || b_mn_major) return false;
+    launch2_t<256, false, true>(p, num_images, stream);
+    return true;
+  }
   if (block_n == 256) {
     if (b_mn_major) launch2_t<256, true>(p, num_images, stream);
     else launch2_t<256, false>(p, num_images, stream);

@@ -1,6 +1,8 @@
 // Bandwidth-bound kernels around the GEMMs (see elementwise.cuh).
 #include <stdlib.h>
 
+#include <cuda_fp8.h>
+
 #include "elementwise.cuh"
 
 namespace b2 {
@@ -105,6 +107,9 @@ __global__ void __launch_bounds__(kThreads, 4) in_apply_kernel(const InApplyPara
   __syncthreads();
   const bool has_skip = p.skip.p != nullptr;
   const float slope = act_slope(p.act);
+  const bool has8 = p.dst8.p != nullptr;
+  const float s8 = has8 ? __ldg(p.scale8) : 1.f;
+  float amax = 0.f;
   constexpr int U = 4;
   int hh[U], ww[U];
 #pragma unroll
@@ -132,6 +137,7 @@ __global__ void __launch_bounds__(kThreads, 4) in_apply_kernel(const InApplyPara
       const uint32_t xw[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
       const uint32_t sw[4] = {sv[u].x, sv[u].y, sv[u].z, sv[u].w};
       uint32_t ow[4];
+      uint16_t o8[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 t = unpack_bf16x2(xw[j]);
@@ -144,9 +150,20 @@ __global__ void __launch_bounds__(kThreads, 4) in_apply_kernel(const InApplyPara
           v1 += q.y;
         }
         ow[j] = pack_bf16x2(v0, v1);
+        if (has8) {
+          amax = fmaxf(amax, fmaxf(fabsf(v0), fabsf(v1)));
+          o8[j] = __nv_cvt_float2_to_fp8x2(make_float2(v0 * s8, v1 * s8), __NV_SATFINITE, __NV_E4M3);
+        }
       }
       const uint4 pk = make_uint4(ow[0], ow[1], ow[2], ow[3]);
       *reinterpret_cast<uint4*>(vptr_mut(p.dst, n, hh[u], ww[u]) + c) = pk;
+      uint2 pk8 = make_uint2(0u, 0u);
+      if (has8) {
+        pk8 = make_uint2(static_cast<uint32_t>(o8[0]) | (static_cast<uint32_t>(o8[1]) << 16),
+                         static_cast<uint32_t>(o8[2]) | (static_cast<uint32_t>(o8[3]) << 16));
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(p.dst8.p) + n * p.dst8.sn + hh[u] * p.dst8.sh +
+                                  ww[u] * p.dst8.sw + c) = pk8;
+      }
       if (p.halo > 0 && (hh[u] <= p.halo || hh[u] >= p.H - 1 - p.halo || ww[u] <= p.halo ||
                          ww[u] >= p.W - 1 - p.halo)) {   // only border pixels have mirror images
         int hs[2], ws[2];
@@ -155,7 +172,12 @@ __global__ void __launch_bounds__(kThreads, 4) in_apply_kernel(const InApplyPara
         if (nh + nw > 2)
           for (int a = 0; a < nh; ++a)
             for (int b = 0; b < nw; ++b)
-              if (a + b > 0) *reinterpret_cast<uint4*>(vptr_mut(p.dst, n, hs[a], ws[b]) + c) = pk;
+              if (a + b > 0) {
+                *reinterpret_cast<uint4*>(vptr_mut(p.dst, n, hs[a], ws[b]) + c) = pk;
+                if (has8)
+                  *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(p.dst8.p) + n * p.dst8.sn +
+                                            hs[a] * p.dst8.sh + ws[b] * p.dst8.sw + c) = pk8;
+              }
       }
     }
 #pragma unroll
@@ -164,6 +186,11 @@ __global__ void __launch_bounds__(kThreads, 4) in_apply_kernel(const InApplyPara
       ww[u] += step_w;
       if (ww[u] >= p.W) { ww[u] -= p.W; ++hh[u]; }
     }
+  }
+  if (has8) {   // delayed-scaling statistics: one atomic per warp (values are >= 0, so int order == float order)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(p.amax8), __float_as_int(amax));
   }
 }
 
@@ -561,6 +588,47 @@ __global__ void __launch_bounds__(kThreads) mask_grad_kernel(float* g, const uin
     if (mask[i] == 0) g[i] = 0.f;
 }
 
+// ------------------------------------------------------------- FP8 bookkeeping
+__global__ void __launch_bounds__(kThreads) fp8_w_amax_kernel(const Fp8Table t) {
+  const int l = blockIdx.y;
+  const __nv_bfloat16* w = t.w + t.w_off[l];
+  float m = 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < t.w_numel[l];
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    m = fmaxf(m, fabsf(__bfloat162float(w[i])));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(t.w_amax + l), __float_as_int(m));
+}
+__device__ __forceinline__ float pow2_scale(float amax, float target) {
+  return exp2f(floorf(log2f(target / amax)));
+}
+__global__ void fp8_scales_kernel(const Fp8Table t) {
+  const int l = threadIdx.x;
+  if (l >= t.num_layers) return;
+  const float a = t.act_amax[l];
+  const float sa = a > 0.f ? pow2_scale(a, 224.f) : t.default_act_scale;   // E4M3 max = 448: 2x headroom
+  const float wa = t.w_amax[l];
+  const float sb = wa > 0.f ? pow2_scale(wa, 224.f) : t.w_scale[l];
+  t.act_scale[l] = sa;
+  t.w_scale[l] = sb;
+  t.out_scale[l] = 1.f / (sa * sb);
+  t.act_amax[l] = 0.f;
+}
+__global__ void __launch_bounds__(kThreads) fp8_w_quant_kernel(const Fp8Table t) {
+  const int l = blockIdx.y;
+  const __nv_bfloat16* w = t.w + t.w_off[l];
+  uint8_t* w8 = t.w8 + t.w_off[l];
+  const float sb = t.w_scale[l];
+  const long long n2 = t.w_numel[l] / 2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n2;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(w + 2 * i));
+    *reinterpret_cast<uint16_t*>(w8 + 2 * i) =
+        __nv_cvt_float2_to_fp8x2(make_float2(v.x * sb, v.y * sb), __NV_SATFINITE, __NV_E4M3);
+  }
+}
+
 // --------------------------------------------------- PatchGAN output layer bwd
 // dX[n,h,w,c] = sum_{r,s} gd[n, h - r + pb, w - s + pb] * W[0][r*4+s][c]
 __global__ void __launch_bounds__(kThreads) d4_dgrad_kernel(const D4BwdParams p) {
@@ -716,6 +784,14 @@ void launch_l1_loss(const L1LossParams& p, cudaStream_t s) {
 void launch_mse_loss(const MseLossParams& p, cudaStream_t s) {
   const long long total = static_cast<long long>(p.N) * p.H * p.W;
   mse_loss_kernel<<<grid_for(total, 148), kThreads, 0, s>>>(p);
+}
+
+void launch_fp8_w_amax(const Fp8Table& t, cudaStream_t s) {
+  fp8_w_amax_kernel<<<dim3(64, t.num_layers), kThreads, 0, s>>>(t);
+}
+void launch_fp8_scales(const Fp8Table& t, cudaStream_t s) { fp8_scales_kernel<<<1, 32, 0, s>>>(t); }
+void launch_fp8_w_quant(const Fp8Table& t, cudaStream_t s) {
+  fp8_w_quant_kernel<<<dim3(64, t.num_layers), kThreads, 0, s>>>(t);
 }
 
 void launch_tap_gather(const TapGatherParams& p, cudaStream_t s) {

@@ -25,6 +25,11 @@ struct InApplyParams {
   View dst;             // bf16 destination
   int halo;             // reflect-pad width written around dst (0 = none)
   int N, H, W, C;
+  // optional FP8 (E4M3) copy of the output for an FP8 consumer conv: bytes = sat(v * *scale8);
+  // |v| maxima are accumulated into *amax8 (delayed scaling). Same logical layout / halo as dst.
+  View dst8;            // uint8 view (strides in bytes), p == nullptr if unused
+  const float* scale8;
+  float* amax8;
 };
 void launch_in_apply(const InApplyParams& p, cudaStream_t s);
 
@@ -142,6 +147,29 @@ struct TapGatherParams {
   int N, H, W;
 };
 void launch_tap_gather(const TapGatherParams& p, cudaStream_t s);
+
+// FP8 weight quantisation + delayed-scaling bookkeeping (per FP8 layer l of a network):
+//   w_amax:  amax_w[l] = max |w| over the layer's kernel segment
+//   scales:  sa = pow2 scale from the previous step's activation amax (default when 0), sb from
+//            amax_w; act_scale[l] = sa, w_scale[l] = sb, out_scale[l] = 1 / (sa * sb); amaxes reset
+//   w_quant: w8 = sat_e4m3(w * w_scale[l])
+constexpr int kMaxFp8Layers = 32;
+struct Fp8Table {
+  long long w_off[kMaxFp8Layers];     // element offset of the kernel segment in the flat buffers
+  long long w_numel[kMaxFp8Layers];
+  int num_layers;
+  const __nv_bfloat16* w;             // bf16 compute copy of the weights (complete on every rank)
+  uint8_t* w8;                        // E4M3 copy (same flat layout)
+  float* act_amax;                    // [L]
+  float* w_amax;                      // [L]
+  float* act_scale;                   // [L]
+  float* w_scale;                     // [L]
+  float* out_scale;                   // [L]
+  float default_act_scale;
+};
+void launch_fp8_w_amax(const Fp8Table& t, cudaStream_t s);
+void launch_fp8_scales(const Fp8Table& t, cudaStream_t s);
+void launch_fp8_w_quant(const Fp8Table& t, cudaStream_t s);
 
 // PatchGAN output layer (512 -> 1) backward: SIMT kernels (GEMV-shaped).
 struct D4BwdParams {

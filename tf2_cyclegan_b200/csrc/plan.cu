@@ -261,7 +261,8 @@ class Plan {
                     std::vector<TapT> taps, int cin_blocks, int tiles_w, int tiles_h, int bw,
                     int bh, int w_limit, uint64_t out, long long sn, long long sh, long long sw,
                     int cout, uint64_t bias, int act, uint64_t stats, int block_n, bool b_mn,
-                    int num_images, std::vector<std::tuple<int, int, long long>> phases) {
+                    int num_images, std::vector<std::tuple<int, int, long long>> phases,
+                    uint64_t out_scale, bool fp8) {
     auto p = std::make_shared<ConvGemmParams>();
     memset(p.get(), 0, sizeof(ConvGemmParams));
     if (a_maps.empty() || a_maps.size() > kMaxAMaps) throw std::runtime_error("bad a_maps");
@@ -273,6 +274,7 @@ class Plan {
     p->bw = bw; p->bh = bh; p->w_limit = w_limit;
     p->out = P<__nv_bfloat16>(out); p->out_sn = sn; p->out_sh = sh; p->out_sw = sw;
     p->cout = cout; p->bias = P<const float>(bias); p->act = act; p->stats = P<float>(stats);
+    p->out_scale = P<const float>(out_scale); p->fp8 = fp8 ? 1 : 0;
     if (phases.empty()) phases.push_back({0, p->num_taps, 0});
     if (phases.size() > kMaxPhases) throw std::runtime_error("too many phases");
     p->num_phases = static_cast<int>(phases.size());
@@ -321,10 +323,10 @@ class Plan {
   // ------------------------------------------------------ elementwise ops
   int add_in_apply(std::string name, ViewT x, uint64_t stats, uint64_t gamma, uint64_t beta,
                    float inv_count, float eps, int act, ViewT skip, ViewT dst, int halo, int N,
-                   int H, int W, int C) {
+                   int H, int W, int C, ViewT dst8, uint64_t scale8, uint64_t amax8) {
     InApplyParams p{view_from(x), P<const float>(stats), P<const float>(gamma),
                     P<const float>(beta), inv_count, eps, act, view_from(skip), view_from(dst),
-                    halo, N, H, W, C};
+                    halo, N, H, W, C, view_from(dst8), P<const float>(scale8), P<float>(amax8)};
     return add(std::move(name), [p](cudaStream_t s) { launch_in_apply(p, s); });
   }
   int add_in_bwd_reduce(std::string name, ViewT g1, int fold1, ViewT g2, ViewT x, uint64_t stats,
@@ -367,6 +369,24 @@ class Plan {
     MseLossParams p{view_from(d), target, loss_scale, grad_scale, P<float>(loss_slot),
                     view_from(g), N, H, W};
     return add(std::move(name), [p](cudaStream_t s) { launch_mse_loss(p, s); });
+  }
+  // kind: 0 = weight amax, 1 = scales (from amaxes), 2 = weight quantisation
+  int add_fp8_op(std::string name, int kind, std::vector<long long> w_off, std::vector<long long> w_numel,
+                 uint64_t w, uint64_t w8, uint64_t act_amax, uint64_t w_amax, uint64_t act_scale,
+                 uint64_t w_scale, uint64_t out_scale, float default_act_scale) {
+    auto t = std::make_shared<Fp8Table>();
+    memset(t.get(), 0, sizeof(Fp8Table));
+    if (w_off.size() > kMaxFp8Layers || w_off.size() != w_numel.size()) throw std::runtime_error("fp8 table");
+    t->num_layers = static_cast<int>(w_off.size());
+    for (size_t i = 0; i < w_off.size(); ++i) { t->w_off[i] = w_off[i]; t->w_numel[i] = w_numel[i]; }
+    t->w = P<const __nv_bfloat16>(w); t->w8 = P<uint8_t>(w8); t->act_amax = P<float>(act_amax);
+    t->w_amax = P<float>(w_amax); t->act_scale = P<float>(act_scale); t->w_scale = P<float>(w_scale);
+    t->out_scale = P<float>(out_scale); t->default_act_scale = default_act_scale;
+    return add(std::move(name), [t, kind](cudaStream_t s) {
+      if (kind == 0) launch_fp8_w_amax(*t, s);
+      else if (kind == 1) launch_fp8_scales(*t, s);
+      else launch_fp8_w_quant(*t, s);
+    });
   }
   int add_tap_gather(std::string name, uint64_t q, uint64_t bias, ViewT out, int act, int k, int Hp,
                      int Wp, int N, int H, int W) {
@@ -466,10 +486,19 @@ PYBIND11_MODULE(_C, m) {
       .def("add_event_wait", &Plan::add_event_wait)
       .def("run_timed", &Plan::run_timed, py::arg("begin") = 0, py::arg("end") = -1,
            py::arg("stream") = 0)
-      .def("add_conv_gemm", &Plan::add_conv_gemm)
+      .def("add_conv_gemm", &Plan::add_conv_gemm, py::arg("name"), py::arg("a_maps"), py::arg("b_map"),
+           py::arg("taps"), py::arg("cin_blocks"), py::arg("tiles_w"), py::arg("tiles_h"), py::arg("bw"),
+           py::arg("bh"), py::arg("w_limit"), py::arg("out"), py::arg("sn"), py::arg("sh"), py::arg("sw"),
+           py::arg("cout"), py::arg("bias"), py::arg("act"), py::arg("stats"), py::arg("block_n"),
+           py::arg("b_mn"), py::arg("num_images"), py::arg("phases"), py::arg("out_scale") = 0,
+           py::arg("fp8") = false)
       .def("add_wgrad", &Plan::add_wgrad)
       .def("add_wgrad_row", &Plan::add_wgrad_row)
-      .def("add_in_apply", &Plan::add_in_apply)
+      .def("add_in_apply", &Plan::add_in_apply, py::arg("name"), py::arg("x"), py::arg("stats"),
+           py::arg("gamma"), py::arg("beta"), py::arg("inv_count"), py::arg("eps"), py::arg("act"),
+           py::arg("skip"), py::arg("dst"), py::arg("halo"), py::arg("N"), py::arg("H"), py::arg("W"),
+           py::arg("C"), py::arg("dst8") = ViewT{0, 0, 0, 0}, py::arg("scale8") = 0, py::arg("amax8") = 0)
+      .def("add_fp8_op", &Plan::add_fp8_op)
       .def("add_in_bwd_reduce", &Plan::add_in_bwd_reduce)
       .def("add_in_bwd_apply", &Plan::add_in_bwd_apply)
       .def("add_act_bwd", &Plan::add_act_bwd)

@@ -49,8 +49,8 @@ class StepPlan:
     self.y_in = torch.zeros(b, S, S, 3, device=dev)
     self.slots = torch.zeros(NUM_SLOTS, device=dev)
     self.ex: Dict[str, NetExec] = {
-        "G": NetExec(be.specs["G"], be.state["G"], 3 * b, S, dev, "G"),
-        "F": NetExec(be.specs["F"], be.state["F"], 3 * b, S, dev, "F"),
+        "G": NetExec(be.specs["G"], be.state["G"], 3 * b, S, dev, "G", fp8=be.fp8),
+        "F": NetExec(be.specs["F"], be.state["F"], 3 * b, S, dev, "F", fp8=be.fp8),
         "X": NetExec(be.specs["X"], be.state["X"], 2 * b, S, dev, "X"),
         "Y": NetExec(be.specs["Y"], be.state["Y"], 2 * b, S, dev, "Y"),
     }
@@ -71,6 +71,9 @@ class StepPlan:
       e = self.ex[n]
       plan.add_memset(f"zero.{n}.stats", e.stat_arena.data_ptr(), e.stat_arena.numel() * 4)
       plan.add_memset(f"zero.{n}.bstats", e.bstat_arena.data_ptr(), e.bstat_arena.numel() * 4)
+    if be.fp8:   # FP8 weight copies + scales for this step (from the previous step's statistics)
+      for n in ("G", "F"):
+        be.state[n].emit_fp8_refresh(plan, n)
     # ---- P1: inputs -> 8-channel padded bf16 layouts
     xi, yi = self.x_in.data_ptr(), self.y_in.data_ptr()
     plan.add_img_prep("prep.x->G0,X1", xi, NULL_VIEW, G.inp[0].view(0), 3, X.inp[0].view(b), b, S, S)
@@ -182,8 +185,9 @@ class NativeBackend:
                fused_allreduce: str = "auto", use_graph: Optional[bool] = None):
     if not nv.available():
       raise RuntimeError("the native backend needs an sm_100 GPU (B200)")
-    if dtype not in ("bf16",):
-      raise NotImplementedError(f"native backend: dtype {dtype!r} is not available yet (bf16 only)")
+    if dtype not in ("bf16", "fp8"):
+      raise NotImplementedError(f"native backend: dtype {dtype!r} is not available (bf16 | fp8)")
+    self.fp8 = dtype == "fp8"   # residual-block forward convs in E4M3 (per-tensor delayed scaling)
     if image_size < 128 or image_size & (image_size - 1):
       raise ValueError("native backend: image_size must be a power of two >= 128 "
                        "(every layer must tile into 128-pixel boxes); use --backend oracle")

@@ -23,7 +23,7 @@ import torch
 from ..models.spec import ConvLayer, NetSpec
 from ..ops import native as nv
 from ..ops import oracle as O
-from ..ops.native import ACT, NULL_VIEW, Buf
+from ..ops.native import ACT, NULL_VIEW, Buf, Buf8
 from . import native_ops as no
 from .native_params import FlatLayout, is_small_cin
 
@@ -49,6 +49,44 @@ class NetState:
     self.mask = self.layout.mask().to(device)
     self.step = torch.zeros(1, dtype=torch.int32, device=device)
     self.derived: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}   # name -> (bf16 dst, int32 idx)
+    self.fp8_layers: List[ConvLayer] = []
+    self.w8: Optional[torch.Tensor] = None
+
+  # ---- FP8 (E4M3, per-tensor power-of-two delayed scaling) for the residual-block convs
+  def enable_fp8(self):
+    if self.w8 is not None:
+      return
+    dev = self.w.device
+    self.fp8_layers = [l for l in self.spec.layers if fp8_ok(l)]
+    L = max(1, len(self.fp8_layers))
+    self.w8 = torch.zeros(self.n, dtype=torch.uint8, device=dev)
+    self.act_amax = torch.zeros(L, device=dev)
+    self.w_amax = torch.zeros(L, device=dev)
+    self.act_scale = torch.ones(L, device=dev)
+    self.w_scale = torch.ones(L, device=dev)
+    self.out_scale = torch.ones(L, device=dev)
+
+  def fp8_slot(self, l: ConvLayer) -> int:
+    return self.fp8_layers.index(l)
+
+  def kernel_fp8(self, l: ConvLayer) -> torch.Tensor:
+    s = self.seg(l, "kernel")
+    return self.w8[s.offset:s.offset + s.numel].view(*s.shape)
+
+  def emit_fp8_refresh(self, plan, tag: str):
+    """Start-of-step bookkeeping: weight amax -> scales (activations: previous step's amax) ->
+    E4M3 weight copy. Reads the bf16 compute copy, which is complete on every rank."""
+    if not self.fp8_layers:
+      return
+    offs = [self.seg(l, "kernel").offset for l in self.fp8_layers]
+    nums = [self.seg(l, "kernel").numel for l in self.fp8_layers]
+    args = (offs, nums, self.wb.data_ptr(), self.w8.data_ptr(), self.act_amax.data_ptr(),
+            self.w_amax.data_ptr(), self.act_scale.data_ptr(), self.w_scale.data_ptr(),
+            self.out_scale.data_ptr(), 16.0)
+    plan.add_memset(f"zero.{tag}.fp8_w_amax", self.w_amax.data_ptr(), self.w_amax.numel() * 4)
+    plan.add_fp8_op(f"fp8.{tag}.w_amax", 0, *args)
+    plan.add_fp8_op(f"fp8.{tag}.scales", 1, *args)
+    plan.add_fp8_op(f"fp8.{tag}.w_quant", 2, *args)
 
   def seg(self, l: ConvLayer, what: str):
     return self.layout.seg(l, what)
@@ -83,6 +121,11 @@ class NetState:
       dst.copy_(src[idx.long().clamp_min(-1)].to(torch.bfloat16).view_as(dst))
 
 
+def fp8_ok(l: ConvLayer) -> bool:
+  """Layers that run their forward conv in FP8: the residual-block 3x3 convs."""
+  return l.kind == "conv" and l.res in ("a", "b") and l.cin % 128 == 0 and l.cout == 256
+
+
 def _out_hw(l: ConvLayer, h: int, w: int) -> Tuple[int, int]:
   return l.out_hw(h, w)
 
@@ -90,8 +133,12 @@ def _out_hw(l: ConvLayer, h: int, w: int) -> Tuple[int, int]:
 class NetExec:
   """Buffers + op emission for ``nb`` images of one network at resolution ``size``."""
 
-  def __init__(self, spec: NetSpec, state: NetState, nb: int, size: int, device, tag: str):
+  def __init__(self, spec: NetSpec, state: NetState, nb: int, size: int, device, tag: str,
+               fp8: bool = False):
     self.spec, self.st, self.nb, self.size, self.tag = spec, state, nb, size, tag
+    self.fp8 = fp8 and any(fp8_ok(l) for l in spec.layers)
+    if self.fp8:
+      state.enable_fp8()
     self.layers = list(spec.layers)
     L = len(self.layers)
     dev = device
@@ -115,6 +162,13 @@ class NetExec:
       self.inp.append(Buf(nb, hh, ww, cpad(l.cin), halo=halo, device=dev, slack_rows=slack))
     ho, wo = self.out_hw[-1]
     self.inp.append(Buf(nb, ho, wo, cpad(self.layers[-1].cout), device=dev))
+    # E4M3 twins of the inputs of the FP8 layers (written by the producing IN-apply kernel)
+    self.inp8: Dict[int, Buf8] = {}
+    if self.fp8:
+      for j, l in enumerate(self.layers):
+        if fp8_ok(l):
+          hh, ww = self.in_hw[j]
+          self.inp8[j] = Buf8(nb, hh, ww, l.cin, halo=l.k // 2, device=dev)
     self.raw: List[Optional[Buf]] = []
     self.stats: List[Optional[torch.Tensor]] = []
     self.bstats: List[Optional[torch.Tensor]] = []
@@ -265,6 +319,13 @@ class NetExec:
         if is_small_cin(l):
           maps, taps = self._small_cin_maps(j, n0, nimg, bw, bh)
           kch = 64
+        elif j in self.inp8:
+          # FP8 forward: E4M3 activations x E4M3 weights, fp32 accumulate, de-scaled in the epilogue
+          slot = st.fp8_slot(l)
+          no.add_conv(plan, name + ".fp8", [self.inp8[j].tmap_padded(bw, bh, n0, nimg)],
+                      no.taps_conv(l.k, l.cin), l.cin, st.kernel_fp8(l), dst.view(n0), ho, wo, nimg, l.cout,
+                      bias, act, stats, fp8=True, out_scale=st.out_scale[slot:].data_ptr())
+          maps = None
         elif l.pad == "reflect":
           maps, taps, kch = [src.tmap_padded(bw, bh, n0, nimg)], no.taps_conv(l.k, l.cin), l.cin
         elif l.stride == 2:
@@ -273,13 +334,22 @@ class NetExec:
         else:
           maps = [src.tmap_interior(bw, bh, n0, nimg)]
           taps, kch = no.taps_conv(l.k, l.cin, origin=-self._pad_before(j)), l.cin
-        no.add_conv(plan, name, maps, taps, kch, w2, dst.view(n0), ho, wo, nimg, l.cout, bias, act, stats)
+        if maps is not None:
+          no.add_conv(plan, name, maps, taps, kch, w2, dst.view(n0), ho, wo, nimg, l.cout, bias, act, stats)
       if l.norm:
         nxt = self.inp[j + 1]
         skip = self.inp[j - 1].view(n0) if l.res == "b" else NULL_VIEW
+        dst8, scale8, amax8 = NULL_VIEW, 0, 0
+        if (j + 1) in self.inp8:
+          b8 = self.inp8[j + 1]
+          slot = st.fp8_slot(self.layers[j + 1])
+          dst8 = b8.view(n0)
+          scale8 = st.act_scale[slot:].data_ptr()
+          amax8 = st.act_amax[slot:].data_ptr()
         plan.add_in_apply(f"{self.tag}.{l.name}.in_apply[{n0}:{n0 + nimg}]", self.raw[j].view(n0),
                           stats, st.wptr(l, "gamma"), st.wptr(l, "beta"), 1.0 / (ho * wo), IN_EPS,
-                          ACT[l.act], skip, nxt.view(n0), nxt.halo, nimg, ho, wo, l.cout)
+                          ACT[l.act], skip, nxt.view(n0), nxt.halo, nimg, ho, wo, l.cout,
+                          dst8, scale8, amax8)
 
   # -------------------------------------------------------------- backward
   def backward(self, plan, n0: int, nimg: int, wgrad: bool, stop_layer: int = 0,

@@ -78,7 +78,8 @@ def add_conv(plan, name: str, a_maps: Sequence[bytes], taps: Sequence[Tap], k_ch
              bias: int = 0, act: int = 0, stats: int = 0, b_mn: bool = False,
              block_n: Optional[int] = None, tile: Optional[Tuple[int, int]] = None,
              w_limit: Optional[int] = None,
-             phases: Optional[Sequence[Tuple[Sequence[Tap], int]]] = None):
+             phases: Optional[Sequence[Tuple[Sequence[Tap], int]]] = None,
+             fp8: bool = False, out_scale: int = 0):
   """Box-mode implicit GEMM: out[n, h, w, :n_channels] over an out_h x out_w grid.
 
   k_channels: channels of the A views (K per tap); n_channels: valid output channels."""
@@ -93,10 +94,11 @@ def add_conv(plan, name: str, a_maps: Sequence[bytes], taps: Sequence[Tap], k_ch
     for ptaps, off in phases:
       ph.append((len(taps), len(ptaps), int(off)))
       taps.extend(ptaps)
+  kblock = 128 if fp8 else 64   # elements per 128-byte K block
   return plan.add_conv_gemm(name, list(a_maps), nv.wmat_tmap(w2_bf16, block_n, b_mn),
-                            list(taps), k_channels // 64, out_w // bw, out_h // bh, bw, bh,
+                            list(taps), k_channels // kblock, out_w // bw, out_h // bh, bw, bh,
                             out_w if w_limit is None else w_limit, ptr, sn, sh, sw, n_channels,
-                            bias, act, stats, block_n, b_mn, nimg, ph)
+                            bias, act, stats, block_n, b_mn, nimg, ph, out_scale, fp8)
 
 
 def add_conv_flat(plan, name: str, a_map: bytes, taps: Sequence[Tap], k_channels: int,

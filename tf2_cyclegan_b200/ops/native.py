@@ -131,6 +131,25 @@ class Buf:
                 [self.sw, rows * self.sw, rows * self.sw], [64, rows_box, 1, 1])
 
 
+class Buf8(Buf):
+  """E4M3 (1 byte / element) twin of :class:`Buf`: same logical layout, TMA boxes of 128 channels."""
+
+  def __init__(self, n: int, h: int, w: int, c: int, halo: int = 0, device="cuda"):
+    self.n, self.h, self.w, self.c, self.halo = n, h, w, c, halo
+    self.hp, self.wp = h + 2 * halo, w + 2 * halo
+    self.storage = torch.zeros(n * self.hp * self.wp * c, dtype=torch.uint8, device=device)
+    self.t = self.storage.view(n, self.hp, self.wp, c)
+
+  def ptr(self, n: int = 0, h: int = 0, w: int = 0, c: int = 0, padded: bool = False) -> int:
+    off = 0 if padded else self.halo
+    return self.t.data_ptr() + (n * self.sn + (h + off) * self.sh + (w + off) * self.sw + c)
+
+  def tmap_padded(self, bw: int, bh: int, n0: int = 0, nimg: Optional[int] = None, cbox: int = 128):
+    nimg = self.n - n0 if nimg is None else nimg
+    return tmap(self.ptr(n0, padded=True), [self.c, self.wp, self.hp, nimg],
+                [self.sw, self.sh, self.sn], [cbox, bw, bh, 1], elem_bytes=1, dtype=2)
+
+
 def tile_shape(h: int, w: int, pixels: int = 128) -> Tuple[int, int]:
   """(bw, bh) with bw*bh == pixels, bw | w, bh | h."""
   bw = min(w, pixels)
@@ -146,6 +165,9 @@ def wmat_tmap(w2: torch.Tensor, block_n: int, mn_major: bool) -> bytes:
   """Weights as a [rows, K] bf16 matrix. K-major: box {64, block_n};
   MN-major use (B[k][n] = w2[k, n]): box {64, 64}."""
   rows, k = w2.shape
+  if w2.dtype == torch.uint8:   # E4M3 weights: 128 elements per 128-byte K block
+    return tmap(w2.data_ptr(), [k, rows], [k], [128, block_n // 2 if block_n >= 128 else block_n],
+                elem_bytes=1, dtype=2)
   # wide K-major tiles are fetched as two half-height boxes so that the same descriptor serves
   # the 1-CTA kernel (two loads) and the cta_group::2 kernel (one half per CTA)
   box = [64, 64] if mn_major else [64, block_n // 2 if block_n >= 128 else block_n]
