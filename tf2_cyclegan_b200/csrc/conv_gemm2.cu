@@ -49,6 +49,7 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int 
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;          // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
+  constexpr int KB = FP8 ? 128 : 64;   // elements per 128-byte K block
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();               // 0 = leader
@@ -115,14 +116,14 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int 
             uint8_t* sa = smem + s * Cfg::kStageBytes;
             uint8_t* sb = sa + Cfg::kABytes;
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);
-            tma_load_4d_2sm(sa, amap, &full_bar[s], cb * 64, w0 + tap.dw, h0 + tap.dh, img + tap.dn);
+            tma_load_4d_2sm(sa, amap, &full_bar[s], cb * KB, w0 + tap.dw, h0 + tap.dh, img + tap.dn);
             if constexpr (!B_MN) {
-              tma_load_2d_2sm(sb, &p.tmB, &full_bar[s], tap.bk + cb * 64, n0 + rank * Cfg::kHalfN);
+              tma_load_2d_2sm(sb, &p.tmB, &full_bar[s], tap.bk + cb * KB, n0 + rank * Cfg::kHalfN);
             } else {
 #pragma unroll
               for (int j = 0; j < Cfg::kHalfN / 64; ++j)
                 tma_load_2d_2sm(sb + j * (64 * 128), &p.tmB, &full_bar[s],
-                                tap.bk + n0 + rank * Cfg::kHalfN + j * 64, cb * 64);
+                                tap.bk + n0 + rank * Cfg::kHalfN + j * 64, cb * KB);
             }
             if (rank != 0) mbar_arrive_cluster(&full_bar[s], 0);
           }
