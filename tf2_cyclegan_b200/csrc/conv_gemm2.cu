@@ -23,7 +23,7 @@ struct Gemm2Cfg {
   static constexpr int kABytes = 128 * 128;
   static constexpr int kBBytes = kHalfN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N >= 256) ? 5 : 6;   // ~40 KB of smem stay free for co-resident kernels
+  static constexpr int kStages = (BLOCK_N >= 256) ? 6 : 8;
   static constexpr int kAccCols = BLOCK_N;
   static constexpr int kTmemCols = 2 * kAccCols;
   static constexpr int kStagingBytes = EpiCfg<BLOCK_N>::kStagingBytes;
@@ -35,7 +35,7 @@ struct Gemm2Cfg {
 };
 
 template <int BLOCK_N, bool B_MN, bool FP8>
-__global__ void __launch_bounds__(256, 2)   // <= 128 registers: leaves room for bandwidth kernels of other lanes
+__global__ void __launch_bounds__(256, 1)
 conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int dbg) {
   using Cfg = Gemm2Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];

@@ -193,14 +193,14 @@ struct Wgrad2Cfg {
   static constexpr int kABytes = 2 * 64 * 128;
   static constexpr int kBBytes = (kHalfN / 64) * 64 * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = 5;
+  static constexpr int kStages = 6;
   static constexpr int kTmemCols = BLOCK_N;
   static constexpr int kBarrierBytes = (2 * kStages + 1) * 8 + 16;
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarrierBytes + 1024;
 };
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 1)
 wgrad_gemm2_kernel(const __grid_constant__ WgradParams p, int dbg) {
   using Cfg = Wgrad2Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
