@@ -159,29 +159,56 @@ class PairedBatches:
               tf_shuffle_order(n, self.shuffle_buffer, self.rng))
     return list(range(n)), list(range(n))
 
+  def _staging(self, k: int, n: int, like: torch.Tensor) -> torch.Tensor:
+    """Rotating pinned host buffers (allocated once): the gather target of a batch and the
+    source of its async H2D copy. `prefetch + 2` slots so a slot is never rewritten in flight."""
+    dev = self.strategy.device
+    if not self.to_device or dev.type != "cuda":
+      return torch.empty((n,) + tuple(like.shape[1:]), dtype=like.dtype)
+    if not hasattr(self, "_pinned"):
+      self._pinned = {}
+    key = (k, tuple(like.shape[1:]))
+    if key not in self._pinned:
+      cap = max(1, -(-self.gbs // self.strategy.world_size) if self.distribute else self.gbs)
+      self._pinned[key] = torch.empty((cap,) + tuple(like.shape[1:]), dtype=like.dtype).pin_memory()
+    return self._pinned[key][:n]
+
   def _host_batches(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
     oa, ob = self._orders()
     n = self.a.shape[0]
-    for s in range(0, n, self.gbs):
+    slots = max(2, self.prefetch + 2)
+    for step, s in enumerate(range(0, n, self.gbs)):
       ia, ib = oa[s:s + self.gbs], ob[s:s + self.gbs]
       if self.distribute:
         lo, hi = self.strategy.shard_bounds(len(ia))
         ia, ib = ia[lo:hi], ib[lo:hi]
       idx_a = torch.as_tensor(ia, dtype=torch.long)
       idx_b = torch.as_tensor(ib, dtype=torch.long)
-      yield self.a.index_select(0, idx_a), self.b.index_select(0, idx_b)
+      k = step % slots
+      ev = getattr(self, "_slot_events", {}).get(k)
+      if ev is not None:
+        ev.synchronize()   # the async H2D copy that last read this pinned slot has finished
+      self._slot = k
+      xa = self._staging(2 * k, len(ia), self.a)
+      xb = self._staging(2 * k + 1, len(ib), self.b)
+      if len(ia):
+        torch.index_select(self.a, 0, idx_a, out=xa)
+        torch.index_select(self.b, 0, idx_b, out=xb)
+      yield xa, xb
 
   def _upload(self, x: torch.Tensor, y: torch.Tensor):
     dev = self.strategy.device
     if not self.to_device or dev.type != "cuda":
       return x, y
-    return (x.pin_memory().to(dev, non_blocking=True),
-            y.pin_memory().to(dev, non_blocking=True))
+    return x.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
 
   def __iter__(self):
     if self.prefetch <= 0:
       for x, y in self._host_batches():
-        yield self._upload(x, y)
+        xd, yd = self._upload(x, y)
+        if xd is not x:   # async copy from a pinned slot: finish it before the slot can be rewritten
+          torch.cuda.current_stream(self.strategy.device).synchronize()
+        yield xd, yd
       return
     q: "queue.Queue" = queue.Queue(maxsize=self.prefetch)
     dev = self.strategy.device
@@ -195,6 +222,9 @@ class PairedBatches:
               xd, yd = self._upload(x, y)
               ev = torch.cuda.Event()
               ev.record(stream)
+            if not hasattr(self, "_slot_events"):
+              self._slot_events = {}
+            self._slot_events[self._slot] = ev
             q.put((xd, yd, ev))
           else:
             q.put((x, y, None))
