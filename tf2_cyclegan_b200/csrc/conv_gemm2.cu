@@ -179,7 +179,7 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int 
       const uint32_t taddr = tmem_base + acc * Cfg::kAccCols + (static_cast<uint32_t>(ew * 32) << 16);
       if (dbg == 1) { tc_fence_before(); mbar_arrive_cluster(&tmem_empty_bar[acc], 0); continue; }
       conv_epilogue_tile<BLOCK_N>(p, p.out + p.phase_out_off[pt / pairs_per_phase], stage_buf, red, taddr, img, h0, w0, n0, e, ew, lane, mt < m_tiles,
-                                  [&]() { mbar_arrive_cluster(&tmem_empty_bar[acc], 0); });
+                                  [&]() { mbar_arrive_cluster(&tmem_empty_bar[acc], 0); }, dbg);
     }
   }
 
