@@ -41,14 +41,36 @@ def _epoch_means(results: dict) -> dict:
   return dict(zip(keys, vals))
 
 
+def _check_finite(means: dict, where: str) -> None:
+  """Failure detection the reference lacks: stop on the first non-finite epoch mean instead of
+  silently training on NaNs (checked once per epoch, on values already on the host)."""
+  bad = [k for k, v in means.items() if v != v or v in (float("inf"), float("-inf"))]
+  if bad:
+    raise FloatingPointError(f"non-finite {where} metrics: {bad}")
+
+
 def train(args, train_ds, gan, summary, epoch: int):
   results = {}
+  dev = gan.strategy.device
+  timed = dev.type == "cuda"
+  if timed:   # device-side step timing (CUDA events), logged as `step_ms`
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+  steps = 0
   for x, y in tqdm(train_ds, desc="Train", total=args.train_steps,
                    disable=args.verbose == 0 or not gan.strategy.is_chief):
     result = gan.distributed_train_step(x, y)
     append_dict(results, result)
-  for key, value in _epoch_means(results).items():
+    steps += 1
+  if timed:
+    e1.record()
+  means = _epoch_means(results)
+  _check_finite(means, "train")
+  for key, value in means.items():
     summary.scalar(key, value, step=epoch, training=True)
+  if timed and steps:
+    e1.synchronize()
+    summary.scalar("step_ms", e0.elapsed_time(e1) / steps, step=epoch, training=True)
 
 
 def test(args, test_ds, gan, summary, epoch: int):
@@ -58,6 +80,7 @@ def test(args, test_ds, gan, summary, epoch: int):
     result = gan.distributed_test_step(x, y)
     append_dict(results, result)
   results = _epoch_means(results)
+  _check_finite(results, "test")
   for key, value in results.items():
     summary.scalar(key, value, step=epoch, training=False)
   return results
