@@ -31,6 +31,19 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, __nv
   const bool is_tanh = p.act == ACT_TANH;
   const float slope = act_slope(p.act);
   const float oscale = p.out_scale != nullptr ? __ldg(p.out_scale) : 1.f;
+  // global offsets of the rows this thread stores (same rows for every column chunk): hoists the
+  // integer div / mod and 64-bit address math out of the chunk loop
+  constexpr int RPI = 32 / (CH > 32 ? 32 : CH);   // rows per warp instruction
+  constexpr int kStoreIters = 32 / RPI;
+  long long row_off[kStoreIters];
+#pragma unroll
+  for (int itr = 0; itr < kStoreIters; ++itr) {
+    const int r = ew * 32 + itr * RPI + lane / CH;
+    const int wl = r % p.bw, hl = r / p.bw;
+    row_off[itr] = (w0 + wl < p.w_limit)
+                       ? img * p.out_sn + (h0 + hl) * p.out_sh + (w0 + wl) * p.out_sw
+                       : -1;
+  }
 #pragma unroll 1
   for (int c0 = 0; c0 < BLOCK_N; c0 += CN) {
     // ---- TMEM -> registers -> bias / activation -> bf16 -> staging (swizzled rows)
@@ -143,18 +156,14 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, __nv
     // ---- coalesced store of the staged chunk
     const int n_valid = (tile_valid && dbg != 4) ? min(CN, p.cout - n0 - c0) : 0;   // dbg 4: no global stores
     if (n_valid == CN) {
-      constexpr int RPI = 32 / CH;              // rows per warp instruction
-#pragma unroll 2
-      for (int itr = 0; itr < 32 / RPI; ++itr) {
-        const int r = ew * 32 + itr * RPI + lane / CH;
-        const int cc = lane % CH;
-        const int wl = r % p.bw, hl = r / p.bw;
-        if (w0 + wl < p.w_limit) {
-          __nv_bfloat16* dst = out_base + img * p.out_sn + (h0 + hl) * p.out_sh +
-                               (w0 + wl) * p.out_sw + n0 + c0;
+#pragma unroll
+      for (int itr = 0; itr < kStoreIters; ++itr) {
+        if (row_off[itr] >= 0) {
+          const int r = ew * 32 + itr * RPI + lane / CH;
+          const int cc = lane % CH;
           const int phys = SWZ ? (cc ^ (r & 7)) : cc;
           const uint4 pk = *reinterpret_cast<const uint4*>(stage_buf + r * ROW_BYTES + phys * 16);
-          *reinterpret_cast<uint4*>(dst + cc * 8) = pk;
+          *reinterpret_cast<uint4*>(out_base + row_off[itr] + n0 + c0 + cc * 8) = pk;
         }
       }
     } else if (n_valid > 0) {
