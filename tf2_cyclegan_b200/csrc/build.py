@@ -17,6 +17,22 @@ def so_path() -> str:
   return os.path.join(HERE, "_C" + sysconfig.get_config_var("EXT_SUFFIX"))
 
 
+def host_so_path() -> str:
+  return os.path.join(HERE, "_host.so")
+
+
+def build_host(force: bool = False) -> str:
+  """Host-only helpers (crc32c, image preprocessing, batch gather): plain C ABI, g++."""
+  src, target = os.path.join(HERE, "hostlib.cpp"), host_so_path()
+  if force or _stale(target, [src]):
+    cmd = [os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-msse4.2", "-fPIC", "-shared",
+           "-pthread", src, "-o", target]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+      raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+  return target
+
+
 def _stale(target: str, deps) -> bool:
   if not os.path.exists(target):
     return True
@@ -26,6 +42,7 @@ def _stale(target: str, deps) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
   import pybind11
+  build_host(force)
   nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
   headers = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".cuh", ".h"))]
   objdir = os.path.join(HERE, "build")

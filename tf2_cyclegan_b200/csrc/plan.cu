@@ -19,6 +19,8 @@
 #include "elementwise.cuh"
 #include "wgrad_gemm.cuh"
 
+#include <nvtx3/nvToolsExt.h>
+
 namespace py = pybind11;
 using namespace b2;
 
@@ -172,6 +174,7 @@ class Plan {
     return add_sync(std::move(name), 4, lane, ref);
   }
   int size() const { return static_cast<int>(ops_.size()); }
+  void set_nvtx(bool on) { nvtx_ = on; }
   std::vector<std::string> names() const {
     std::vector<std::string> n;
     for (auto& o : ops_) n.push_back(o.name);
@@ -224,7 +227,9 @@ class Plan {
       }
       const int lane = forked ? o.lane : 0;
       if (lane != 0) dirty[lane] = true;
+      if (nvtx_) nvtxRangePushA(o.name.c_str());
       o.fn(lane_stream(lane, s));
+      if (nvtx_) nvtxRangePop();
       if (check_each) {
         cudaError_t e = cudaStreamSynchronize(s);
         if (e == cudaSuccess) e = cudaGetLastError();
@@ -457,6 +462,8 @@ class Plan {
  private:
   std::vector<Op> ops_;
   int lane_ = 0;
+  // NVTX range per op (name = the op label) for timeline tools; on by B2_NVTX=1 or set_nvtx()
+  bool nvtx_ = [] { const char* e = getenv("B2_NVTX"); return e && e[0] == '1'; }();
   cudaStream_t side_[kLanes] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t lane_ev_[kLanes] = {nullptr, nullptr, nullptr, nullptr};
 };
@@ -477,6 +484,7 @@ PYBIND11_MODULE(_C, m) {
       .def(py::init<>())
       .def("size", &Plan::size)
       .def("names", &Plan::names)
+      .def("set_nvtx", &Plan::set_nvtx)
       .def("run", &Plan::run, py::arg("begin") = 0, py::arg("end") = -1, py::arg("stream") = 0,
            py::arg("check_each") = false, py::call_guard<py::gil_scoped_release>())
       .def("set_lane", &Plan::set_lane)

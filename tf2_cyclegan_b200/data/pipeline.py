@@ -29,6 +29,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+from ..ops import hostlib
 from ..parallel.strategy import Strategy
 
 H2Z_SPLITS = {"trainA": 1067, "trainB": 1334, "testA": 120, "testB": 140}
@@ -191,9 +192,13 @@ class PairedBatches:
       self._slot = k
       xa = self._staging(2 * k, len(ia), self.a)
       xb = self._staging(2 * k + 1, len(ib), self.b)
-      if len(ia):
-        torch.index_select(self.a, 0, idx_a, out=xa)
-        torch.index_select(self.b, 0, idx_b, out=xb)
+      if len(ia):   # batch(): native multi-threaded row gather into the (pinned) staging slot
+        if not (self.a.is_contiguous() and xa.is_contiguous()
+                and hostlib.gather_rows(xa, self.a, idx_a)):
+          torch.index_select(self.a, 0, idx_a, out=xa)
+        if not (self.b.is_contiguous() and xb.is_contiguous()
+                and hostlib.gather_rows(xb, self.b, idx_b)):
+          torch.index_select(self.b, 0, idx_b, out=xb)
       yield xa, xb
 
   def _upload(self, x: torch.Tensor, y: torch.Tensor):
@@ -249,6 +254,35 @@ class PairedBatches:
     t.join()
 
 
+def _materialise_native(source, split: str, n: int, rng: Optional[np.random.Generator],
+                        resize: Tuple[int, int], crop: int, chunk: int = 64) -> Optional[torch.Tensor]:
+  """The per-image map of a split through ``csrc/hostlib.cpp`` (fused flip / bilinear resize /
+  crop / normalise on a thread pool). ``rng`` = None: test map (resize straight to ``crop``).
+  Random draws are consumed in the same order as :func:`preprocess_train` (flip, top, left per
+  image), so both paths pick identical augmentations. Returns None without the library."""
+  if not hostlib.available() or n == 0:
+    return None
+  out = None
+  for s0 in range(0, n, chunk):
+    imgs = [np.ascontiguousarray(source.get(split, i)) for i in range(s0, min(n, s0 + chunk))]
+    params = np.zeros((len(imgs), 3), dtype=np.int32)
+    if rng is not None:
+      for j in range(len(imgs)):
+        params[j, 0] = 1 if rng.random() < 0.5 else 0
+        params[j, 1] = int(rng.integers(0, resize[0] - crop + 1))
+        params[j, 2] = int(rng.integers(0, resize[1] - crop + 1))
+    rs = resize if rng is not None else (crop, crop)
+    if out is None:
+      out = torch.empty((n, crop, crop, imgs[0].shape[2]), dtype=torch.float32)
+    dst = out.numpy()[s0:s0 + len(imgs)]   # written in place by the library
+    if all(im.shape == imgs[0].shape for im in imgs):
+      hostlib.preprocess_batch(np.stack(imgs), params, rs, (crop, crop), out=dst)
+    else:   # mixed raw sizes: one call per image
+      for j, im in enumerate(imgs):
+        hostlib.preprocess_batch(im[None], params[j:j + 1], rs, (crop, crop), out=dst[j:j + 1])
+  return out
+
+
 def _materialise(source, split: str, n: int, fn: Callable[[np.ndarray, int], torch.Tensor]) -> torch.Tensor:
   first = fn(source.get(split, 0), 0)
   out = torch.empty((n,) + tuple(first.shape), dtype=torch.float32)
@@ -285,12 +319,17 @@ def get_datasets(args, strategy: Strategy, buffer_size: int = 256, source=None):
   # cache() after the random map: augmentation is drawn ONCE (main.py:53-54).
   rng_a = np.random.default_rng([seed, 1])
   rng_b = np.random.default_rng([seed, 2])
-  train_a = _materialise(source, "trainA", num_train,
-                         lambda im, i: preprocess_train(im, rng_a, (resize, resize), size))
-  train_b = _materialise(source, "trainB", num_train,
-                         lambda im, i: preprocess_train(im, rng_b, (resize, resize), size))
-  test_a = _materialise(source, "testA", num_test, lambda im, i: preprocess_test(im, size))
-  test_b = _materialise(source, "testB", num_test, lambda im, i: preprocess_test(im, size))
+  def load(split, n, rng):
+    t = _materialise_native(source, split, n, rng, (resize, resize), size)
+    if t is not None:
+      return t
+    if rng is None:
+      return _materialise(source, split, n, lambda im, i: preprocess_test(im, size))
+    return _materialise(source, split, n,
+                        lambda im, i: preprocess_train(im, rng, (resize, resize), size))
+
+  train_a, train_b = load("trainA", num_train, rng_a), load("trainB", num_train, rng_b)
+  test_a, test_b = load("testA", num_test, None), load("testB", num_test, None)
 
   train_ds = PairedBatches(train_a, train_b, args.global_batch_size, strategy,
                            shuffle_buffer=buffer_size, seed=seed, prefetch=2)

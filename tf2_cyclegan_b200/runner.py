@@ -28,6 +28,7 @@ from .parallel.strategy import Strategy
 from .utils import plot
 from .utils.dicts import append_dict
 from .utils.summary import Summary
+from .utils.trace import nvtx_range
 
 
 def _epoch_means(results: dict) -> dict:
@@ -59,7 +60,8 @@ def train(args, train_ds, gan, summary, epoch: int):
   steps = 0
   for x, y in tqdm(train_ds, desc="Train", total=args.train_steps,
                    disable=args.verbose == 0 or not gan.strategy.is_chief):
-    result = gan.distributed_train_step(x, y)
+    with nvtx_range("train_step"):
+      result = gan.distributed_train_step(x, y)
     append_dict(results, result)
     steps += 1
   if timed:
@@ -77,7 +79,8 @@ def test(args, test_ds, gan, summary, epoch: int):
   results = {}
   for x, y in tqdm(test_ds, desc="Test", total=args.test_steps,
                    disable=args.verbose == 0 or not gan.strategy.is_chief):
-    result = gan.distributed_test_step(x, y)
+    with nvtx_range("test_step"):
+      result = gan.distributed_test_step(x, y)
     append_dict(results, result)
   results = _epoch_means(results)
   _check_finite(results, "test")

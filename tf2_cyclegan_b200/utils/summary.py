@@ -20,26 +20,7 @@ from typing import List, Sequence
 import numpy as np
 
 # ------------------------------------------------------------------ crc32c
-_CRC_TABLE = []
-for _i in range(256):
-  _c = _i
-  for _ in range(8):
-    _c = (_c >> 1) ^ 0x82F63B78 if _c & 1 else _c >> 1
-  _CRC_TABLE.append(_c)
-_CRC_NP = np.array(_CRC_TABLE, dtype=np.uint32)
-
-
-def crc32c(data: bytes) -> int:
-  crc = 0xFFFFFFFF
-  tbl = _CRC_TABLE
-  for b in data:
-    crc = tbl[(crc ^ b) & 0xFF] ^ (crc >> 8)
-  return crc ^ 0xFFFFFFFF
-
-
-def masked_crc32c(data: bytes) -> int:
-  crc = crc32c(data)
-  return (((crc >> 15) | (crc << 17)) + 0xA282EAD8) & 0xFFFFFFFF
+from ..ops.hostlib import crc32c, masked_crc32c  # noqa: E402  (native SSE4.2, Python fallback)
 
 
 # ------------------------------------------------------- protobuf encoding
