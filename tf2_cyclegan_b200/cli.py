@@ -33,6 +33,9 @@ def build_parser() -> argparse.ArgumentParser:
                       help="continue the epoch counter stored in the checkpoint")
   parser.add_argument("--fused_allreduce", default="auto", choices=["auto", "on", "off"],
                       help="fused peer-memory reduce+Adam kernel vs NCCL baseline path")
+  parser.add_argument("--checkpoint_format", default="native", choices=["native", "tensorbundle"],
+                      help="container written by save_checkpoint: own (JSON index, atomic) or the "
+                           "reference's TensorFlow TensorBundle; loading auto-detects either")
   return parser
 
 

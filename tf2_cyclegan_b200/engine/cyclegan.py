@@ -33,6 +33,7 @@ class CycleGAN:
   def __init__(self, args, strategy: Strategy):
     self.strategy = strategy
     self.global_batch_size = args.global_batch_size
+    self.checkpoint_format = getattr(args, "checkpoint_format", "native")
     self.lambda_cycle = 10.0
     self.lambda_identity = 0.5 * self.lambda_cycle
 
@@ -71,7 +72,8 @@ class CycleGAN:
     """save checkpoint to checkpoint_dir, overwrite if exists (chief only)."""
     sd = self.backend.state_dict()  # collective for sharded optimizer state
     if self.strategy.is_chief:
-      ckpt.save(self.checkpoint_prefix, sd, extra=extra)
+      ckpt.save(self.checkpoint_prefix, sd, extra=extra,
+                fmt=self.checkpoint_format)
       print(f"\nsaved checkpoint to {self.checkpoint_prefix}\n")
     self.strategy.barrier()
 

@@ -9,6 +9,11 @@ Keys are the Keras object-graph names
 ``…/.OPTIMIZER_SLOT/G_optimizer/m/…``) and tensors are in TF layouts (HWIO
 kernels), so converting to/from a TensorBundle is pure re-packaging.
 
+``save(..., fmt="tensorbundle")`` writes the reference's own on-disk format instead (a TensorFlow
+TensorBundle, see ``tensorbundle.py``), and ``load`` auto-detects which of the two containers
+``<prefix>.index`` is — a checkpoint written by the reference can be dropped into
+``<output_dir>/checkpoints/`` and resumed from.
+
 Beyond the reference: writes are atomic (tmp + fsync + rename, with a nonce
 tying index and data together — the reference can corrupt its only checkpoint
 if it dies mid-write), and ``extra`` carries epoch / RNG state.
@@ -48,7 +53,13 @@ def exists(prefix: str) -> bool:
 
 
 def save(prefix: str, tensors: Dict[str, torch.Tensor],
-         extra: Optional[Dict[str, Any]] = None) -> None:
+         extra: Optional[Dict[str, Any]] = None, fmt: str = "native") -> None:
+  if fmt == "tensorbundle":
+    from . import tensorbundle as tb
+    tb.write_bundle(prefix, tb.to_reference_dtypes(tensors), extra=extra)
+    return
+  if fmt != "native":
+    raise ValueError(f"unknown checkpoint format {fmt!r}")
   os.makedirs(os.path.dirname(prefix) or ".", exist_ok=True)
   nonce = secrets.token_hex(8)
   manifest, offset = {}, 0
@@ -77,6 +88,10 @@ def save(prefix: str, tensors: Dict[str, torch.Tensor],
 
 
 def load(prefix: str) -> Tuple[Dict[str, torch.Tensor], Dict[str, Any]]:
+  from . import tensorbundle as tb
+  if tb.is_bundle(prefix):
+    tensors, info = tb.read_bundle(prefix)
+    return tb.from_reference_dtypes(tensors), info["extra"]
   with open(prefix + ".index") as f:
     index = json.load(f)
   if index.get("format") != FORMAT:
