@@ -25,7 +25,17 @@ class FakePlan:
     return len(self.ops) - 1
 
   def add_conv_gemm(self, name, a_maps, b_map, taps, cin_blocks, tiles_w, tiles_h, bw, bh, w_limit,
-                    out, sn, sh, sw, cout, bias, act, stats, block_n, b_mn, num_images, phases, out_scale=0, fp8=False):
+                    out, sn, sh, sw, cout, bias, act, stats, block_n, b_mn, num_images, phases, out_scale=0, fp8=False,
+                    ts_map=b"", ts=()):
+    if ts:   # tap sharing: one halo tile per channel block, taps = row shifts inside it
+      nbox, box_step, box_bytes, pitch, odw, odh, sbo = ts
+      td = decode(ts_map)
+      assert block_n == 256 and not fp8 and not phases and len(a_maps) == 1
+      assert td["box"][0] == 64 and td["box"][1] * td["box"][2] * 128 == box_bytes, (name, td["box"], box_bytes)
+      assert nbox * box_bytes <= 34 * 1024 and (nbox == 1 or box_bytes % 1024 == 0)
+      for t in taps:
+        shift = (t[3] - odh) * pitch + (t[2] - odw)
+        assert t[0] == 0 and t[1] == 0 and shift >= 0 and shift * 128 + 15 * sbo + 1024 <= nbox * box_bytes, (name, t)
     assert bw * bh == 128 and 1 <= len(a_maps) <= 4 and 1 <= len(taps) <= 52 and len(phases) <= 4
     if phases:
       assert sum(c for _, c, _ in phases) == len(taps) and all(c >= 1 for _, c, _ in phases)
@@ -51,7 +61,7 @@ class FakePlan:
       for t in taps:
         assert t[4] + cout <= bd["dims"][0] + 63, (name, t, bd["dims"], cout)
     assert out % 16 == 0 or cout < 8
-    return self._add("conv_gemm", name, len(taps), cout, block_n, b_mn, num_images)
+    return self._add("conv_gemm_ts" if ts else "conv_gemm", name, len(taps), cout, block_n, b_mn, num_images)
 
   def add_wgrad(self, name, dy_maps, a_maps, taps, ktw, kth, kbw, kbh, nimg, cin, cout, dw, ldw, block_n, ksplit):
     assert kbw * kbh == 64 and ksplit != 0 and block_n in (64, 128, 256)

@@ -400,3 +400,78 @@ def test_fp8_conv_and_in_apply_quantisation():
   assert rel_err(out.t, ref) < 1e-2
   full = O.conv2d(O.reflect_pad(x, 1), kern, 1, "valid")
   assert rel_err(out.t, full) < 8e-2          # quantisation error of E4M3 operands
+
+
+@pytest.mark.parametrize("n,h,c,cout", [(2, 64, 256, 256), (3, 32, 64, 256), (1, 16, 128, 512)])
+def test_conv3x3_tap_shared_boxed(n, h, c, cout):
+  """conv_gemm_ts.cu: 8 x 16 pixel tiles, ONE 10 x 18 halo tile per channel block, the nine
+  taps read it through row-shifted descriptors (stride between 8-row groups = 10 rows)."""
+  nv, no, O = _mods()
+  C = nv.load()
+  torch.manual_seed(10)
+  x = bf(torch.randn(n, h, h, c, device="cuda"))
+  k = bf(torch.randn(3, 3, c, cout, device="cuda") * 0.05)
+  xin = nv.Buf(n, h, h, c, halo=1)
+  fill_reflect(xin, x)
+  w2 = no.pack_conv_weight(k).to(torch.bfloat16)
+  out = nv.Buf(n, h, h, cout)
+  stats = torch.zeros(n, cout, 2, device="cuda")
+  plan = C.Plan()
+  no.add_conv(plan, "conv", [xin.tmap_padded(8, 16)], no.taps_conv(3, c), c, w2, out.view(), h, h,
+              n, cout, stats=stats.data_ptr(), tile=(8, 16), halo_map=lambda w_, h_: xin.tmap_padded(w_, h_))
+  run(plan)
+  ref = O.conv2d(O.reflect_pad(x, 1), k, 1, "valid")
+  assert rel_err(out.t, ref) < 1e-2
+  got = out.t.float()
+  assert torch.allclose(stats[..., 0], got.sum((1, 2)), rtol=1e-3, atol=1e-2 * h)
+  assert torch.allclose(stats[..., 1], (got * got).sum((1, 2)), rtol=1e-3, atol=1e-2 * h)
+
+
+def test_conv4x4_same_tap_shared_zero_fill():
+  """TF-SAME 4x4 stride-1 conv (PatchGAN conv3 shape): the halo box starts at negative
+  coordinates, TMA zero-fills outside the image."""
+  nv, no, O = _mods()
+  C = nv.load()
+  torch.manual_seed(11)
+  n, h, c, cout = 2, 32, 64, 512
+  x = bf(torch.randn(n, h, h, c, device="cuda"))
+  k = bf(torch.randn(4, 4, c, cout, device="cuda") * 0.05)
+  xin = nv.Buf(n, h, h, c)
+  xin.t.copy_(x.to(torch.bfloat16))
+  w2 = no.pack_conv_weight(k).to(torch.bfloat16)
+  out = nv.Buf(n, h, h, cout)
+  plan = C.Plan()
+  no.add_conv(plan, "conv", [xin.tmap_interior(8, 16)], no.taps_conv(4, c, origin=-1), c, w2, out.view(),
+              h, h, n, cout, tile=(8, 16), halo_map=lambda w_, h_: xin.tmap_interior(w_, h_))
+  run(plan)
+  ref = O.conv2d(x, k, 1, "same")
+  assert rel_err(out.t, ref) < 1e-2
+
+
+def test_dgrad_flat_tap_shared():
+  """flat-domain dgrad with one 272-row halo tile (two TMA boxes) shared by the nine taps,
+  MN-major B = forward weights."""
+  nv, no, O = _mods()
+  C = nv.load()
+  torch.manual_seed(12)
+  n, h, c, cout = 2, 32, 256, 128
+  x = bf(torch.randn(n, h, h, c, device="cuda")).requires_grad_(True)
+  kern = bf(torch.randn(3, 3, c, cout, device="cuda") * 0.05)
+  dy = bf(torch.randn(n, h, h, cout, device="cuda"))
+  y = O.conv2d(O.reflect_pad(x, 1), kern, 1, "valid")
+  (gx,) = torch.autograd.grad(y, x, dy)
+  dyb = nv.Buf(n, h, h, cout, halo=1)
+  dyb.interior().copy_(dy.to(torch.bfloat16))
+  w2 = no.pack_conv_weight(kern).to(torch.bfloat16)
+  P = h + 2
+  rows = n * P * P
+  dxpad = nv.Buf(n, h, h, c, halo=1)
+  taps = [(0, 0, (1 - r) * P + (1 - s), 0, (r * 3 + s) * c) for r in range(3) for s in range(3)]
+  plan = C.Plan()
+  no.add_conv_flat(plan, "dgrad", dyb.tmap_flat(), taps, cout, w2, dxpad.ptr(padded=True), c, rows, c,
+                   b_mn=True, halo_map=lambda rb: dyb.tmap_flat(rows_box=rb))
+  g = nv.Buf(n, h, h, c)
+  plan.add_in_bwd_reduce("fold", dxpad.view(), 1, nv.NULL_VIEW, nv.NULL_VIEW, 0, 0, 0, 1.0, 1e-3, 0,
+                         g.view(), 0, n, h, h, c)
+  run(plan)
+  assert rel_err(g.t, gx) < 1.5e-2

@@ -32,6 +32,11 @@ def test_step_plan_builds_and_is_well_formed(monkeypatch, size, b, nres):
   assert any(n.startswith("sync.fork") for n in names) and any(n.startswith("sync.join") for n in names)
   for n in NETS:
     assert f"opt.{n}.adam" in names and f"opt.{n}.step" in names
+  # tap sharing: every residual 3x3 conv (forward: 8x16 boxed halo; dgrad: flat halo) qualifies
+  kinds = {o[1]: o[0] for o in sp.plan.ops}
+  res = [n for n in names if ".res" in n and (".fwd" in n or ".dgrad" in n)]
+  assert res and all(kinds[n] == "conv_gemm_ts" for n in res), [n for n in res if kinds[n] != "conv_gemm_ts"][:4]
+  assert kinds[next(n for n in names if n.startswith("G.stem.fwd"))] == "conv_gemm"
   # every conv layer of every network gets exactly one wgrad group in the full backward
   full = names[sp.marks["test_end"]:]
   for l in be.specs["G"].layers:

@@ -90,7 +90,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int n
 
   if (warp == 0) {
     // ============================ TMA producer ============================
-    if (lane == 0) {
+    // warp-uniform loop; one elected lane issues (operands stay in uniform registers)
+    {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int phase = tile / tiles_per_phase;
@@ -112,30 +113,38 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int n
             mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* sa = smem + s * Cfg::kStageBytes;
             uint8_t* sb = sa + Cfg::kABytes;
-            if (dbg == 3) { mbar_arrive(&full_bar[s]); continue; }
-            mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
-            tma_load_4d(sa, amap, &full_bar[s], cb * 64, w0 + tap.dw, h0 + tap.dh, img + tap.dn);
-            if constexpr (!B_MN) {
-              if constexpr (BLOCK_N >= 128) {   // the host encodes half-height boxes for wide tiles
-                tma_load_2d(sb, &p.tmB, &full_bar[s], tap.bk + cb * 64, n0);
-                tma_load_2d(sb + (BLOCK_N / 2) * 128, &p.tmB, &full_bar[s], tap.bk + cb * 64,
-                            n0 + BLOCK_N / 2);
+            if (elect_one()) {
+              if (dbg == 3) {
+                mbar_arrive(&full_bar[s]);
               } else {
-                tma_load_2d(sb, &p.tmB, &full_bar[s], tap.bk + cb * 64, n0);
-              }
-            } else {
+                mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+                tma_load_4d(sa, amap, &full_bar[s], cb * 64, w0 + tap.dw, h0 + tap.dh, img + tap.dn);
+                if constexpr (!B_MN) {
+                  if constexpr (BLOCK_N >= 128) {   // the host encodes half-height boxes for wide tiles
+                    tma_load_2d(sb, &p.tmB, &full_bar[s], tap.bk + cb * 64, n0);
+                    tma_load_2d(sb + (BLOCK_N / 2) * 128, &p.tmB, &full_bar[s], tap.bk + cb * 64,
+                                n0 + BLOCK_N / 2);
+                  } else {
+                    tma_load_2d(sb, &p.tmB, &full_bar[s], tap.bk + cb * 64, n0);
+                  }
+                } else {
 #pragma unroll
-              for (int j = 0; j < BLOCK_N / 64; ++j)
-                tma_load_2d(sb + j * (64 * 128), &p.tmB, &full_bar[s], tap.bk + n0 + j * 64, cb * 64);
+                  for (int j = 0; j < BLOCK_N / 64; ++j)
+                    tma_load_2d(sb + j * (64 * 128), &p.tmB, &full_bar[s], tap.bk + n0 + j * 64, cb * 64);
+                }
+              }
             }
+            __syncwarp();
           }
         }
       }
     }
   } else if (warp == 1) {
     // ============================= MMA issuer =============================
-    if (lane == 0) {
+    // warp-uniform loop; one elected lane issues the MMAs and commits
+    {
       constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, B_MN ? 1 : 0);
+      const uint32_t smem_base = smem_u32(smem);
       uint32_t it = 0, tile_i = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
         const int num_kb = p.phase_tap_count[tile / tiles_per_phase] * p.cin_blocks;
@@ -149,22 +158,27 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int n
           const uint32_t ph = (it / nstages) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint32_t sa = smem_base + s * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
           const uint64_t da = make_desc_kmajor(sa);
           const uint64_t db = B_MN ? make_desc_mnmajor(sb, 64) : make_desc_kmajor(sb);
+          if (elect_one()) {
+            if (dbg != 2) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (dbg == 2) break;
-            // K advance of 16 elements: +32 B inside the swizzle row (K-major),
-            // +16 rows * 128 B (MN-major); descriptor address field is in 16-byte units
-            const uint64_t da_k = da + static_cast<uint64_t>(k * 2);
-            const uint64_t db_k = db + static_cast<uint64_t>(B_MN ? k * 128 : k * 2);
-            umma_bf16(tmem_d, da_k, db_k, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) {
+                // K advance of 16 elements: +32 B inside the swizzle row (K-major),
+                // +16 rows * 128 B (MN-major); descriptor address field is in 16-byte units
+                const uint64_t da_k = da + static_cast<uint64_t>(k * 2);
+                const uint64_t db_k = db + static_cast<uint64_t>(B_MN ? k * 128 : k * 2);
+                umma_bf16(tmem_d, da_k, db_k, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+            }
+            umma_commit(&empty_bar[s]);        // frees the smem slot when these MMAs retire
           }
-          umma_commit(&empty_bar[s]);        // frees the smem slot when these MMAs retire
+          __syncwarp();
         }
-        umma_commit(&tmem_full_bar[acc]);    // accumulator complete
+        if (elect_one()) umma_commit(&tmem_full_bar[acc]);    // accumulator complete
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -237,6 +251,8 @@ static void launch_t(const ConvGemmParams& p, int num_images, cudaStream_t strea
 
 bool launch_conv_gemm_2cta(const ConvGemmParams& p, int block_n, bool b_mn_major, int num_images,
                            cudaStream_t stream);
+bool launch_conv_gemm_ts(const ConvGemmParams& p, int block_n, bool b_mn_major, int num_images,
+                         cudaStream_t stream);
 
 int dbg_flag() {
   static int v = -1;
@@ -266,6 +282,9 @@ void launch_conv_gemm(const ConvGemmParams& p, int block_n, bool b_mn_major, int
     }
     return;
   }
+  if (p.ts.enabled && use_2cta() && p.tiles_w * p.tiles_h * num_images >= 2 &&
+      launch_conv_gemm_ts(p, block_n, b_mn_major, num_images, stream))
+    return;
   if (block_n >= 128 && use_2cta() && p.tiles_w * p.tiles_h * num_images >= 2 &&
       launch_conv_gemm_2cta(p, block_n, b_mn_major, num_images, stream))
     return;

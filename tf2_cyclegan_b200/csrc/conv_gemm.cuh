@@ -17,6 +17,21 @@ struct Tap {
   int32_t bk;
 };
 
+// Tap sharing: ONE halo tile of the activations (all pixels any tap of the tile touches) is
+// loaded per 64-channel block and every tap reads it through a row-shifted UMMA descriptor
+// (SWIZZLE_128B is a function of the absolute shared-memory address, so a K-major operand may
+// start at any 128-byte row). Cuts the L2 -> SM activation traffic of a 3x3 conv from 9 tiles
+// to 1.4 (8 x 16 pixel tiles) or 2.1 (flat 128-row tiles) per channel block.
+struct TapShare {
+  int enabled;
+  int nbox;          // TMA boxes per halo tile (stacked along w; box_bytes % 1024 == 0 if > 1)
+  int box_step;      // w-coordinate step between consecutive boxes
+  int box_bytes;     // bytes per box = box rows x 128
+  int pitch;         // halo rows per unit of dh: shift(tap) = (dh - origin_dh) * pitch + dw - origin_dw
+  int origin_dw, origin_dh;   // coordinate offset of the halo origin relative to the tile origin
+  int sbo;           // bytes between the 8-row groups of the M dimension inside the halo tile
+};
+
 constexpr int kMaxPhases = 4;   // sub-pixel phases of a transposed conv share one launch
 
 struct ConvGemmParams {
@@ -40,6 +55,8 @@ struct ConvGemmParams {
   float* stats;                 // [images][cout][2] (sum, sumsq) of the stored bf16 values, or nullptr
   const float* out_scale;       // device scalar multiplied into the accumulators (FP8 de-scaling), or nullptr
   int fp8;                      // operands are E4M3 bytes (128 channels per 128-byte K block)
+  TapShare ts;                  // optional (BLOCK_N == 256, cta_group::2, one phase, one A view)
+  CUtensorMap tmTS;             // halo box view of the activations when ts.enabled
 };
 
 void launch_conv_gemm(const ConvGemmParams& p, int block_n, bool b_mn_major, int num_images,

@@ -99,7 +99,8 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int 
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    // warp-uniform loop, one elected lane issues (keeps tensor-map / barrier operands uniform)
+    {
       uint32_t it = 0;
       for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
         int mt, n0, img, h0, w0;
@@ -115,25 +116,31 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int 
             mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* sa = smem + s * Cfg::kStageBytes;
             uint8_t* sb = sa + Cfg::kABytes;
-            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);
-            tma_load_4d_2sm(sa, amap, &full_bar[s], cb * KB, w0 + tap.dw, h0 + tap.dh, img + tap.dn);
-            if constexpr (!B_MN) {
-              tma_load_2d_2sm(sb, &p.tmB, &full_bar[s], tap.bk + cb * KB, n0 + rank * Cfg::kHalfN);
-            } else {
+            if (elect_one()) {
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);
+              tma_load_4d_2sm(sa, amap, &full_bar[s], cb * KB, w0 + tap.dw, h0 + tap.dh, img + tap.dn);
+              if constexpr (!B_MN) {
+                tma_load_2d_2sm(sb, &p.tmB, &full_bar[s], tap.bk + cb * KB, n0 + rank * Cfg::kHalfN);
+              } else {
 #pragma unroll
-              for (int j = 0; j < Cfg::kHalfN / 64; ++j)
-                tma_load_2d_2sm(sb + j * (64 * 128), &p.tmB, &full_bar[s],
-                                tap.bk + n0 + rank * Cfg::kHalfN + j * 64, cb * KB);
+                for (int j = 0; j < Cfg::kHalfN / 64; ++j)
+                  tma_load_2d_2sm(sb + j * (64 * 128), &p.tmB, &full_bar[s],
+                                  tap.bk + n0 + rank * Cfg::kHalfN + j * 64, cb * KB);
+              }
+              if (rank != 0) mbar_arrive_cluster(&full_bar[s], 0);
             }
-            if (rank != 0) mbar_arrive_cluster(&full_bar[s], 0);
+            __syncwarp();
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (lane == 0 && rank == 0) {
+    // The whole warp runs the loop (warp-uniform control flow and operands, so descriptors
+    // live in uniform registers); one elected lane issues the MMAs and commits.
+    if (rank == 0) {
       constexpr uint32_t idesc = FP8 ? make_idesc_e4m3(256, BLOCK_N) : make_idesc_bf16(256, BLOCK_N, 0, B_MN ? 1 : 0);
+      const uint32_t smem_base = smem_u32(smem);
       uint32_t it = 0, tile_i = 0;
       for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++tile_i) {
         const int num_kb = p.phase_tap_count[pt / pairs_per_phase] * p.cin_blocks;
@@ -147,21 +154,26 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int 
           const uint32_t ph = (it / Cfg::kStages) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint32_t sa = smem_base + s * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
           const uint64_t da = make_desc_kmajor(sa);
           const uint64_t db = B_MN ? make_desc_mnmajor(sb, 64) : make_desc_kmajor(sb);
+          if (elect_one()) {
+            if (dbg != 2) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            if (dbg == 2) break;
-            const uint64_t da_k = da + static_cast<uint64_t>(k * 2);
-            const uint64_t db_k = db + static_cast<uint64_t>(B_MN ? k * 128 : k * 2);
-            if constexpr (FP8) umma_f8_2sm(tmem_d, da_k, db_k, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_bf16_2sm(tmem_d, da_k, db_k, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t da_k = da + static_cast<uint64_t>(k * 2);
+                const uint64_t db_k = db + static_cast<uint64_t>(B_MN ? k * 128 : k * 2);
+                if constexpr (FP8) umma_f8_2sm(tmem_d, da_k, db_k, idesc, (kb | k) != 0 ? 1u : 0u);
+                else umma_bf16_2sm(tmem_d, da_k, db_k, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+            }
+            umma_commit_2sm(&empty_bar[s]);
           }
-          umma_commit_2sm(&empty_bar[s]);
+          __syncwarp();
         }
-        umma_commit_2sm(&tmem_full_bar[acc]);
+        if (elect_one()) umma_commit_2sm(&tmem_full_bar[acc]);
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {

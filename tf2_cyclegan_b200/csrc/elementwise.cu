@@ -723,27 +723,49 @@ inline int grid_for_fixed_c(long long total, int c8) {
 
 }  // namespace
 
-static int ew_target_blocks() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("B2_EW_BLOCKS");
-    v = e ? atoi(e) : 592;
-  }
-  return v;
+static int ew_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
 }
 
-static int pick_pix_per_block(int HW, int N, int lanes) {
-  // >= 4 pixels per thread per pass; enough blocks to fill the machine
-  int ppb = lanes * 32;
-  while (ppb > lanes * 4 && static_cast<long long>((HW + ppb - 1) / ppb) * N < ew_target_blocks()) ppb /= 2;
-  if (ppb > HW) ppb = HW;
-  return ppb;
+static int ew_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// Pixels per block of the (pixel chunks, N) grids. The kernels keep `blocks_per_sm` blocks
+// resident, so the grid is sized to fill whole waves of the machine: with B2_EW_WAVES = w
+// (default 1) every image gets floor(w * slots / N) chunks (chunk length need not be a power of
+// two, only a multiple of the pixel lanes), e.g. 12 images x 37 chunks = 444 blocks = exactly one
+// wave of 148 x 3. Longer chunks also amortise the per-block coefficient table / reduction.
+static int pick_pix_per_block(int HW, int N, int lanes, int blocks_per_sm) {
+  static const int legacy = ew_env("B2_EW_BLOCKS", 0);
+  if (legacy > 0) {   // old heuristic: power-of-two chunks until >= B2_EW_BLOCKS blocks
+    int ppb = lanes * 32;
+    while (ppb > lanes * 4 && static_cast<long long>((HW + ppb - 1) / ppb) * N < legacy) ppb /= 2;
+    return ppb > HW ? HW : ppb;
+  }
+  static const int waves = ew_env("B2_EW_WAVES", 1);
+  const int slots = ew_num_sms() * blocks_per_sm * (waves > 0 ? waves : 1);
+  int chunks = slots / (N > 0 ? N : 1);
+  if (chunks < 1) chunks = 1;
+  int ppb = (HW + chunks - 1) / chunks;
+  const int min_ppb = lanes * 4;             // >= 4 pixels per thread
+  if (ppb < min_ppb) ppb = min_ppb;
+  ppb = (ppb + lanes - 1) / lanes * lanes;
+  return ppb > HW ? HW : ppb;
 }
 
 void launch_in_apply(const InApplyParams& p, cudaStream_t s) {
   const int HW = p.H * p.W;
   const int lanes = kThreads / (p.C / 8);
-  const int ppb = pick_pix_per_block(HW, p.N, lanes);
+  const int ppb = pick_pix_per_block(HW, p.N, lanes, 4);
   dim3 grid((HW + ppb - 1) / ppb, p.N);
   in_apply_kernel<<<grid, kThreads, 2 * p.C * sizeof(float), s>>>(p, ppb);
 }
@@ -752,7 +774,7 @@ void launch_in_bwd_reduce(const InBwdReduceParams& p, cudaStream_t s) {
   const int HW = p.H * p.W;
   const int c8 = p.C / 8;
   const int lanes = kThreads / c8;
-  const int pix_per_block = pick_pix_per_block(HW, p.N, lanes);
+  const int pix_per_block = pick_pix_per_block(HW, p.N, lanes, 3);
   dim3 grid((HW + pix_per_block - 1) / pix_per_block, p.N);
   const size_t smem = (static_cast<size_t>(lanes) * p.C * 2 + 4 * p.C) * sizeof(float);
   in_bwd_reduce_kernel<<<grid, kThreads, smem, s>>>(p, pix_per_block);
@@ -761,7 +783,7 @@ void launch_in_bwd_reduce(const InBwdReduceParams& p, cudaStream_t s) {
 void launch_in_bwd_apply(const InBwdApplyParams& p, cudaStream_t s) {
   const int HW = p.H * p.W;
   const int lanes = kThreads / (p.C / 8);
-  const int ppb = pick_pix_per_block(HW, p.N, lanes);
+  const int ppb = pick_pix_per_block(HW, p.N, lanes, 4);
   dim3 grid((HW + ppb - 1) / ppb, p.N);
   in_bwd_apply_kernel<<<grid, kThreads, 4 * p.C * sizeof(float), s>>>(p, ppb);
 }

@@ -267,7 +267,7 @@ class Plan {
                     int bh, int w_limit, uint64_t out, long long sn, long long sh, long long sw,
                     int cout, uint64_t bias, int act, uint64_t stats, int block_n, bool b_mn,
                     int num_images, std::vector<std::tuple<int, int, long long>> phases,
-                    uint64_t out_scale, bool fp8) {
+                    uint64_t out_scale, bool fp8, py::bytes ts_map, std::vector<int> ts) {
     auto p = std::make_shared<ConvGemmParams>();
     memset(p.get(), 0, sizeof(ConvGemmParams));
     if (a_maps.empty() || a_maps.size() > kMaxAMaps) throw std::runtime_error("bad a_maps");
@@ -280,6 +280,17 @@ class Plan {
     p->out = P<__nv_bfloat16>(out); p->out_sn = sn; p->out_sh = sh; p->out_sw = sw;
     p->cout = cout; p->bias = P<const float>(bias); p->act = act; p->stats = P<float>(stats);
     p->out_scale = P<const float>(out_scale); p->fp8 = fp8 ? 1 : 0;
+    if (!ts.empty()) {   // tap sharing: {nbox, box_step, box_bytes, pitch, origin_dw, origin_dh, sbo}
+      if (ts.size() != 7) throw std::runtime_error("ts needs 7 integers");
+      p->tmTS = tmap_from(ts_map);
+      p->ts = TapShare{1, ts[0], ts[1], ts[2], ts[3], ts[4], ts[5], ts[6]};
+      for (int i = 0; i < p->num_taps; ++i) {
+        const Tap& t = p->taps[i];
+        const int shift = (t.dh - ts[5]) * ts[3] + (t.dw - ts[4]);
+        if (t.map != 0 || t.dn != 0 || shift < 0 || shift * 128 + 15 * ts[6] + 1024 > ts[0] * ts[2])
+          throw std::runtime_error("tap outside the shared halo tile");
+      }
+    }
     if (phases.empty()) phases.push_back({0, p->num_taps, 0});
     if (phases.size() > kMaxPhases) throw std::runtime_error("too many phases");
     p->num_phases = static_cast<int>(phases.size());
@@ -499,7 +510,7 @@ PYBIND11_MODULE(_C, m) {
            py::arg("bh"), py::arg("w_limit"), py::arg("out"), py::arg("sn"), py::arg("sh"), py::arg("sw"),
            py::arg("cout"), py::arg("bias"), py::arg("act"), py::arg("stats"), py::arg("block_n"),
            py::arg("b_mn"), py::arg("num_images"), py::arg("phases"), py::arg("out_scale") = 0,
-           py::arg("fp8") = false)
+           py::arg("fp8") = false, py::arg("ts_map") = py::bytes(), py::arg("ts") = std::vector<int>())
       .def("add_wgrad", &Plan::add_wgrad)
       .def("add_wgrad_row", &Plan::add_wgrad_row)
       .def("add_in_apply", &Plan::add_in_apply, py::arg("name"), py::arg("x"), py::arg("stats"),

@@ -106,21 +106,22 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p, int dbg) {
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (num_kb > 0) {
+    // producer and MMA warps run warp-uniform loops (operands stay in uniform registers, the K
+    // tile coordinates advance incrementally); one elected lane issues
     if (warp == 0) {
-      if (lane == 0) {
-        const CUtensorMap* amap = &p.tmA[tap.map];
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int kt = kt_begin + kb;
-          const int img = kt / ktiles_per_img;
-          const int t_in = kt - img * ktiles_per_img;
-          const int th = t_in / p.ktiles_w;
-          const int w0 = (t_in - th * p.ktiles_w) * p.kbw;
-          const int h0 = th * p.kbh;
-          const int s = kb % Cfg::kStages;
-          const uint32_t ph = (kb / Cfg::kStages) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + s * Cfg::kStageBytes;
-          uint8_t* sb = sa + Cfg::kABytes;
+      const CUtensorMap* amap = &p.tmA[tap.map];
+      int img = kt_begin / ktiles_per_img;
+      int t_in = kt_begin - img * ktiles_per_img;
+      int th = t_in / p.ktiles_w;
+      int tw = t_in - th * p.ktiles_w;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int w0 = tw * p.kbw, h0 = th * p.kbh;
+        const int s = kb % Cfg::kStages;
+        const uint32_t ph = (kb / Cfg::kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * Cfg::kStageBytes;
+        uint8_t* sb = sa + Cfg::kABytes;
+        if (elect_one()) {
           mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
           // channels beyond the tensor extent are zero-filled by TMA (cout / cin < tile)
 #pragma unroll
@@ -131,27 +132,34 @@ wgrad_gemm_kernel(const __grid_constant__ WgradParams p, int dbg) {
             tma_load_4d(sb + j * (64 * 128), amap, &full_bar[s], n0 + j * 64, w0 + tap.dw,
                         h0 + tap.dh, img);
         }
+        __syncwarp();
+        if (++tw == p.ktiles_w) { tw = 0; if (++th == p.ktiles_h) { th = 0; ++img; } }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int s = kb % Cfg::kStages;
-          const uint32_t ph = (kb / Cfg::kStages) & 1;
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kABytes;
-          const uint64_t da = make_desc_mnmajor(sa, 64);
-          const uint64_t db = make_desc_mnmajor(sb, 64);
+      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);
+      const uint32_t smem_base = smem_u32(smem);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % Cfg::kStages;
+        const uint32_t ph = (kb / Cfg::kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+        const uint32_t sb = sa + Cfg::kABytes;
+        const uint64_t da = make_desc_mnmajor(sa, 64);
+        const uint64_t db = make_desc_mnmajor(sb, 64);
+        if (elect_one()) {
+          if (dbg != 2) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)   // 16 pixels per MMA = 16 rows x 128 B = 128 x 16-byte units
-            if (dbg != 2) umma_bf16(tmem_base, da + static_cast<uint64_t>(k * 128),
-                      db + static_cast<uint64_t>(k * 128), idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)   // 16 pixels per MMA = 16 rows x 128 B = 128 x 16-byte units
+              umma_bf16(tmem_base, da + static_cast<uint64_t>(k * 128),
+                        db + static_cast<uint64_t>(k * 128), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
           umma_commit(&empty_bar[s]);
         }
-        umma_commit(tmem_full_bar);
+        __syncwarp();
       }
+      if (elect_one()) umma_commit(tmem_full_bar);
+      __syncwarp();
     } else if (warp >= 4) {
       const int e = threadIdx.x - 128;
       const int ew = warp - 4;
@@ -246,20 +254,19 @@ wgrad_gemm2_kernel(const __grid_constant__ WgradParams p, int dbg) {
 
   if (num_kb > 0) {
     if (warp == 0) {
-      if (lane == 0) {
-        const CUtensorMap* amap = &p.tmA[tap.map];
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int kt = kt_begin + kb;
-          const int img = kt / ktiles_per_img;
-          const int t_in = kt - img * ktiles_per_img;
-          const int th = t_in / p.ktiles_w;
-          const int w0 = (t_in - th * p.ktiles_w) * p.kbw;
-          const int h0 = th * p.kbh;
-          const int s = kb % Cfg::kStages;
-          const uint32_t ph = (kb / Cfg::kStages) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + s * Cfg::kStageBytes;
-          uint8_t* sb = sa + Cfg::kABytes;
+      const CUtensorMap* amap = &p.tmA[tap.map];
+      int img = kt_begin / ktiles_per_img;
+      int t_in = kt_begin - img * ktiles_per_img;
+      int th = t_in / p.ktiles_w;
+      int tw = t_in - th * p.ktiles_w;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int w0 = tw * p.kbw, h0 = th * p.kbh;
+        const int s = kb % Cfg::kStages;
+        const uint32_t ph = (kb / Cfg::kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * Cfg::kStageBytes;
+        uint8_t* sb = sa + Cfg::kABytes;
+        if (elect_one()) {
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);
 #pragma unroll
           for (int j = 0; j < 2; ++j)
@@ -271,26 +278,35 @@ wgrad_gemm2_kernel(const __grid_constant__ WgradParams p, int dbg) {
                             img);
           if (rank != 0) mbar_arrive_cluster(&full_bar[s], 0);
         }
+        __syncwarp();
+        if (++tw == p.ktiles_w) { tw = 0; if (++th == p.ktiles_h) { th = 0; ++img; } }
       }
     } else if (warp == 1) {
-      if (lane == 0 && rank == 0) {
+      if (rank == 0) {
         constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N, 1, 1);
+        const uint32_t smem_base = smem_u32(smem);
         for (int kb = 0; kb < num_kb; ++kb) {
           const int s = kb % Cfg::kStages;
           const uint32_t ph = (kb / Cfg::kStages) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint32_t sa = smem_base + s * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
           const uint64_t da = make_desc_mnmajor(sa, 64);
           const uint64_t db = make_desc_mnmajor(sb, 64);
+          if (elect_one()) {
+            if (dbg != 2) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            if (dbg != 2) umma_bf16_2sm(tmem_base, da + static_cast<uint64_t>(k * 128),
-                          db + static_cast<uint64_t>(k * 128), idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_2sm(&empty_bar[s]);
+              for (int k = 0; k < 4; ++k)
+                umma_bf16_2sm(tmem_base, da + static_cast<uint64_t>(k * 128),
+                              db + static_cast<uint64_t>(k * 128), idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_2sm(&empty_bar[s]);
+          }
+          __syncwarp();
         }
-        umma_commit_2sm(tmem_full_bar);
+        if (elect_one()) umma_commit_2sm(tmem_full_bar);
+        __syncwarp();
       }
     } else if (warp >= 4) {
       const int e = threadIdx.x - 128;

@@ -61,19 +61,19 @@ wgrad_multi_kernel(const __grid_constant__ WgradParams p, int T, int stages) {
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (num_kb > 0) {
+    // producer / MMA warps: warp-uniform loops, one elected lane issues
     if (warp == 0) {
-      if (lane == 0) {
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int kt = kt_begin + kb;
-          const int img = kt / ktiles_per_img;
-          const int t_in = kt - img * ktiles_per_img;
-          const int th = t_in / p.ktiles_w;
-          const int w0 = (t_in - th * p.ktiles_w) * p.kbw;
-          const int h0 = th * p.kbh;
-          const int s = kb % stages;
-          const uint32_t ph = (kb / stages) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          uint8_t* sa = smem + s * stage_bytes;
+      int img = kt_begin / ktiles_per_img;
+      int t_in = kt_begin - img * ktiles_per_img;
+      int th = t_in / p.ktiles_w;
+      int tw = t_in - th * p.ktiles_w;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int w0 = tw * p.kbw, h0 = th * p.kbh;
+        const int s = kb % stages;
+        const uint32_t ph = (kb / stages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * stage_bytes;
+        if (elect_one()) {
           mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
 #pragma unroll
           for (int j = 0; j < 2; ++j)
@@ -84,17 +84,20 @@ wgrad_multi_kernel(const __grid_constant__ WgradParams p, int T, int stages) {
                         h0 + tap.dh, img);
           }
         }
+        __syncwarp();
+        if (++tw == p.ktiles_w) { tw = 0; if (++th == p.ktiles_h) { th = 0; ++img; } }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int s = kb % stages;
-          const uint32_t ph = (kb / stages) & 1;
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * stage_bytes);
-          const uint64_t da = make_desc_mnmajor(sa, 64);
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+      const uint32_t smem_base = smem_u32(smem);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % stages;
+        const uint32_t ph = (kb / stages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * stage_bytes;
+        const uint64_t da = make_desc_mnmajor(sa, 64);
+        if (elect_one()) {
           for (int t = 0; t < T; ++t) {
             const uint64_t db = make_desc_mnmajor(sa + (2 + t) * kBoxBytes, 64);
 #pragma unroll
@@ -104,8 +107,10 @@ wgrad_multi_kernel(const __grid_constant__ WgradParams p, int T, int stages) {
           }
           umma_commit(&empty_bar[s]);
         }
-        umma_commit(tmem_full_bar);
+        __syncwarp();
       }
+      if (elect_one()) umma_commit(tmem_full_bar);
+      __syncwarp();
     } else if (warp >= 4) {
       const int e = threadIdx.x - 128;
       const int ew = warp - 4;

@@ -335,7 +335,16 @@ class NetExec:
           maps = [src.tmap_interior(bw, bh, n0, nimg)]
           taps, kch = no.taps_conv(l.k, l.cin, origin=-self._pad_before(j)), l.cin
         if maps is not None:
-          no.add_conv(plan, name, maps, taps, kch, w2, dst.view(n0), ho, wo, nimg, l.cout, bias, act, stats)
+          tile, halo = None, None
+          if (len(maps) == 1 and l.stride == 1 and not is_small_cin(l) and l.kind == "conv"
+              and nv.pick_block_n(l.cout) == 256 and ho % 16 == 0 and wo % 8 == 0):
+            # wide stride-1 convs: 8 x 16 pixel tiles whose taps share one halo tile (conv_gemm_ts.cu)
+            tile = (8, 16)
+            view_of = src.tmap_padded if l.pad == "reflect" else src.tmap_interior
+            halo = lambda w_, h_, f=view_of: f(w_, h_, n0, nimg)
+            maps = [view_of(8, 16, n0, nimg)]
+          no.add_conv(plan, name, maps, taps, kch, w2, dst.view(n0), ho, wo, nimg, l.cout, bias, act, stats,
+                      tile=tile, halo_map=halo)
       if l.norm:
         nxt = self.inp[j + 1]
         skip = self.inp[j - 1].view(n0) if l.res == "b" else NULL_VIEW
@@ -522,7 +531,8 @@ class NetExec:
         taps = [(0, 0, (p - r) * P + (p - s), 0, (r * l.k + s) * l.cin)
                 for r in range(l.k) for s in range(l.k)]
         no.add_conv_flat(plan, name, dY.tmap_flat(n0, nimg), taps, l.cout, w2, gin.ptr(n0, padded=True),
-                         l.cin, rows, l.cin, b_mn=True)
+                         l.cin, rows, l.cin, b_mn=True,
+                         halo_map=lambda rows_box: dY.tmap_flat(n0, nimg, rows_box=rows_box))
       return (gin.view(n0), p)
     pb = self._pad_before(j)
     if l.stride == 2:
@@ -545,7 +555,11 @@ class NetExec:
     # stride-1 TF-SAME conv: dX[q] = sum dY[q + pb - (r, s)] W[r, s]
     gin = self.gin[j]
     bw, bh = nv.tile_shape(hi, wi)
+    halo = None
+    if nv.pick_block_n(l.cin) == 256 and hi % 16 == 0 and wi % 8 == 0:
+      bw, bh = 8, 16
+      halo = lambda w_, h_: dY.tmap_interior(w_, h_, n0, nimg)
     taps = [(0, 0, pb - s, pb - r, (r * l.k + s) * l.cin) for r in range(l.k) for s in range(l.k)]
     no.add_conv(plan, name, [dY.tmap_interior(bw, bh, n0, nimg)], taps, l.cout, w2, gin.view(n0), hi, wi,
-                nimg, l.cin, b_mn=True)
+                nimg, l.cin, b_mn=True, tile=(bw, bh), halo_map=halo)
     return (gin.view(n0), 0)

@@ -79,7 +79,7 @@ def add_conv(plan, name: str, a_maps: Sequence[bytes], taps: Sequence[Tap], k_ch
              block_n: Optional[int] = None, tile: Optional[Tuple[int, int]] = None,
              w_limit: Optional[int] = None,
              phases: Optional[Sequence[Tuple[Sequence[Tap], int]]] = None,
-             fp8: bool = False, out_scale: int = 0):
+             fp8: bool = False, out_scale: int = 0, halo_map=None):
   """Box-mode implicit GEMM: out[n, h, w, :n_channels] over an out_h x out_w grid.
 
   k_channels: channels of the A views (K per tap); n_channels: valid output channels."""
@@ -95,41 +95,93 @@ def add_conv(plan, name: str, a_maps: Sequence[bytes], taps: Sequence[Tap], k_ch
       ph.append((len(taps), len(ptaps), int(off)))
       taps.extend(ptaps)
   kblock = 128 if fp8 else 64   # elements per 128-byte K block
+  ts_map, ts = b"", []
+  if halo_map is not None and tap_share_ok(block_n, fp8, phases, a_maps):
+    # halo_map(box_w, box_h) -> tensor map of the same view as a_maps[0] with a halo-sized box
+    dws, dhs = [t[2] for t in taps], [t[3] for t in taps]
+    box_w, box_h = bw + max(dws) - min(dws), bh + max(dhs) - min(dhs)
+    if bw % 8 == 0 and box_w <= 256 and box_h <= 256 and box_w * box_h * 128 <= TS_STAGE_BYTES:
+      ts_map = halo_map(box_w, box_h)
+      ts = [1, 0, box_w * box_h * 128, box_w, min(dws), min(dhs), box_w * 128 if bw == 8 else 1024]
+      if bw != 8 and bh != 1:
+        ts_map, ts = b"", []   # 8-row groups must be equally spaced: bw == 8 (pitch) or a single row
   return plan.add_conv_gemm(name, list(a_maps), nv.wmat_tmap(w2_bf16, block_n, b_mn),
                             list(taps), k_channels // kblock, out_w // bw, out_h // bh, bw, bh,
                             out_w if w_limit is None else w_limit, ptr, sn, sh, sw, n_channels,
-                            bias, act, stats, block_n, b_mn, nimg, ph, out_scale, fp8)
+                            bias, act, stats, block_n, b_mn, nimg, ph, out_scale, fp8, ts_map, ts)
+
+
+TS_STAGE_BYTES = 34 * 1024   # csrc/conv_gemm_ts.cu: TsCfg::kAStageBytes
+
+
+def tap_share_ok(block_n: int, fp8: bool, phases, a_maps) -> bool:
+  import os
+  return (block_n == 256 and not fp8 and phases is None and len(a_maps) == 1
+          and os.environ.get("B2_TAPSHARE", "1") != "0")
 
 
 def add_conv_flat(plan, name: str, a_map: bytes, taps: Sequence[Tap], k_channels: int,
                   w2_bf16: torch.Tensor, out_ptr: int, out_row_stride: int, rows: int,
-                  n_channels: int, b_mn: bool = False, block_n: Optional[int] = None):
+                  n_channels: int, b_mn: bool = False, block_n: Optional[int] = None,
+                  halo_map=None):
   """Flat-mode implicit GEMM over ``rows`` consecutive pixels of a zero-ringed domain
   (taps are constant row offsets): out[row, :n_channels]."""
   block_n = block_n or nv.pick_block_n(n_channels)
   if b_mn:
     block_n = max(block_n, 64)
   tiles = (rows + 127) // 128
+  ts_map, ts = b"", []
+  if halo_map is not None and tap_share_ok(block_n, False, None, [a_map]):
+    # flat rows: the halo of a 128-row tile is [min_dw, 128 + max_dw) rows, loaded as two boxes
+    dws = [t[2] for t in taps]
+    span = 128 + max(dws) - min(dws)
+    box_rows = -(-((span + 1) // 2) // 8) * 8
+    if all(t[3] == 0 for t in taps) and 2 * box_rows * 128 <= TS_STAGE_BYTES and box_rows <= 256:
+      ts_map = halo_map(box_rows)
+      ts = [2, box_rows, box_rows * 128, 0, min(dws), 0, 1024]
   return plan.add_conv_gemm(name, [a_map], nv.wmat_tmap(w2_bf16, block_n, b_mn), list(taps),
                             k_channels // 64, tiles, 1, 128, 1, rows, out_ptr, 0, 0,
-                            out_row_stride, n_channels, 0, 0, 0, block_n, b_mn, 1, [])
+                            out_row_stride, n_channels, 0, 0, 0, block_n, b_mn, 1, [], 0, False,
+                            ts_map, ts)
+
+
+def pick_ksplit(base_ctas: int, total_kt: int, slots: int = 148, epilogue_kt: int = 12) -> int:
+  """Split-K factor of a wgrad launch, chosen per whole waves of the machine.
+
+  The wgrad kernels need > 114 KB of shared memory, so one CTA is resident per SM and a grid of
+  ``base_ctas * ksplit`` CTAs runs in ceil(ctas / 148) waves of ceil(total_kt / ksplit) K tiles
+  each plus one (un-overlapped) reduce-add epilogue worth ~12 K tiles (measured: 3x3 256->256,
+  12 images: ksplit 8 -> 1 wave, 54 us; ksplit 17 -> 3 waves, 77 us)."""
+  best, best_cost = 1, None
+  for ks in range(1, max(1, min(total_kt, 4 * slots // max(1, base_ctas) + 1)) + 1):
+    waves = -(-base_ctas * ks // slots)
+    cost = waves * (-(-total_kt // ks) + epilogue_kt)
+    if best_cost is None or cost < best_cost:
+      best, best_cost = ks, cost
+  return best
 
 
 def add_wgrad(plan, name: str, dy_map, a_maps: Sequence[bytes], taps: Sequence[Tap],
               kt_w: int, kt_h: int, kbw: int, kbh: int, nimg: int, cin: int, cout: int,
               dw_ptr: int, ldw: int, block_n: Optional[int] = None, target_ctas: Optional[int] = None):
   import os
-  target_ctas = target_ctas or int(os.environ.get("B2_WGRAD_CTAS", "296"))
+  target_ctas = target_ctas or int(os.environ.get("B2_WGRAD_CTAS", "0"))   # 0: wave-aware choice
   block_n = block_n or max(64, nv.pick_block_n(cin))
   m_tiles = (cout + 127) // 128
   n_tiles = (cin + block_n - 1) // block_n
   base = m_tiles * n_tiles * len(taps)
   total_kt = kt_w * kt_h * nimg
-  ksplit = max(1, min(total_kt, (target_ctas + base - 1) // base))
+
+  def split(base_ctas):
+    if target_ctas:
+      return max(1, min(total_kt, (target_ctas + base_ctas - 1) // base_ctas))
+    return pick_ksplit(base_ctas, total_kt)
+
+  ksplit = split(base)
   multi = (cin == 64 and 2 <= len(taps) <= 7 and not isinstance(dy_map, (list, tuple))
            and os.environ.get("B2_WGRAD_MULTI", "1") != "0")
   if multi:   # narrow layers: one CTA accumulates all taps (dY tile loaded once per K tile)
-    ksplit = -max(1, min(total_kt, (target_ctas + m_tiles - 1) // m_tiles))
+    ksplit = -split(m_tiles)
   # dy_map: one view, or a list of views selected per tap through tap[1] (phase-merged wgrad)
   dy_maps = list(dy_map) if isinstance(dy_map, (list, tuple)) else [dy_map]
   return plan.add_wgrad(name, dy_maps, list(a_maps), list(taps), kt_w, kt_h, kbw, kbh, nimg,
@@ -144,10 +196,11 @@ def add_wgrad_row(plan, name: str, dY: Buf, src: Buf, n0: int, nimg: int, cin: i
                   dw_ptr: int, ldw: int, target_ctas: Optional[int] = None):
   """Tap-shared 2-CTA wgrad of a 3x3 stride-1 reflect-padded conv (csrc/wgrad_row.cu)."""
   import os
-  target_ctas = target_ctas or int(os.environ.get("B2_WGRAD_CTAS", "296"))
+  target_ctas = target_ctas or int(os.environ.get("B2_WGRAD_CTAS", "0"))
   base = 2 * (cout // 256) * (cin // 128) * 3
   total_kt = (dY.w // 64) * dY.h * nimg
-  ksplit = max(1, min(total_kt, (target_ctas + base - 1) // base))
+  ksplit = (max(1, min(total_kt, (target_ctas + base - 1) // base)) if target_ctas
+            else pick_ksplit(base, total_kt))
   return plan.add_wgrad_row(name, dY.tmap_interior(64, 1, n0, nimg), src.tmap_padded(66, 1, n0, nimg),
                             dY.w // 64, dY.h, nimg, cin, cout, dw_ptr, ldw, ksplit)
 

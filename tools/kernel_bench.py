@@ -44,16 +44,19 @@ dw = torch.zeros(c, 9 * c, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
 plans = {}
-bw, bh = nv.tile_shape(h, h)
+ts = os.environ.get("B2_TAPSHARE", "1") != "0"   # tap-shared halo tiles (csrc/conv_gemm_ts.cu)
+bw, bh = (8, 16) if ts else nv.tile_shape(h, h)
 p = C.Plan()
 no.add_conv(p, "fwd", [x.tmap_padded(bw, bh)], no.taps_conv(3, c), c, w2, out.view(), h, h, n, c,
-            stats=0 if a.no_stats else stats.data_ptr())
+            stats=0 if a.no_stats else stats.data_ptr(), tile=(bw, bh),
+            halo_map=(lambda w_, h_: x.tmap_padded(w_, h_)) if ts else None)
 plans["fwd"] = (p, 2.0 * n * h * h * 9 * c * c)
 P = h + 2
 rows = n * P * P
 p = C.Plan()
 taps = [(0, 0, (1 - r) * P + (1 - s), 0, (r * 3 + s) * c) for r in range(3) for s in range(3)]
-no.add_conv_flat(p, "dgrad", dy.tmap_flat(), taps, c, w2, dxp.ptr(padded=True), c, rows, c, b_mn=True)
+no.add_conv_flat(p, "dgrad", dy.tmap_flat(), taps, c, w2, dxp.ptr(padded=True), c, rows, c, b_mn=True,
+                 halo_map=(lambda rb: dy.tmap_flat(rows_box=rb)) if ts else None)
 plans["dgrad"] = (p, 2.0 * n * h * h * 9 * c * c)
 kbw, kbh = nv.tile_shape(h, h, 64)
 p = C.Plan()

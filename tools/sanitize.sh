@@ -1,0 +1,22 @@
+#!/bin/bash
+# compute-sanitizer passes over the native kernels. Run on a GPU box:
+#   bash tools/sanitize.sh [memcheck|racecheck|synccheck|initcheck] ...   (default: memcheck synccheck racecheck)
+# Logs go to gpurun_out/sanitizer_<tool>.log; the last line of each is the ERROR SUMMARY.
+# memcheck runs the whole smoke step (every kernel of the plan, eager launches); the slower tools
+# run the single-kernel tests at their smallest shapes.
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+TOOLS=${*:-memcheck synccheck racecheck}
+export B2_NO_GRAPH=1
+for tool in $TOOLS; do
+  log=gpurun_out/sanitizer_${tool}.log
+  if [ "$tool" = memcheck ]; then
+    target=(python -c "import __graft_entry__ as g; g.smoke()")
+  else
+    target=(python -m pytest tests/test_native_kernels.py -x -q -m gpu -k "conv3x3 or in_apply or losses")
+  fi
+  timeout ${SANITIZE_TIMEOUT:-900} compute-sanitizer --tool "$tool" --print-limit 20 \
+      --log-file "$log" "${target[@]}" > gpurun_out/sanitizer_${tool}.out 2>&1
+  echo "== $tool rc=$? $(grep -a 'ERROR SUMMARY' "$log" | tail -1)"
+done
