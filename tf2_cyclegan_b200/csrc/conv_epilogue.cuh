@@ -15,13 +15,17 @@ struct EpiCfg {
   static constexpr int kRedBytes = kRowGroups * kChunkN * 2 * 4;
 };
 
-// Called by the 128 epilogue threads (e = TMEM lane = tile row). `release` is invoked once by
-// every thread right after its last TMEM read (arrive on the tmem-empty barrier).
+// Called by the 128 threads of ONE epilogue warpgroup (e = TMEM lane = tile row) for BLOCK_N
+// accumulator columns starting at `taddr` / output channel n0; kernels run two warpgroups per
+// tile, each on its own half of the columns with its own staging / red buffers and named
+// barriers (bar_id, bar_id + 1). `release` is invoked once by every thread right after its last
+// TMEM read (arrive on the tmem-empty barrier).
 template <int BLOCK_N, class Release>
 __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, __nv_bfloat16* out_base, uint8_t* stage_buf,
                                                    float* red, uint32_t taddr, int img, int h0,
                                                    int w0, int n0, int e, int ew, int lane,
-                                                   bool tile_valid, Release release, int dbg = 0) {
+                                                   bool tile_valid, Release release, int dbg = 0,
+                                                   int bar_id = 1) {
   constexpr int CN = EpiCfg<BLOCK_N>::kChunkN;
   constexpr int CH = EpiCfg<BLOCK_N>::kChunks16;
   constexpr int RG = EpiCfg<BLOCK_N>::kRowGroups;
@@ -113,7 +117,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, __nv
       tc_fence_before();
       release();
     }
-    named_bar_sync(1, 128);
+    named_bar_sync(bar_id, 128);
 
     // ---- InstanceNorm partial statistics (sum, sum of squares per channel)
     if (p.stats != nullptr && tile_valid) {
@@ -139,7 +143,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, __nv
         red[(rg * CN + ci * 8 + j) * 2 + 0] = s[j];
         red[(rg * CN + ci * 8 + j) * 2 + 1] = q[j];
       }
-      named_bar_sync(2, 128);
+      named_bar_sync(bar_id + 1, 128);
       if (e < CN && n0 + c0 + e < p.cout) {
         float ss = 0.f, qq = 0.f;
 #pragma unroll 8
@@ -180,7 +184,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, __nv
         }
       }
     }
-    named_bar_sync(1, 128);   // staging / red buffers are reused by the next chunk
+    named_bar_sync(bar_id, 128);   // staging / red buffers are reused by the next chunk
   }
 }
 

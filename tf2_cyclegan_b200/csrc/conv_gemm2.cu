@@ -23,11 +23,12 @@ struct Gemm2Cfg {
   static constexpr int kABytes = 128 * 128;
   static constexpr int kBBytes = kHalfN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N >= 256) ? 6 : 8;
+  static constexpr int kStages = (BLOCK_N >= 256) ? 5 : 7;
   static constexpr int kAccCols = BLOCK_N;
   static constexpr int kTmemCols = 2 * kAccCols;
-  static constexpr int kStagingBytes = EpiCfg<BLOCK_N>::kStagingBytes;
-  static constexpr int kRedBytes = EpiCfg<BLOCK_N>::kRedBytes;
+  // two epilogue warpgroups, each owns half of the columns and its own staging / red buffers
+  static constexpr int kStagingBytes = 2 * EpiCfg<kHalfN>::kStagingBytes;
+  static constexpr int kRedBytes = 2 * EpiCfg<kHalfN>::kRedBytes;
   static constexpr int kBarrierBytes = (2 * kStages + 4) * 8 + 16;
   static constexpr int kSmemBytes =
       kStages * kStageBytes + kStagingBytes + kRedBytes + kBarrierBytes + 1024;
@@ -35,7 +36,7 @@ struct Gemm2Cfg {
 };
 
 template <int BLOCK_N, bool B_MN, bool FP8>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int dbg) {
   using Cfg = Gemm2Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
@@ -73,7 +74,7 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 256);   // 128 epilogue threads x 2 CTAs (used in the leader)
+      mbar_init(&tmem_empty_bar[a], 512);   // 256 epilogue threads x 2 CTAs (used in the leader)
     }
     fence_barrier_init();
   }
@@ -178,8 +179,12 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int 
     }
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, own TMEM half) =====================
-    const int e = threadIdx.x - 128;
-    const int ew = warp - 4;
+    // two warpgroups (warps 4-7, 8-11): each drains half of the accumulator columns
+    const int wg = (warp - 4) >> 2;
+    const int e = (threadIdx.x - 128) & 127;
+    const int ew = warp & 3;
+    uint8_t* my_stage = stage_buf + wg * EpiCfg<Cfg::kHalfN>::kStagingBytes;
+    float* my_red = red + wg * (EpiCfg<Cfg::kHalfN>::kRedBytes / 4);
     uint32_t tile_i = 0;
     for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++tile_i) {
       int mt, n0, img, h0, w0;
@@ -188,10 +193,12 @@ conv_gemm2_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int 
       const uint32_t acc_ph = (tile_i >> 1) & 1;
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * Cfg::kAccCols + (static_cast<uint32_t>(ew * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * Cfg::kAccCols + wg * Cfg::kHalfN +
+                             (static_cast<uint32_t>(ew * 32) << 16);
       if (dbg == 1) { tc_fence_before(); mbar_arrive_cluster(&tmem_empty_bar[acc], 0); continue; }
-      conv_epilogue_tile<BLOCK_N>(p, p.out + p.phase_out_off[pt / pairs_per_phase], stage_buf, red, taddr, img, h0, w0, n0, e, ew, lane, mt < m_tiles,
-                                  [&]() { mbar_arrive_cluster(&tmem_empty_bar[acc], 0); }, dbg);
+      conv_epilogue_tile<Cfg::kHalfN>(p, p.out + p.phase_out_off[pt / pairs_per_phase], my_stage, my_red, taddr,
+                                      img, h0, w0, n0 + wg * Cfg::kHalfN, e, ew, lane, mt < m_tiles,
+                                      [&]() { mbar_arrive_cluster(&tmem_empty_bar[acc], 0); }, dbg, 1 + 2 * wg);
     }
   }
 
@@ -226,7 +233,7 @@ static void launch2_t(const ConvGemmParams& p, int num_images, cudaStream_t stre
   const int clusters = pairs < max_clusters ? pairs : max_clusters;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * clusters);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(384);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

@@ -23,11 +23,12 @@ struct TsCfg {
   static constexpr int kAStageBytes = 34 * 1024;       // 272 rows x 128 B (flat: 2 boxes of 136 rows)
   static constexpr int kAStages = 2;
   static constexpr int kBBytes = 128 * 128;            // this CTA's half of the weight tile
-  static constexpr int kBStages = 7;
+  static constexpr int kBStages = 6;
   static constexpr int kAccCols = BLOCK_N;
   static constexpr int kTmemCols = 2 * kAccCols;
-  static constexpr int kStagingBytes = EpiCfg<BLOCK_N>::kStagingBytes;
-  static constexpr int kRedBytes = EpiCfg<BLOCK_N>::kRedBytes;
+  static constexpr int kHalfN = BLOCK_N / 2;           // columns per epilogue warpgroup
+  static constexpr int kStagingBytes = 2 * EpiCfg<kHalfN>::kStagingBytes;
+  static constexpr int kRedBytes = 2 * EpiCfg<kHalfN>::kRedBytes;
   static constexpr int kNumBars = 2 * kAStages + 2 * kBStages + 4;
   static constexpr int kBarrierBytes = kNumBars * 8 + 16;
   static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBBytes + kStagingBytes +
@@ -36,7 +37,7 @@ struct TsCfg {
 };
 
 template <bool B_MN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 conv_gemm_ts_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int dbg) {
   using Cfg = TsCfg;
   constexpr int BLOCK_N = Cfg::BLOCK_N;
@@ -91,7 +92,7 @@ conv_gemm_ts_kernel(const __grid_constant__ ConvGemmParams p, int num_images, in
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 256);   // 128 epilogue threads x 2 CTAs (used in the leader)
+      mbar_init(&tmem_empty_bar[a], 512);   // 256 epilogue threads x 2 CTAs (used in the leader)
     }
     fence_barrier_init();
   }
@@ -210,8 +211,12 @@ conv_gemm_ts_kernel(const __grid_constant__ ConvGemmParams p, int num_images, in
     }
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, own TMEM half) =====================
-    const int e = threadIdx.x - 128;
-    const int ew = warp - 4;
+    // two warpgroups (warps 4-7, 8-11): each drains half of the accumulator columns
+    const int wg = (warp - 4) >> 2;
+    const int e = (threadIdx.x - 128) & 127;
+    const int ew = warp & 3;
+    uint8_t* my_stage = stage_buf + wg * EpiCfg<Cfg::kHalfN>::kStagingBytes;
+    float* my_red = red + wg * (EpiCfg<Cfg::kHalfN>::kRedBytes / 4);
     uint32_t tile_i = 0;
     for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++tile_i) {
       int mt, n0, img, h0, w0;
@@ -219,11 +224,12 @@ conv_gemm_ts_kernel(const __grid_constant__ ConvGemmParams p, int num_images, in
       const uint32_t acc = tile_i & 1;
       mbar_wait(&tmem_full_bar[acc], (tile_i >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * Cfg::kAccCols + (static_cast<uint32_t>(ew * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * Cfg::kAccCols + wg * Cfg::kHalfN +
+                             (static_cast<uint32_t>(ew * 32) << 16);
       if (dbg == 1) { tc_fence_before(); mbar_arrive_cluster(&tmem_empty_bar[acc], 0); continue; }
-      conv_epilogue_tile<BLOCK_N>(p, p.out, stage_buf, red, taddr, img, h0, w0, n0, e, ew, lane,
-                                  mt < m_tiles,
-                                  [&]() { mbar_arrive_cluster(&tmem_empty_bar[acc], 0); }, dbg);
+      conv_epilogue_tile<Cfg::kHalfN>(p, p.out, my_stage, my_red, taddr, img, h0, w0, n0 + wg * Cfg::kHalfN,
+                                      e, ew, lane, mt < m_tiles,
+                                      [&]() { mbar_arrive_cluster(&tmem_empty_bar[acc], 0); }, dbg, 1 + 2 * wg);
     }
   }
 
@@ -253,7 +259,7 @@ static void launch_ts_t(const ConvGemmParams& p, int num_images, cudaStream_t st
   const int clusters = pairs < sms / 2 ? pairs : sms / 2;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * clusters);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(384);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

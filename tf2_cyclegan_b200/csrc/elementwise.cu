@@ -50,6 +50,16 @@ __device__ __forceinline__ int reflect_set(int i, int n, int p, int (&out)[2]) {
   return cnt;
 }
 
+// linear pixel index -> (n, h, w) with 32-bit unsigned arithmetic (every tensor here has
+// far fewer than 2^31 pixels; 64-bit div / mod costs ~5x more instructions)
+__device__ __forceinline__ void unravel(uint32_t i, int W, int H, int& n, int& h, int& w) {
+  const uint32_t r = i / static_cast<uint32_t>(W);
+  w = static_cast<int>(i - r * static_cast<uint32_t>(W));
+  const uint32_t q = r / static_cast<uint32_t>(H);
+  h = static_cast<int>(r - q * static_cast<uint32_t>(H));
+  n = static_cast<int>(q);
+}
+
 __device__ __forceinline__ float act_grad_from_pre(float y, float slope) {
   return y > 0.f ? 1.f : slope;
 }
@@ -405,8 +415,8 @@ __global__ void __launch_bounds__(kThreads, 4) in_bwd_apply_kernel(const InBwdAp
 // ------------------------------------------------------------------ act_bwd
 __global__ void __launch_bounds__(kThreads) act_bwd_kernel(const ActBwdParams p) {
   __shared__ float sb[64];
-  const int c8 = p.C >> 3;
-  const long long total = static_cast<long long>(p.N) * p.H * p.W * c8;
+  const uint32_t c8 = static_cast<uint32_t>(p.C >> 3);
+  const uint32_t total = static_cast<uint32_t>(p.N) * p.H * p.W * c8;
   if (threadIdx.x < 64) sb[threadIdx.x] = 0.f;
   __syncthreads();
   float bacc[8];
@@ -415,14 +425,11 @@ __global__ void __launch_bounds__(kThreads) act_bwd_kernel(const ActBwdParams p)
   int my_c = -1;
   const bool is_tanh = p.act == ACT_TANH;
   const float slope = act_slope(p.act);
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % c8) * 8;
-    long long r = i / c8;
-    const int w = static_cast<int>(r % p.W);
-    r /= p.W;
-    const int h = static_cast<int>(r % p.H);
-    const int n = static_cast<int>(r / p.H);
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t pix = i / c8;
+    const int c = static_cast<int>(i - pix * c8) * 8;
+    int n, h, w;
+    unravel(pix, p.W, p.H, n, h, w);
     float g[8], o[8];
     gather_g(p.g1, p.fold1, p.g2, n, h, w, p.H, p.W, c, g);
     load8(vptr(p.out, n, h, w) + c, o);
@@ -436,10 +443,21 @@ __global__ void __launch_bounds__(kThreads) act_bwd_kernel(const ActBwdParams p)
     store8(vptr_mut(p.dy, n, h, w) + c, g);
   }
   if (p.dbias != nullptr) {
-    if (my_c >= 0) {
+    // lanes l and l + k * c8 of a warp hold the same channel group: combine them with shuffles
+    // first (blockDim and the grid stride are multiples of c8), then one shared atomic per warp
+    if (c8 <= 32) {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (my_c + j < p.c_valid) atomicAdd(&sb[my_c + j], bacc[j]);
+        for (uint32_t o = 16; o >= c8; o >>= 1) bacc[j] += __shfl_xor_sync(0xffffffffu, bacc[j], o);
+    }
+    const int lane_c = static_cast<int>((threadIdx.x & 31u) % c8) * 8;
+    if ((threadIdx.x & 31u) < c8 || c8 > 32) {
+      const int cc = c8 <= 32 ? lane_c : my_c;
+      if (cc >= 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (cc + j < p.c_valid) atomicAdd(&sb[cc + j], bacc[j]);
+      }
     }
     __syncthreads();
     if (threadIdx.x < p.c_valid) atomicAdd(p.dbias + threadIdx.x, sb[threadIdx.x]);
@@ -451,10 +469,8 @@ __global__ void __launch_bounds__(kThreads) img_prep_kernel(const ImgPrepParams 
   const long long total = static_cast<long long>(p.N) * p.H * p.W;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int w = static_cast<int>(i % p.W);
-    long long r = i / p.W;
-    const int h = static_cast<int>(r % p.H);
-    const int n = static_cast<int>(r / p.H);
+    int n, h, w;
+    unravel(static_cast<uint32_t>(i), p.W, p.H, n, h, w);
     float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (p.src_is_f32) {
       const float* s = reinterpret_cast<const float*>(p.src) + i * 3;
@@ -496,10 +512,8 @@ __global__ void __launch_bounds__(kThreads) l1_loss_kernel(const L1LossParams p)
   float acc = 0.f;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int w = static_cast<int>(i % p.W);
-    long long r = i / p.W;
-    const int h = static_cast<int>(r % p.H);
-    const int n = static_cast<int>(r / p.H);
+    int n, h, w;
+    unravel(static_cast<uint32_t>(i), p.W, p.H, n, h, w);
     float pr[8];
     load8(vptr(p.pred, n, h, w), pr);
     const float* t = p.target + i * 3;
@@ -524,10 +538,8 @@ __global__ void __launch_bounds__(kThreads) mse_loss_kernel(const MseLossParams 
   float acc = 0.f;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int w = static_cast<int>(i % p.W);
-    long long r = i / p.W;
-    const int h = static_cast<int>(r % p.H);
-    const int n = static_cast<int>(r / p.H);
+    int n, h, w;
+    unravel(static_cast<uint32_t>(i), p.W, p.H, n, h, w);
     const float d = __bfloat162float(*vptr(p.d, n, h, w));
     const float e = p.target - d;
     acc += e * e;
@@ -544,10 +556,8 @@ __global__ void __launch_bounds__(kThreads) tap_gather_kernel(const TapGatherPar
   const float b0 = p.bias ? p.bias[0] : 0.f, b1 = p.bias ? p.bias[1] : 0.f, b2 = p.bias ? p.bias[2] : 0.f;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int w = static_cast<int>(i % p.W);
-    long long r = i / p.W;
-    const int h = static_cast<int>(r % p.H);
-    const int n = static_cast<int>(r / p.H);
+    int n, h, w;
+    unravel(static_cast<uint32_t>(i), p.W, p.H, n, h, w);
     const long long row0 = (static_cast<long long>(n) * p.Hp + h) * p.Wp + w;
     float a0 = b0, a1 = b1, a2 = b2;
 #pragma unroll 7
@@ -632,28 +642,27 @@ __global__ void __launch_bounds__(kThreads) fp8_w_quant_kernel(const Fp8Table t)
 // --------------------------------------------------- PatchGAN output layer bwd
 // dX[n,h,w,c] = sum_{r,s} gd[n, h - r + pb, w - s + pb] * W[0][r*4+s][c]
 __global__ void __launch_bounds__(kThreads) d4_dgrad_kernel(const D4BwdParams p) {
-  const int c8 = p.C >> 3;
-  const long long total = static_cast<long long>(p.N) * p.H * p.W * c8;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % c8) * 8;
-    long long r = i / c8;
-    const int w = static_cast<int>(r % p.W);
-    r /= p.W;
-    const int h = static_cast<int>(r % p.H);
-    const int n = static_cast<int>(r / p.H);
+  const uint32_t c8 = static_cast<uint32_t>(p.C >> 3);
+  const uint32_t total = static_cast<uint32_t>(p.N) * p.H * p.W * c8;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t pix = i / c8;
+    const int c = static_cast<int>(i - pix * c8) * 8;
+    int n, h, w;
+    unravel(pix, p.W, p.H, n, h, w);
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
     for (int kr = 0; kr < 4; ++kr) {
       const int oh = h - kr + p.pad_before;
       if (oh < 0 || oh >= p.H) continue;
+#pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         const int ow = w - ks + p.pad_before;
         if (ow < 0 || ow >= p.W) continue;
         const float g = __bfloat162float(*vptr(p.gd, n, oh, ow));
         float wv[8];
-        load8(p.w + static_cast<long long>(kr * 4 + ks) * p.C + c, wv);
+        load8(p.w + (kr * 4 + ks) * p.C + c, wv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] += g * wv[j];
       }
@@ -662,51 +671,53 @@ __global__ void __launch_bounds__(kThreads) d4_dgrad_kernel(const D4BwdParams p)
   }
 }
 
-// dW[0][t][c] += sum_pix gd[pix] * a[pix + tap]; grid: (16 taps, pixel chunks).
-// A thread owns 2 channels; pixels are walked 4 at a time so the loads overlap.
-__global__ void __launch_bounds__(kThreads) d4_wgrad_kernel(const D4BwdParams p, int chunks) {
-  const int t = blockIdx.x;
-  const int kr = t >> 2, ks = t & 3;
-  const long long npix = static_cast<long long>(p.N) * p.H * p.W;
-  const long long per = (npix + chunks - 1) / chunks;
-  const long long i0 = blockIdx.y * per, i1 = min(npix, i0 + per);
-  float gsum = 0.f;
-  const int c = threadIdx.x * 2;
-  const bool c_ok = c < p.C;
-  float a0 = 0.f, a1 = 0.f;
-  constexpr int U = 4;
-  for (long long base = i0; base < i1; base += U) {
-    float g[U];
-    uint32_t av[U];
+// dW[0][t][c] += sum_q gd[q - tap_t] * a[q][c]. The activation is read ONCE: a thread owns 8
+// channels (one 16-byte load per pixel) and keeps the 16 tap accumulators in registers; the
+// 256 / (C/8) pixel lanes of a block are combined in shared memory, then one atomic per value.
+// grid: pixel chunks. dbias += sum gd.
+__global__ void __launch_bounds__(kThreads) d4_wgrad_kernel(const D4BwdParams p, int pix_per_block) {
+  extern __shared__ float red[];   // [16][C]
+  const int c8 = p.C >> 3;
+  const int lanes = kThreads / c8;
+  const int c = (threadIdx.x % c8) * 8;
+  const int ln = threadIdx.x / c8;
+  const uint32_t npix = static_cast<uint32_t>(p.N) * p.H * p.W;
+  const uint32_t q0 = blockIdx.x * static_cast<uint32_t>(pix_per_block);
+  const uint32_t q1 = min(npix, q0 + static_cast<uint32_t>(pix_per_block));
+  for (int i = threadIdx.x; i < 16 * p.C; i += kThreads) red[i] = 0.f;
+  __syncthreads();
+  float acc[16][8];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long i = base + u;
-      g[u] = 0.f;
-      av[u] = 0u;
-      if (i < i1) {
-        const int w = static_cast<int>(i % p.W);
-        long long r = i / p.W;
-        const int h = static_cast<int>(r % p.H);
-        const int n = static_cast<int>(r / p.H);
-        g[u] = __bfloat162float(*vptr(p.gd, n, h, w));
-        const int ih = h + kr - p.pad_before, iw = w + ks - p.pad_before;
-        if (c_ok && ih >= 0 && ih < p.H && iw >= 0 && iw < p.W)
-          av[u] = __ldg(reinterpret_cast<const uint32_t*>(vptr(p.a, n, ih, iw) + c));
+  for (int t = 0; t < 16; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+  float gsum = 0.f;
+  for (uint32_t q = q0 + ln; q < q1; q += lanes) {
+    int n, h, w;
+    unravel(q, p.W, p.H, n, h, w);
+    float a[8];
+    load8(vptr(p.a, n, h, w) + c, a);
+    if (c == 0) gsum += __bfloat162float(*vptr(p.gd, n, h, w));
+#pragma unroll
+    for (int kr = 0; kr < 4; ++kr) {
+      const int oh = h - kr + p.pad_before;      // output pixel that reads a[q] through tap (kr, ks)
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const int ow = w - ks + p.pad_before;
+        float g = 0.f;
+        if (oh >= 0 && oh < p.H && ow >= 0 && ow < p.W) g = __bfloat162float(*vptr(p.gd, n, oh, ow));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[kr * 4 + ks][j] += g * a[j];
       }
     }
+  }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const float2 f = unpack_bf16x2(av[u]);
-      gsum += g[u];
-      a0 += g[u] * f.x;
-      a1 += g[u] * f.y;
-    }
-  }
-  if (c_ok) {
-    atomicAdd(p.dw + static_cast<long long>(t) * p.C + c, a0);
-    atomicAdd(p.dw + static_cast<long long>(t) * p.C + c + 1, a1);
-  }
-  if (t == 0 && threadIdx.x == 0 && p.dbias != nullptr) atomicAdd(p.dbias, gsum);
+  for (int t = 0; t < 16; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&red[t * p.C + c + j], acc[t][j]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < 16 * p.C; i += kThreads) atomicAdd(p.dw + i, red[i]);
+  if (p.dbias != nullptr && c == 0) atomicAdd(p.dbias, gsum);
 }
 
 inline int grid_for(long long total, int cap = 148 * 16) {
@@ -790,7 +801,8 @@ void launch_in_bwd_apply(const InBwdApplyParams& p, cudaStream_t s) {
 
 void launch_act_bwd(const ActBwdParams& p, cudaStream_t s) {
   const long long total = static_cast<long long>(p.N) * p.H * p.W * (p.C / 8);
-  act_bwd_kernel<<<grid_for_fixed_c(total, p.C / 8), kThreads, 0, s>>>(p);
+  // every block ends with c_valid same-address global atomics (dbias): keep the grid small
+  act_bwd_kernel<<<grid_for(total, ew_num_sms() * 2), kThreads, 0, s>>>(p);
 }
 
 void launch_img_prep(const ImgPrepParams& p, cudaStream_t s) {
@@ -835,11 +847,16 @@ void launch_d4_dgrad(const D4BwdParams& p, cudaStream_t s) {
   d4_dgrad_kernel<<<grid_for(total), kThreads, 0, s>>>(p);
 }
 void launch_d4_wgrad(const D4BwdParams& p, cudaStream_t s) {
-  const long long npix = static_cast<long long>(p.N) * p.H * p.W;
-  int chunks = static_cast<int>(npix / 32);   // ~32 pixels per block
-  if (chunks < 1) chunks = 1;
-  if (chunks > 256) chunks = 256;
-  d4_wgrad_kernel<<<dim3(16, chunks), kThreads, 0, s>>>(p, chunks);
+  const int npix = p.N * p.H * p.W;
+  const int lanes = kThreads / (p.C / 8);
+  int ppb = (npix + ew_num_sms() - 1) / ew_num_sms();      // one block per SM
+  ppb = (ppb + lanes - 1) / lanes * lanes;
+  const size_t smem = static_cast<size_t>(16) * p.C * sizeof(float);
+  if (p.C % 8 != 0 || kThreads % (p.C / 8) != 0 || smem > 48 * 1024) {
+    fprintf(stderr, "launch_d4_wgrad: unsupported channel count %d\n", p.C);
+    abort();
+  }
+  d4_wgrad_kernel<<<(npix + ppb - 1) / ppb, kThreads, smem, s>>>(p, ppb);
 }
 
 }  // namespace b2
