@@ -29,6 +29,21 @@ for _ in range(3):
   res = st.reduce_dict(nb.train_step(st.shard(x), st.shard(y)))
 sd = nb.state_dict()          # collective (gathers the ZeRO-1 shards)
 ok = True
+# replica consistency: the bf16 compute copy and every derived (re-laid-out) weight tensor must be
+# identical on all ranks and current (the fp32 master is sharded, so they may only come from wb)
+for n, stn in nb.state.items():
+  tensors = [("wb", stn.wb)] + [(k, d) for k, (d, _) in stn.derived.items()]
+  for name, t in tensors:
+    lo, hi = t.float().clone(), t.float().clone()
+    torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN)
+    torch.distributed.all_reduce(hi, op=torch.distributed.ReduceOp.MAX)
+    if not torch.equal(lo, hi):
+      ok = False; print("replicas diverge:", n, name, (hi - lo).abs().max().item())
+  for k, (d, idx) in stn.derived.items():
+    src = torch.cat([stn.wb, stn.wb.new_zeros(1)])
+    want = src[idx.long().clamp_min(-1)].view_as(d)
+    if not torch.equal(want, d):
+      ok = False; print("stale derived weights:", n, k, (want.float() - d.float()).abs().max().item())
 if st.rank == 0:
   one = types.SimpleNamespace(world_size=1, rank=0, device=st.device,
                               all_reduce_sum=lambda t: t)
@@ -51,7 +66,7 @@ if st.rank == 0:
       ok = False; print("weight mismatch", k, d)
   print("fused =", nb.fused, "multicast =", bool(nb.symm and nb.symm.multicast_ptrs("G")[0]), "ok =", ok)
 flag = torch.tensor([1 if ok else 0], device="cuda")
-st.broadcast(flag, 0)
+torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
 st.barrier(); st.shutdown()
 sys.exit(0 if flag.item() == 1 else 1)
 '''

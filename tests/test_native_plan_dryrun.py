@@ -80,3 +80,34 @@ def test_fp8_plan_builds(monkeypatch):
   assert "fp8.G.w_quant" in sp.names and "fp8.F.scales" in sp.names
   # backward stays bf16: same wgrad / dgrad op names as the bf16 plan
   assert any(n.startswith("G.res0a.wgrad") for n in sp.names)
+
+
+def test_allreduce_buckets_and_ownership(monkeypatch):
+  """Bucket plan of the fused all-reduce (CPU logic only): buckets tile the flat buffer in
+  backward order, and the per-bucket rank shards give every element exactly one owner."""
+  fake_native.install(monkeypatch)
+  monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+  from tf2_cyclegan_b200.engine.cyclegan import build_specs
+  from tf2_cyclegan_b200.engine.native_backend import NETS, NativeBackend
+  from tf2_cyclegan_b200.parallel.fused_allreduce import SymmetricBuffers
+  from tf2_cyclegan_b200.parallel.strategy import Strategy
+  be = NativeBackend(build_specs(A(9)), 1, Strategy(device="cpu"), seed=1, image_size=128, local_batch=1)
+  for n in NETS:
+    bs = be.plan_buckets(n)
+    st = be.state[n]
+    assert len(bs) == (4 if n in "GF" else 2)
+    assert bs[0][2] == st.n and bs[-1][0] == 0 and bs[-1][1] == 0
+    for (j0, lo0, hi0), (j1, lo1, hi1) in zip(bs, bs[1:]):
+      assert j1 < j0 and hi1 == lo0 and lo0 % 8 == 0           # descending layers, contiguous
+    if n in "GF":
+      assert max(hi - lo for _, lo, hi in bs) < 0.4 * st.n      # reasonably balanced (layer granularity)
+    assert bs[-1][2] - bs[-1][1] < 0.3 * st.n                   # the exposed (last) bucket is small
+    for world in (2, 3, 8):
+      owners = torch.zeros(st.n, dtype=torch.int32)
+      for rank in range(world):
+        sb = SymmetricBuffers.__new__(SymmetricBuffers)
+        sb.rank, sb.world, sb.buckets = rank, world, {}
+        sb.set_buckets(n, sorted((lo, hi) for _, lo, hi in bs))
+        for lo, hi in sb.owned_ranges(n, st.n):
+          owners[lo:hi] += 1
+      assert int(owners.min()) == 1 and int(owners.max()) == 1

@@ -156,6 +156,16 @@ __global__ void gather_bf16_kernel(__nv_bfloat16* dst, const float* src, const i
   }
 }
 
+// same gather from the bf16 compute copy (complete on every rank; the fp32 master is sharded)
+__global__ void gather_bf16_from_bf16_kernel(__nv_bfloat16* dst, const __nv_bfloat16* src, const int* idx,
+                                             long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int j = idx[i];
+    dst[i] = j >= 0 ? src[j] : __float2bfloat16(0.f);
+  }
+}
+
 __global__ void scatter_add_kernel(float* dst, const float* src, const int* idx, long long n) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -183,6 +193,14 @@ void launch_gather_bf16(__nv_bfloat16* dst, const float* src, const int* idx, lo
   if (b > 148 * 8) b = 148 * 8;
   if (b < 1) b = 1;
   gather_bf16_kernel<<<static_cast<int>(b), 256, 0, s>>>(dst, src, idx, n);
+}
+
+void launch_gather_bf16_from_bf16(__nv_bfloat16* dst, const __nv_bfloat16* src, const int* idx, long long n,
+                                  cudaStream_t s) {
+  long long b = (n + 255) / 256;
+  if (b > 1184) b = 1184;
+  if (b < 1) b = 1;
+  gather_bf16_from_bf16_kernel<<<static_cast<int>(b), 256, 0, s>>>(dst, src, idx, n);
 }
 
 }  // namespace b2

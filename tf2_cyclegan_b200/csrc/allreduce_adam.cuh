@@ -26,5 +26,7 @@ void launch_allreduce_adam(const AllreduceAdamParams& p, int num_blocks, cudaStr
 void launch_scatter_add(float* dst, const float* src, const int* idx, long long n, cudaStream_t s);
 void launch_gather_bf16(__nv_bfloat16* dst, const float* src, const int* idx, long long n,
                         cudaStream_t s);
+void launch_gather_bf16_from_bf16(__nv_bfloat16* dst, const __nv_bfloat16* src, const int* idx, long long n,
+                                  cudaStream_t s);
 
 }  // namespace b2

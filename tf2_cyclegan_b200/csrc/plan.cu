@@ -424,9 +424,14 @@ class Plan {
     return add(std::move(name),
                [g, mask, n](cudaStream_t s) { launch_mask_grad(P<float>(g), P<const uint8_t>(mask), n, s); });
   }
-  int add_gather_bf16(std::string name, uint64_t dst, uint64_t src_f32, uint64_t idx, long long n) {
-    return add(std::move(name), [dst, src_f32, idx, n](cudaStream_t s) {
-      launch_gather_bf16(P<__nv_bfloat16>(dst), P<const float>(src_f32), P<const int>(idx), n, s);
+  // dst[i] = bf16(src[idx[i]]) (0 where idx < 0); src is fp32, or bf16 when src_is_bf16
+  int add_gather_bf16(std::string name, uint64_t dst, uint64_t src, uint64_t idx, long long n,
+                      bool src_is_bf16) {
+    return add(std::move(name), [dst, src, idx, n, src_is_bf16](cudaStream_t s) {
+      if (src_is_bf16)
+        launch_gather_bf16_from_bf16(P<__nv_bfloat16>(dst), P<const __nv_bfloat16>(src), P<const int>(idx), n, s);
+      else
+        launch_gather_bf16(P<__nv_bfloat16>(dst), P<const float>(src), P<const int>(idx), n, s);
     });
   }
   int add_scatter_add(std::string name, uint64_t dst, uint64_t src, uint64_t idx, long long n) {
@@ -528,7 +533,8 @@ PYBIND11_MODULE(_C, m) {
       .def("add_adam", &Plan::add_adam)
       .def("add_step_increment", &Plan::add_step_increment)
       .def("add_mask_grad", &Plan::add_mask_grad)
-      .def("add_gather_bf16", &Plan::add_gather_bf16)
+      .def("add_gather_bf16", &Plan::add_gather_bf16, py::arg("name"), py::arg("dst"), py::arg("src"),
+           py::arg("idx"), py::arg("n"), py::arg("src_is_bf16") = false)
       .def("add_scatter_add", &Plan::add_scatter_add)
       .def("add_memset", &Plan::add_memset)
       .def("add_d4_bwd", &Plan::add_d4_bwd)

@@ -150,14 +150,40 @@ class StepPlan:
                  gout_view=self.gd_adv[D].view(0), gout_is_dy=True)
       plan.add_memset(f"zero.{D}.bstats2", e.bstat_arena.data_ptr(), e.bstat_arena.numel() * 4)
 
+    # With wgrad lanes and the fused all-reduce the optimizer (cross-GPU reduce + Adam + weight
+    # broadcast) is issued in BUCKETS on the WGRAD lane while the backward pass is still running:
+    # only the last bucket (the first layers of the network) is exposed.
+    opt_on_wgrad_lane = two and be.fused and be.wgrad_lanes and os.environ.get("B2_OPT_LANE", "1") != "0"
+
     def full(n, lanes=None):
       e = self.ex[n]
+      detach = opt_on_wgrad_lane and lanes is not None
+      hook = None
+      if detach:
+        # bucketed: as soon as the lowest layer of a bucket has been processed, its reduce +
+        # Adam + broadcast kernel is queued on the wgrad lane (behind that layer's wgrad GEMMs,
+        # after an event that covers the norm / bias gradients written on the main lane)
+        bs = be.buckets[n]
+        first = {j: k for k, (j, _, _) in enumerate(bs)}
+
+        def hook(j):
+          k = first.get(j)
+          if k is None:
+            return
+          ev = plan.add_event_record(f"sync.rec.{n}.bucket{k}", lanes[0])
+          plan.set_lane(lanes[1])
+          plan.add_event_wait(f"sync.wait.{n}.bucket{k}", lanes[1], ev)
+          be.emit_optimizer(plan, n, bucket=k, finish=(k == len(bs) - 1))
+          plan.set_lane(lanes[0])
+
       if n in ("G", "F"):
-        e.backward(plan, 0, 3 * b, wgrad=True, lanes=lanes)
+        e.backward(plan, 0, 3 * b, wgrad=True, lanes=lanes, join_wgrad=not detach, on_layer_done=hook)
       else:
-        e.backward(plan, 0, 2 * b, wgrad=True, gout_is_dy=True, lanes=lanes)
+        e.backward(plan, 0, 2 * b, wgrad=True, gout_is_dy=True, lanes=lanes, join_wgrad=not detach,
+                   on_layer_done=hook)
       self.marks[f"{n}_bwd_end"] = plan.size()
-      be.emit_optimizer(plan, n)
+      if not detach:
+        be.emit_optimizer(plan, n)
       self.marks[f"{n}_opt_end"] = plan.size()
 
     if two:
@@ -227,24 +253,60 @@ class NativeBackend:
         numel = FlatLayout(specs[n]).numel
         gbuf, wbuf = self.symm.alloc(n, numel)
       self.state[n] = NetState(specs[n], logical, self.device, grad_buffer=gbuf, wb_buffer=wbuf)
+    # gradient all-reduce buckets (fused path): plan order = the order their gradients become final
+    self.buckets: Dict[str, List[tuple]] = {}
+    self.bucket_index: Dict[str, List[int]] = {}
+    if self.fused:
+      for n in NETS:
+        bs = self.plan_buckets(n)
+        asc = sorted((lo, hi) for _, lo, hi in bs)
+        self.symm.set_buckets(n, asc)
+        self.buckets[n] = bs
+        self.bucket_index[n] = [asc.index((lo, hi)) for _, lo, hi in bs]
+    self._opt_only_plan = None
     self._plans: Dict[int, StepPlan] = {}
     self._launches = 0
     torch.cuda.synchronize(self.device)
     strategy.barrier()
 
   # ------------------------------------------------------------ optimizer
-  def emit_optimizer(self, plan, n: str):
+  def plan_buckets(self, n: str) -> List[tuple]:
+    """All-reduce buckets of network n: [(first layer index, lo, hi)] in the order their gradients
+    become final (the backward pass visits layers last to first), about equal in bytes. A bucket
+    is reduced as soon as its first (lowest) layer has been processed."""
     st = self.state[n]
-    plan.add_mask_grad(f"opt.{n}.mask", st.g.data_ptr(), st.mask.data_ptr(), st.n)
-    if self.fused:
-      self.symm.emit_allreduce_adam(plan, n, st, **ADAM)
+    layers = st.layout.spec.layers
+    offs = [st.layout.seg(l, "kernel").offset for l in layers] + [st.n]
+    want = int(os.environ.get("B2_AR_BUCKETS", "4" if n in ("G", "F") else "2"))
+    target = st.n / max(1, want)
+    out, hi = [], st.n
+    for j in range(len(layers) - 1, -1, -1):
+      if j == 0 or (hi - offs[j] >= target and len(out) < want - 1):
+        out.append((j, offs[j] if j else 0, hi))
+        hi = offs[j]
+    return out
+
+  def emit_optimizer(self, plan, n: str, bucket: Optional[int] = None, finish: bool = True):
+    """Optimizer ops of network n. Fused path: ``bucket`` selects ONE all-reduce bucket (index into
+    plan_buckets(n)); ``finish`` adds the per-step tail (step counter, derived weights)."""
+    st = self.state[n]
+    fused = self.fused and os.environ.get("B2_AR_SKIP", "0") != "1"   # B2_AR_SKIP: timing experiment only
+    if fused and bucket is not None:
+      _, lo, hi = self.buckets[n][bucket]
+      plan.add_mask_grad(f"opt.{n}.mask[{lo}:{hi}]", st.g.data_ptr() + 4 * lo, st.mask.data_ptr() + lo, hi - lo)
+      self.symm.emit_allreduce_adam(plan, n, st, bucket=self.bucket_index[n][bucket], **ADAM)
     else:
-      plan.add_adam(f"opt.{n}.adam", st.w.data_ptr(), st.m.data_ptr(), st.v.data_ptr(), st.g.data_ptr(),
-                    st.wb.data_ptr(), st.step.data_ptr(), ADAM["lr"], ADAM["b1"], ADAM["b2"], ADAM["eps"],
-                    1.0, st.n)
-      plan.add_memset(f"zero.{n}.grads", st.g.data_ptr(), st.n * 4)
-    plan.add_step_increment(f"opt.{n}.step", st.step.data_ptr())
-    st.refresh_derived_ops(plan, f"opt.{n}")
+      plan.add_mask_grad(f"opt.{n}.mask", st.g.data_ptr(), st.mask.data_ptr(), st.n)
+      if fused:
+        self.symm.emit_allreduce_adam(plan, n, st, **ADAM)
+      else:
+        plan.add_adam(f"opt.{n}.adam", st.w.data_ptr(), st.m.data_ptr(), st.v.data_ptr(), st.g.data_ptr(),
+                      st.wb.data_ptr(), st.step.data_ptr(), ADAM["lr"], ADAM["b1"], ADAM["b2"], ADAM["eps"],
+                      1.0, st.n)
+        plan.add_memset(f"zero.{n}.grads", st.g.data_ptr(), st.n * 4)
+    if finish:
+      plan.add_step_increment(f"opt.{n}.step", st.step.data_ptr())
+      st.refresh_derived_ops(plan, f"opt.{n}")
 
   # ---------------------------------------------------------------- plans
   def plan_for(self, b: int) -> StepPlan:
@@ -329,8 +391,19 @@ class NativeBackend:
       if self.world > 1 and not self.fused:
         self.strategy.all_reduce_sum(st.g)
       # run just the optimizer ops of any existing plan (gradients are zero locally)
-    sp = self.plan_for(max(self._plans.keys(), default=1))
     s = self._stream()
+    if self.fused:
+      # the bucketed optimizer launches are interleaved with the backward pass in the step plan:
+      # replay them from an optimizer-only plan, bucket by bucket in the same order as the peers
+      if self._opt_only_plan is None:
+        plan = nv.load().Plan()
+        for n in NETS:
+          for k in range(len(self.buckets[n])):
+            self.emit_optimizer(plan, n, bucket=k, finish=(k == len(self.buckets[n]) - 1))
+        self._opt_only_plan = plan
+      self._opt_only_plan.run(0, -1, s, False)
+      return self._zero_results(False)
+    sp = self.plan_for(max(self._plans.keys(), default=1))
     for n in NETS:
       sp.plan.run(sp.marks[f"{n}_bwd_end"], sp.marks[f"{n}_opt_end"], s, False)
     return self._zero_results(False)
@@ -360,7 +433,7 @@ class NativeBackend:
   def _full(self, n: str, t: torch.Tensor) -> torch.Tensor:
     """fp32 master / moments are sharded across ranks on the fused path (ZeRO-1)."""
     if self.fused:
-      return self.symm.gather_sharded(t)
+      return self.symm.gather_sharded(t, n)
     return t
 
   def state_dict(self) -> Dict[str, torch.Tensor]:

@@ -111,14 +111,16 @@ class NetState:
     return dst
 
   def refresh_derived_ops(self, plan, tag: str):
+    # source = the bf16 compute copy: it is complete on every rank, whereas the fp32 master is
+    # only current inside the rank's own optimizer shard on the fused (ZeRO-1) path
     for name, (dst, idx) in self.derived.items():
-      plan.add_gather_bf16(f"{tag}.gather.{name}", dst.data_ptr(), self.w.data_ptr(), idx.data_ptr(),
-                           idx.numel())
+      plan.add_gather_bf16(f"{tag}.gather.{name}", dst.data_ptr(), self.wb.data_ptr(), idx.data_ptr(),
+                           idx.numel(), True)
 
   def refresh_derived_now(self):
     for dst, idx in self.derived.values():
-      src = torch.cat([self.w, self.w.new_zeros(1)])
-      dst.copy_(src[idx.long().clamp_min(-1)].to(torch.bfloat16).view_as(dst))
+      src = torch.cat([self.wb, self.wb.new_zeros(1)])
+      dst.copy_(src[idx.long().clamp_min(-1)].view_as(dst))
 
 
 def fp8_ok(l: ConvLayer) -> bool:
@@ -364,7 +366,8 @@ class NetExec:
   def backward(self, plan, n0: int, nimg: int, wgrad: bool, stop_layer: int = 0,
                input_grad_target: Optional[Tuple[Buf, int]] = None,
                gout_view=None, gout_is_dy: bool = False,
-               lanes: Optional[Tuple[int, int]] = None):
+               lanes: Optional[Tuple[int, int]] = None, join_wgrad: bool = True,
+               on_layer_done=None):
     """Emit the backward pass for images [n0, n0 + nimg).
 
     ``gout_view``: view of the gradient wrt the network output (default: self.gout_final).
@@ -375,7 +378,9 @@ class NetExec:
     has no dgrad. Layers below ``stop_layer`` are skipped entirely.
     ``lanes``: (main lane, wgrad lane): weight-gradient GEMMs are issued on their own stream —
     nothing downstream of a layer depends on its wgrad — so they fill the tail waves of the
-    dgrad / normalisation chain; the caller joins the wgrad lane before the optimizer."""
+    dgrad / normalisation chain; the caller joins the wgrad lane before the optimizer.
+    ``on_layer_done(j)``: called after every op that writes layer j's parameter gradients has
+    been emitted (layers are visited last to first): hook for bucketed gradient all-reduce."""
     main_lane, wg_lane = lanes if lanes is not None else (None, None)
     self.enable_backward()
     st = self.st
@@ -383,7 +388,11 @@ class NetExec:
     g1 = (gout_view if gout_view is not None else self.gout_final.view(n0), 0)
     g2 = NULL_VIEW
     pending_skip = None
+    prev_j = None
     for j in range(L - 1, stop_layer - 1, -1):
+      if prev_j is not None and on_layer_done is not None:
+        on_layer_done(prev_j)
+      prev_j = j
       l = self.layers[j]
       hi, wi = self.in_hw[j]
       ho, wo = self.out_hw[j]
@@ -444,7 +453,9 @@ class NetExec:
         if l.res == "a" and pending_skip is not None:
           g2 = pending_skip
           pending_skip = None
-    if wgrad and wg_lane is not None:
+    if prev_j is not None and on_layer_done is not None:
+      on_layer_done(prev_j)
+    if wgrad and wg_lane is not None and join_wgrad:
       ev = plan.add_event_record(f"sync.rec.{self.tag}.wgrad_done", wg_lane)
       plan.add_event_wait(f"sync.wait.{self.tag}.wgrad_done", main_lane, ev)
 

@@ -14,7 +14,7 @@ launches issued per step by the reference's ``optimizer.minimize`` calls
 from __future__ import annotations
 
 import os
-from typing import Dict, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -37,6 +37,7 @@ class SymmetricBuffers:
     if symm_mem.get_signal_pad_size() < need:
       symm_mem.set_signal_pad_size(max(need, 16384))
     self.handles: Dict[str, Tuple[object, object]] = {}
+    self.buckets: Dict[str, List[Tuple[int, int]]] = {}
     self.use_multicast = os.environ.get("B2_NVLS", "auto")
 
   def alloc(self, name: str, numel: int):
@@ -63,24 +64,59 @@ class SymmetricBuffers:
       return 0, 0
     return mg, mw
 
-  def emit_allreduce_adam(self, plan, name: str, st, lr: float, b1: float, b2: float, eps: float):
+  def set_buckets(self, name: str, bounds):
+    """Split network ``name``'s flat buffer into all-reduce buckets [lo, hi) (multiples of 8
+    elements, ascending, covering [0, n)). Every bucket is reduced / updated by its own kernel
+    launch as soon as its gradients are final, and is sharded over the ranks on its own — so the
+    optimizer-state ownership map (ZeRO-1) is per bucket: see :meth:`owned_ranges`."""
+    bounds = [(int(lo), int(hi)) for lo, hi in bounds]
+    assert all(lo % 8 == 0 and hi % 8 == 0 and lo < hi for lo, hi in bounds), bounds
+    assert bounds[0][0] == 0 and all(a[1] == b[0] for a, b in zip(bounds, bounds[1:])), bounds
+    self.buckets[name] = bounds
+
+  def bucket_list(self, name: str, n: int):
+    return self.buckets.get(name) or [(0, n)]
+
+  def emit_allreduce_adam(self, plan, name: str, st, lr: float, b1: float, b2: float, eps: float,
+                          bucket: Optional[int] = None):
+    """One fused reduce + Adam + broadcast launch over the whole buffer (``bucket`` None: all
+    buckets, back to back) or over one bucket (pointers offset to the bucket start)."""
     hg, hw = self.handles[name]
     mg, mw = self.multicast_ptrs(name)
-    plan.add_allreduce_adam(f"opt.{name}.fused_allreduce_adam", [int(p) for p in hg.buffer_ptrs],
-                            [int(p) for p in hw.buffer_ptrs], [int(p) for p in hg.signal_pad_ptrs],
-                            st.w.data_ptr(), st.m.data_ptr(), st.v.data_ptr(), st.step.data_ptr(),
-                            lr, b1, b2, eps, st.n, self.rank, self.world, NUM_BLOCKS, mg, mw)
+    todo = self.bucket_list(name, st.n)
+    if bucket is not None:
+      todo = [todo[bucket]]
+    for lo, hi in todo:
+      plan.add_allreduce_adam(f"opt.{name}.fused_allreduce_adam[{lo}:{hi}]",
+                              [int(p) + 4 * lo for p in hg.buffer_ptrs],
+                              [int(p) + 2 * lo for p in hw.buffer_ptrs], [int(p) for p in hg.signal_pad_ptrs],
+                              st.w.data_ptr() + 4 * lo, st.m.data_ptr() + 4 * lo, st.v.data_ptr() + 4 * lo,
+                              st.step.data_ptr(), lr, b1, b2, eps, hi - lo, self.rank, self.world,
+                              NUM_BLOCKS, mg + 4 * lo if mg else 0, mw + 2 * lo if mw else 0)
 
-  def shard_bounds(self, n: int) -> Tuple[int, int]:
+  def shard_bounds(self, n: int, rank: Optional[int] = None) -> Tuple[int, int]:
+    """This rank's shard of a buffer (or bucket) of n elements — mirrors the kernel."""
+    rank = self.rank if rank is None else rank
     n8 = n // 8
     per = (n8 + self.world - 1) // self.world
-    lo = min(n8, per * self.rank)
+    lo = min(n8, per * rank)
     return lo * 8, min(n8, lo + per) * 8
 
-  def gather_sharded(self, t: torch.Tensor) -> torch.Tensor:
+  def owned_ranges(self, name: str, n: int):
+    """[lo, hi) ranges of network ``name``'s flat buffers whose fp32 master / moments live on
+    this rank: its shard of every bucket."""
+    out = []
+    for lo, hi in self.bucket_list(name, n):
+      a, b = self.shard_bounds(hi - lo)
+      if b > a:
+        out.append((lo + a, lo + b))
+    return out
+
+  def gather_sharded(self, t: torch.Tensor, name: Optional[str] = None) -> torch.Tensor:
     """Assemble a full tensor from the per-rank live shards (ZeRO-1 layout)."""
-    lo, hi = self.shard_bounds(t.numel())
     full = torch.zeros_like(t)
-    full[lo:hi] = t[lo:hi]
+    ranges = self.owned_ranges(name, t.numel()) if name is not None else [self.shard_bounds(t.numel())]
+    for lo, hi in ranges:
+      full[lo:hi] = t[lo:hi]
     self.strategy.all_reduce_sum(full)
     return full

@@ -4,8 +4,8 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 NG=$(python -c "import torch; print(torch.cuda.device_count())")
 echo "gpus=$NG"
-timeout 600 python -m pytest tests/test_fused_allreduce.py -m gpu -x -q -s > gpurun_out/pytest_ar_w$NG.log 2>&1; tail -4 gpurun_out/pytest_ar_w$NG.log
-for n in 1 2 4 8; do
+timeout 600 python -m pytest tests/test_fused_allreduce.py tests/test_native_dp.py -m gpu -x -q -s > gpurun_out/pytest_ar_w$NG.log 2>&1; tail -4 gpurun_out/pytest_ar_w$NG.log
+for n in ${SCALE_NS:-1 2 4 8}; do
   [ $n -le $NG ] || continue
   if [ $n -eq 1 ]; then
     timeout 300 python bench.py --gpus 1 --steps 15 --warmup 4 > gpurun_out/scale_n$n.json 2> gpurun_out/scale_n$n.err
@@ -17,7 +17,7 @@ done
 # NCCL baseline path for comparison at full width
 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29650 bench.py --gpus $NG --steps 15 --warmup 4 --fused_allreduce off --no_e2e > gpurun_out/scale_n${NG}_nccl.json 2> gpurun_out/scale_nccl.err
 grep '"metric"' gpurun_out/scale_n${NG}_nccl.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('NCCL path N=%d %.1f img/s %.2f ms' % (d['n_gpus'], d['value'], d['ms_per_step']))" || tail -3 gpurun_out/scale_nccl.err
-for w in 2 8; do
+for w in ${SWEEP_WS:-2 8}; do
   [ $w -le $NG ] || continue
   timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $w --master-addr 127.0.0.1 --master-port $((29700+w)) tools/allreduce_bench.py > gpurun_out/sweep_w$w.log 2>&1
   python - <<PY
