@@ -111,3 +111,61 @@ def test_allreduce_buckets_and_ownership(monkeypatch):
         for lo, hi in sb.owned_ranges(n, st.n):
           owners[lo:hi] += 1
       assert int(owners.min()) == 1 and int(owners.max()) == 1
+
+
+def test_bucketed_allreduce_plan_order(monkeypatch):
+  """Fused data-parallel plan (stub peer memory): every bucket's reduce + Adam launch sits on the
+  wgrad lane, after the wgrad GEMMs of all layers inside the bucket and after an event recorded on
+  the main lane once the bucket's lowest layer is done; buckets run in backward order and the
+  per-step tail (step counter, derived weights) follows the last bucket."""
+  fake_native.install(monkeypatch)
+  monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+  from tf2_cyclegan_b200.engine.cyclegan import build_specs
+  from tf2_cyclegan_b200.engine.native_backend import NETS, NativeBackend
+  from tf2_cyclegan_b200.parallel.strategy import Strategy
+  be = NativeBackend(build_specs(A(3)), 2, Strategy(device="cpu"), seed=1, image_size=128, local_batch=2)
+
+  class Symm:
+    def emit_allreduce_adam(self, plan, n, st, bucket=None, **kw):
+      plan.add_memset(f"opt.{n}.AR.b{bucket}", st.g.data_ptr(), 16)
+
+  be.fused, be.symm = True, Symm()
+  for n in NETS:
+    be.buckets[n] = be.plan_buckets(n)
+    be.bucket_index[n] = list(range(len(be.buckets[n])))
+  lanes = []
+  import tests.fake_native as fn
+  plan_cls = next(v for v in vars(fn).values() if isinstance(v, type) and hasattr(v, "_add"))
+  orig = plan_cls._add
+
+  def _add(self, kind, name, *args):
+    lanes.append(getattr(self, "lane", 0))
+    return orig(self, kind, name, *args)
+
+  monkeypatch.setattr(plan_cls, "_add", _add)
+  sp = be.plan_for(2)
+  names = sp.names
+  assert len(lanes) == len(names)
+  pos = {nm: i for i, nm in enumerate(names)}
+  for n, main_lane, wg_lane in (("G", 0, 2), ("Y", 0, 2), ("F", 1, 3), ("X", 1, 3)):
+    layers = be.specs[n].layers
+    ars = [i for i, nm in enumerate(names) if nm.startswith(f"opt.{n}.AR.b")]
+    assert len(ars) == len(be.buckets[n]) and ars == sorted(ars)
+    assert [names[i] for i in ars] == [f"opt.{n}.AR.b{k}" for k in range(len(ars))]   # backward order
+    for k, i in enumerate(ars):
+      assert lanes[i] == wg_lane
+      first_layer = be.buckets[n][k][0]
+      last_layer = be.buckets[n][k - 1][0] - 1 if k else len(layers) - 1
+      # the wait just before the mask op pairs with a record on the main lane
+      w = max(j for j in range(i) if names[j].startswith(f"sync.wait.{n}.bucket{k}"))
+      r = pos[f"sync.rec.{n}.bucket{k}"]
+      assert r < w < i and lanes[r] == main_lane and lanes[w] == wg_lane
+      for j in range(first_layer, last_layer + 1):
+        grads = [q for q, nm in enumerate(names)
+                 if nm.startswith(f"{n}.{layers[j].name}.") and ("wgrad" in nm or ".bwd[" in nm or "in_bwd_apply" in nm
+                                                                  or "act_bwd" in nm)
+                 and q > sp.marks["test_end"] and f"[0:{2 * (3 if n in 'GF' else 2)}]" in nm]
+        assert grads and max(grads) < i, (n, k, layers[j].name)
+        assert all(q < r or lanes[q] == wg_lane for q in grads), (n, k, layers[j].name)
+    tail = pos[f"opt.{n}.step"]
+    assert tail > ars[-1] and lanes[tail] == wg_lane
