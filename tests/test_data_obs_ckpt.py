@@ -137,3 +137,24 @@ def test_append_dict():
   assert d == {"a": [1, 2]}
   append_dict(d, {"a": 3}, replace=True)
   assert d == {"a": 3}
+
+
+def test_prefetch_iterator_abandoned_early_exits_cleanly(tmp_path):
+  """A consumer that stops iterating a prefetching dataset early (exception in the training loop,
+  a benchmark that takes K batches) must not leave an un-joined worker thread behind: that
+  aborts the interpreter at exit ("terminate called without an active exception")."""
+  import subprocess
+  import sys
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  code = (
+      "import torch\n"
+      "from tf2_cyclegan_b200.data.pipeline import PairedBatches\n"
+      "from tf2_cyclegan_b200.parallel.strategy import Strategy\n"
+      "a = torch.rand(14, 8, 8, 3); b = a.flip(0).contiguous()\n"
+      "it = iter(PairedBatches(a, b, 2, Strategy(device='cpu'), distribute=False, prefetch=2))\n"
+      "x, y = next(it); x, y = next(it)\n"
+      "assert torch.equal(x, a[2:4])\n"
+      "print('done')\n")
+  r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120,
+                     env=dict(os.environ, PYTHONPATH=root))
+  assert r.returncode == 0 and "done" in r.stdout, (r.returncode, r.stderr[-500:])

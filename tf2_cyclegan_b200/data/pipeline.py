@@ -19,6 +19,7 @@ device on a side stream (the B200 counterpart of MultiDeviceIterator).
 """
 from __future__ import annotations
 
+import atexit
 import os
 import threading
 import queue
@@ -133,6 +134,20 @@ def tf_shuffle_order(n: int, buffer_size: int, rng: np.random.Generator) -> List
 
 
 # ----------------------------------------------------------------- datasets
+_LIVE_WORKERS: set = set()   # (stop event, thread) of prefetch workers whose consumer is still open
+
+
+@atexit.register
+def _join_prefetch_workers():
+  """Iterators that are still open when the interpreter exits (a consumer that stopped early)
+  must not leave their worker thread un-joined."""
+  for stop, t in list(_LIVE_WORKERS):
+    stop.set()
+  for stop, t in list(_LIVE_WORKERS):
+    t.join(timeout=10)
+  _LIVE_WORKERS.clear()
+
+
 class PairedBatches:
   """zip(A.batch(gbs), B.batch(gbs)) restricted to this replica's share."""
 
@@ -218,6 +233,16 @@ class PairedBatches:
     q: "queue.Queue" = queue.Queue(maxsize=self.prefetch)
     dev = self.strategy.device
     stream = torch.cuda.Stream(device=dev) if dev.type == "cuda" and self.to_device else None
+    stop = threading.Event()
+
+    def put(item) -> bool:
+      while not stop.is_set():
+        try:
+          q.put(item, timeout=0.1)
+          return True
+        except queue.Full:
+          continue
+      return False
 
     def worker():
       try:
@@ -230,28 +255,38 @@ class PairedBatches:
             if not hasattr(self, "_slot_events"):
               self._slot_events = {}
             self._slot_events[self._slot] = ev
-            q.put((xd, yd, ev))
+            ok = put((xd, yd, ev))
           else:
-            q.put((x, y, None))
+            ok = put((x, y, None))
+          if not ok:
+            return
       except BaseException as e:  # surface worker errors in the consumer
-        q.put(e)
-      q.put(None)
+        put(e)
+      put(None)
 
     t = threading.Thread(target=worker, daemon=True)
     t.start()
-    while True:
-      item = q.get()
-      if item is None:
-        break
-      if isinstance(item, BaseException):
-        raise item
-      x, y, ev = item
-      if ev is not None:
-        torch.cuda.current_stream(dev).wait_event(ev)
-        x.record_stream(torch.cuda.current_stream(dev))
-        y.record_stream(torch.cuda.current_stream(dev))
-      yield x, y
-    t.join()
+    _LIVE_WORKERS.add((stop, t))
+    try:
+      while True:
+        item = q.get()
+        if item is None:
+          break
+        if isinstance(item, BaseException):
+          raise item
+        x, y, ev = item
+        if ev is not None:
+          torch.cuda.current_stream(dev).wait_event(ev)
+          x.record_stream(torch.cuda.current_stream(dev))
+          y.record_stream(torch.cuda.current_stream(dev))
+        yield x, y
+    finally:
+      # also runs when the consumer stops early (generator closed / garbage collected): the
+      # prefetch thread must be joined, an un-joined thread that used the intra-op pool aborts
+      # the interpreter at exit
+      stop.set()
+      t.join(timeout=10)
+      _LIVE_WORKERS.discard((stop, t))
 
 
 def _materialise_native(source, split: str, n: int, rng: Optional[np.random.Generator],
