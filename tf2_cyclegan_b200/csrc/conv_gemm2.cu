@@ -9,6 +9,13 @@
 // LEADER's full barrier (peer-bit-cleared mbarrier address, cta_group::2 TMA); the leader's MMA
 // thread commits with multicast to BOTH CTAs' empty / tmem-full barriers; epilogue threads of
 // both CTAs arrive on the leader's tmem-empty barrier; TMEM is allocated with cta_group::2.
+//
+// Warp roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA only), warp 2 =
+// TMEM allocator, warps 4-7 and 8-11 = two epilogue warpgroups, each draining half of the
+// accumulator columns (TMEM lane quarter = warp % 4). The producer / MMA loops are executed by
+// the whole warp with only the issue instructions under elect.sync: inside an `if (lane == 0)`
+// region the compiler wraps every uniform operand of UTMALDG / UTCHMMA in an
+// ELECT / R2UR.BROADCAST / BRA.U.ANY loop and the single issuing thread becomes the bottleneck.
 #include <cuda_runtime.h>
 
 #include "conv_epilogue.cuh"
