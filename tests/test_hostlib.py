@@ -58,3 +58,23 @@ def test_gather_rows():
   dst = torch.empty(5, 5, 7, 3)
   assert hostlib.gather_rows(dst, src, idx)
   assert torch.equal(dst, src[idx])
+
+
+def test_pipeline_without_native_library_matches(monkeypatch):
+  """Installs without csrc/_host.so use the PyTorch / Python paths: same datasets, same batches."""
+  import types
+  from tf2_cyclegan_b200.parallel.strategy import Strategy
+
+  def datasets():
+    args = types.SimpleNamespace(image_size=32, synthetic_size=6, seed=7, global_batch_size=2, data_dir=None)
+    tr, te, pl = P.get_datasets(args, Strategy(device="cpu"))
+    return [torch.cat([x, y]) for x, y in tr], [torch.cat([x, y]) for x, y in te]
+
+  with_lib = datasets()
+  monkeypatch.setattr(hostlib, "_tried", True)
+  monkeypatch.setattr(hostlib, "_lib", None)
+  assert not hostlib.available()
+  without = datasets()
+  for a, b in zip(with_lib[0] + with_lib[1], without[0] + without[1]):
+    assert a.shape == b.shape and (a - b).abs().max() < 1e-4
+  assert hostlib.crc32c(b"123456789") == 0xE3069283
