@@ -220,9 +220,14 @@ def test_overlapped_stride_stem():
   assert rel_err(out.t, ref) < 1e-2
 
 
-def test_in_apply_and_backward_match_autograd():
+@pytest.mark.parametrize("variant", [0] + ([1, 2, 3] if __import__("os").environ.get("B2_TEST_EW_VARIANTS") == "1" else []))
+def test_in_apply_and_backward_match_autograd(variant, request):
+  """variant: tuning variants of the InstanceNorm kernels (same arithmetic); only the default runs
+  unless B2_TEST_EW_VARIANTS=1."""
   nv, no, O = _mods()
   C = nv.load()
+  C.set_ew_variant(variant)
+  request.addfinalizer(lambda: C.set_ew_variant(0))
   torch.manual_seed(7)
   n, h, c = 2, 16, 64
   x = bf(torch.randn(n, h, h, c, device="cuda") * 2 + 0.5).requires_grad_(True)

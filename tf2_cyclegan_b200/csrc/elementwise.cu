@@ -90,7 +90,10 @@ __device__ __forceinline__ void gather_g(const View& g1, int fold, const View& g
 // ------------------------------------------------------------------ in_apply
 // grid: (pixel chunks, N). A thread owns one 8-channel group (coefficients live in
 // registers) and walks pixels, 4 at a time so that several 16-byte loads are in flight.
-__global__ void __launch_bounds__(kThreads, 4) in_apply_kernel(const InApplyParams p, int pix_per_block) {
+// U = pixels in flight per thread, MINB = resident blocks per SM the register budget is set for
+// (variants are selected at run time, see ew_variant(); <4, 4> is the default)
+template <int U, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) in_apply_kernel(const InApplyParams p, int pix_per_block) {
   const int c8 = p.C >> 3;
   const int lanes = kThreads / c8;
   const int c = (threadIdx.x % c8) * 8;
@@ -120,7 +123,6 @@ __global__ void __launch_bounds__(kThreads, 4) in_apply_kernel(const InApplyPara
   const bool has8 = p.dst8.p != nullptr;
   const float s8 = has8 ? __ldg(p.scale8) : 1.f;
   float amax = 0.f;
-  constexpr int U = 4;
   int hh[U], ww[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {   // one division per slot, then incremental (h, w) updates
@@ -206,8 +208,9 @@ __global__ void __launch_bounds__(kThreads, 4) in_apply_kernel(const InApplyPara
 
 // ------------------------------------------------------------ in_bwd_reduce
 // grid: (pixel chunks, N). Threads: (C/8 channel groups) x (256 / (C/8) pixel lanes).
-__global__ void __launch_bounds__(kThreads, 3) in_bwd_reduce_kernel(const InBwdReduceParams p,
-                                                                 int pix_per_block) {
+template <int U, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) in_bwd_reduce_kernel(const InBwdReduceParams p,
+                                                                    int pix_per_block) {
   extern __shared__ float red[];   // [lanes][C][2]
   const int c8 = p.C >> 3;
   const int lanes = kThreads / c8;
@@ -236,7 +239,6 @@ __global__ void __launch_bounds__(kThreads, 3) in_bwd_reduce_kernel(const InBwdR
 
   const bool has_g2 = p.g2.p != nullptr;
   const float slope = act_slope(p.act);
-  constexpr int U = 2;
   int hh[U], ww[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
@@ -332,7 +334,8 @@ __global__ void __launch_bounds__(kThreads, 3) in_bwd_reduce_kernel(const InBwdR
 
 // ------------------------------------------------------------- in_bwd_apply
 // dx = A*dy + B*x + C per channel (A = gamma*rstd, B = -gamma*rstd^2*m2, C = gamma*rstd*(mean*rstd*m2 - m1))
-__global__ void __launch_bounds__(kThreads, 4) in_bwd_apply_kernel(const InBwdApplyParams p, int pix_per_block) {
+template <int U, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) in_bwd_apply_kernel(const InBwdApplyParams p, int pix_per_block) {
   const int c8 = p.C >> 3;
   const int lanes = kThreads / c8;
   const int c = (threadIdx.x % c8) * 8;
@@ -367,7 +370,6 @@ __global__ void __launch_bounds__(kThreads, 4) in_bwd_apply_kernel(const InBwdAp
     abc[(ch & 7) * c8 + (ch >> 3)] = make_float4(gr, -gr * rstd * m2, gr * (mean * rstd * m2 - m1), 0.f);
   }
   __syncthreads();
-  constexpr int U = 4;
   int hh[U], ww[U];
 #pragma unroll
   for (int u = 0; u < U; ++u) {
@@ -409,6 +411,95 @@ __global__ void __launch_bounds__(kThreads, 4) in_bwd_apply_kernel(const InBwdAp
       ww[u] += step_w;
       if (ww[u] >= p.W) { ww[u] -= p.W; ++hh[u]; }
     }
+  }
+}
+
+// Register double-buffered variant of in_bwd_apply (experiment, ew_variant() == 3): the loads of the
+// next U pixels are issued before the current U are consumed, so a thread always has loads in
+// flight while it computes. Same arithmetic as in_bwd_apply_kernel.
+template <int U, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) in_bwd_apply_pf_kernel(const InBwdApplyParams p, int pix_per_block) {
+  const int c8 = p.C >> 3;
+  const int lanes = kThreads / c8;
+  const int c = (threadIdx.x % c8) * 8;
+  const int ln = threadIdx.x / c8;
+  const int n = blockIdx.y;
+  const int HW = p.H * p.W;
+  const int pix0 = blockIdx.x * pix_per_block;
+  const int pix1 = min(HW, pix0 + pix_per_block);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && p.dgamma != nullptr) {
+    for (int cc = threadIdx.x; cc < p.C; cc += blockDim.x) {
+      float dg = 0.f, db = 0.f;
+      for (int nn = 0; nn < p.N; ++nn) {
+        const float* bs = p.bstats + (static_cast<long long>(nn) * p.C + cc) * 2;
+        db += bs[0];
+        dg += bs[1];
+      }
+      p.dgamma[cc] += dg;
+      p.dbeta[cc] += db;
+    }
+  }
+  extern __shared__ float coef[];   // float4[C] = (A, B, C, -)
+  float4* abc = reinterpret_cast<float4*>(coef);
+  for (int ch = threadIdx.x; ch < p.C; ch += kThreads) {
+    const float* st = p.stats + (static_cast<long long>(n) * p.C + ch) * 2;
+    const float* bs = p.bstats + (static_cast<long long>(n) * p.C + ch) * 2;
+    const float mean = st[0] * p.inv_count;
+    const float var = fmaxf(st[1] * p.inv_count - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + p.eps);
+    const float m1 = bs[0] * p.inv_count;
+    const float m2 = bs[1] * p.inv_count;
+    const float gr = __ldg(p.gamma + ch) * rstd;
+    abc[(ch & 7) * c8 + (ch >> 3)] = make_float4(gr, -gr * rstd * m2, gr * (mean * rstd * m2 - m1), 0.f);
+  }
+  __syncthreads();
+  const int step = lanes * U;
+  const int step2 = 2 * step;
+  const int s2h = step2 / p.W, s2w = step2 - s2h * p.W;
+  int hA[U], wA[U], hB[U], wB[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int pa = pix0 + ln + u * lanes, pb = pa + step;
+    hA[u] = pa / p.W; wA[u] = pa - hA[u] * p.W;
+    hB[u] = pb / p.W; wB[u] = pb - hB[u] * p.W;
+  }
+  uint4 dA[U], xA[U], dB[U], xB[U];
+  auto load = [&](uint4 (&dv)[U], uint4 (&xv)[U], const int (&hh)[U], const int (&ww)[U], int base) {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (base + u * lanes < pix1) {
+        dv[u] = __ldg(reinterpret_cast<const uint4*>(vptr(p.dy, n, hh[u], ww[u]) + c));
+        xv[u] = __ldg(reinterpret_cast<const uint4*>(vptr(p.x, n, hh[u], ww[u]) + c));
+      }
+  };
+  auto consume = [&](const uint4 (&dv)[U], const uint4 (&xv)[U], int (&hh)[U], int (&ww)[U], int base) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (base + u * lanes < pix1) {
+        const uint32_t dw[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+        const uint32_t xw[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 d = unpack_bf16x2(dw[j]);
+          const float2 x = unpack_bf16x2(xw[j]);
+          const float4 k0 = abc[(2 * j) * c8 + (c >> 3)], k1 = abc[(2 * j + 1) * c8 + (c >> 3)];
+          ow[j] = pack_bf16x2(fmaf(k0.x, d.x, fmaf(k0.y, x.x, k0.z)), fmaf(k1.x, d.y, fmaf(k1.y, x.y, k1.z)));
+        }
+        *reinterpret_cast<uint4*>(vptr_mut(p.dx, n, hh[u], ww[u]) + c) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      }
+      hh[u] += s2h;                       // this buffer is next used 2 * step pixels further on
+      ww[u] += s2w;
+      if (ww[u] >= p.W) { ww[u] -= p.W; ++hh[u]; }
+    }
+  };
+  int base = pix0 + ln;
+  load(dA, xA, hA, wA, base);
+  for (; base < pix1; base += step2) {
+    load(dB, xB, hB, wB, base + step);
+    consume(dA, xA, hA, wA, base);
+    load(dA, xA, hA, wA, base + step2);
+    consume(dB, xB, hB, wB, base + step);
   }
 }
 
@@ -773,30 +864,67 @@ static int pick_pix_per_block(int HW, int N, int lanes, int blocks_per_sm) {
   return ppb > HW ? HW : ppb;
 }
 
-void launch_in_apply(const InApplyParams& p, cudaStream_t s) {
+// Tuning variants of the three InstanceNorm kernels (pixels in flight per thread / resident blocks
+// per SM / register double buffering); 0 = default. Same arithmetic in every variant.
+static int g_ew_variant = -1;
+int ew_variant() {
+  if (g_ew_variant < 0) g_ew_variant = ew_env("B2_EW_VARIANT", 0);
+  return g_ew_variant;
+}
+void set_ew_variant(int v) { g_ew_variant = v < 0 ? 0 : v; }
+
+template <int U, int MINB>
+static void launch_in_apply_t(const InApplyParams& p, cudaStream_t s) {
   const int HW = p.H * p.W;
   const int lanes = kThreads / (p.C / 8);
-  const int ppb = pick_pix_per_block(HW, p.N, lanes, 4);
+  const int ppb = pick_pix_per_block(HW, p.N, lanes, MINB);
   dim3 grid((HW + ppb - 1) / ppb, p.N);
-  in_apply_kernel<<<grid, kThreads, 2 * p.C * sizeof(float), s>>>(p, ppb);
+  in_apply_kernel<U, MINB><<<grid, kThreads, 2 * p.C * sizeof(float), s>>>(p, ppb);
+}
+void launch_in_apply(const InApplyParams& p, cudaStream_t s) {
+  switch (ew_variant()) {
+    case 1: return launch_in_apply_t<2, 6>(p, s);
+    case 2: return launch_in_apply_t<8, 3>(p, s);
+    case 3: return launch_in_apply_t<4, 3>(p, s);
+    default: return launch_in_apply_t<4, 4>(p, s);
+  }
 }
 
-void launch_in_bwd_reduce(const InBwdReduceParams& p, cudaStream_t s) {
+template <int U, int MINB>
+static void launch_in_bwd_reduce_t(const InBwdReduceParams& p, cudaStream_t s) {
   const int HW = p.H * p.W;
   const int c8 = p.C / 8;
   const int lanes = kThreads / c8;
-  const int pix_per_block = pick_pix_per_block(HW, p.N, lanes, 3);
+  const int pix_per_block = pick_pix_per_block(HW, p.N, lanes, MINB);
   dim3 grid((HW + pix_per_block - 1) / pix_per_block, p.N);
   const size_t smem = (static_cast<size_t>(lanes) * p.C * 2 + 4 * p.C) * sizeof(float);
-  in_bwd_reduce_kernel<<<grid, kThreads, smem, s>>>(p, pix_per_block);
+  in_bwd_reduce_kernel<U, MINB><<<grid, kThreads, smem, s>>>(p, pix_per_block);
+}
+void launch_in_bwd_reduce(const InBwdReduceParams& p, cudaStream_t s) {
+  switch (ew_variant()) {
+    case 1: return launch_in_bwd_reduce_t<4, 2>(p, s);
+    case 2: return launch_in_bwd_reduce_t<2, 4>(p, s);
+    case 3: return launch_in_bwd_reduce_t<2, 2>(p, s);
+    default: return launch_in_bwd_reduce_t<2, 3>(p, s);
+  }
 }
 
-void launch_in_bwd_apply(const InBwdApplyParams& p, cudaStream_t s) {
+template <int U, int MINB, bool PF>
+static void launch_in_bwd_apply_t(const InBwdApplyParams& p, cudaStream_t s) {
   const int HW = p.H * p.W;
   const int lanes = kThreads / (p.C / 8);
-  const int ppb = pick_pix_per_block(HW, p.N, lanes, 4);
+  const int ppb = pick_pix_per_block(HW, p.N, lanes, MINB);
   dim3 grid((HW + ppb - 1) / ppb, p.N);
-  in_bwd_apply_kernel<<<grid, kThreads, 4 * p.C * sizeof(float), s>>>(p, ppb);
+  if constexpr (PF) in_bwd_apply_pf_kernel<U, MINB><<<grid, kThreads, 4 * p.C * sizeof(float), s>>>(p, ppb);
+  else in_bwd_apply_kernel<U, MINB><<<grid, kThreads, 4 * p.C * sizeof(float), s>>>(p, ppb);
+}
+void launch_in_bwd_apply(const InBwdApplyParams& p, cudaStream_t s) {
+  switch (ew_variant()) {
+    case 1: return launch_in_bwd_apply_t<2, 6, false>(p, s);
+    case 2: return launch_in_bwd_apply_t<8, 3, false>(p, s);
+    case 3: return launch_in_bwd_apply_t<2, 4, true>(p, s);
+    default: return launch_in_bwd_apply_t<4, 4, false>(p, s);
+  }
 }
 
 void launch_act_bwd(const ActBwdParams& p, cudaStream_t s) {

@@ -490,6 +490,8 @@ PYBIND11_MODULE(_C, m) {
   m.doc() = "b200-cyclegan native runtime (sm_100a kernels + plan executor)";
   m.def("encode_tmap", &encode_tmap, py::arg("ptr"), py::arg("dtype"), py::arg("dims"),
         py::arg("strides_bytes"), py::arg("box"), py::arg("swizzle") = 3);
+  m.def("set_ew_variant", &b2::set_ew_variant, "tuning variant of the InstanceNorm kernels (0 = default)");
+  m.def("ew_variant", &b2::ew_variant);
   m.def("shift_probe", [](py::bytes a, py::bytes b, uint64_t out) {
     b2::launch_shift_probe(tmap_from(a), tmap_from(b), P<float>(out), nullptr);
     check(cudaDeviceSynchronize(), "shift_probe");

@@ -8,8 +8,14 @@ from tf2_cyclegan_b200.ops import native as nv
 ap = argparse.ArgumentParser()
 ap.add_argument("--images", type=int, default=12)
 ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--variant", type=int, default=None,
+                help="tuning variant of the InstanceNorm kernels (csrc/elementwise.cu: U / blocks per SM / "
+                     "register double buffering); default: B2_EW_VARIANT or 0. Sweep: for v in 0 1 2 3")
 a = ap.parse_args()
 C = nv.load()
+if a.variant is not None:
+  C.set_ew_variant(a.variant)
+print(f"B2_EW_VARIANT={C.ew_variant()}")
 n, h, c = a.images, 64, 256
 hbm = 6572.9
 try:
