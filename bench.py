@@ -26,7 +26,6 @@ import json
 import os
 import sys
 import threading
-import time
 import types
 
 ROOT = os.path.dirname(os.path.abspath(__file__))

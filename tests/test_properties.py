@@ -1,7 +1,5 @@
 """Property-based (hypothesis) tests of the pure-logic pieces: container encodings, checksums,
 TF-SAME geometry, the shuffle-buffer order and the wave-aware split-K chooser."""
-import os
-
 import numpy as np
 import torch
 from hypothesis import given, settings, strategies as st

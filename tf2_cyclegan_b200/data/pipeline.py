@@ -24,7 +24,7 @@ import os
 import threading
 import queue
 from math import ceil
-from typing import Callable, Iterator, List, Optional, Sequence, Tuple
+from typing import Callable, Iterator, List, Optional, Tuple
 
 import numpy as np
 import torch

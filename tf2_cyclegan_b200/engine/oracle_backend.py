@@ -10,7 +10,7 @@ ATen/cuDNN — which is also what the stand-in baseline in ``baseline/`` measure
 from __future__ import annotations
 
 from collections import OrderedDict
-from typing import Dict, Optional, Tuple
+from typing import Dict
 
 import torch
 

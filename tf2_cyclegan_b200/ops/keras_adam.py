@@ -11,7 +11,7 @@ eps 1e-7 (Keras default). This is the oracle for the fused reduce+Adam kernel.
 from __future__ import annotations
 
 import math
-from typing import Dict, Iterable, List
+from typing import Dict
 
 import torch
 

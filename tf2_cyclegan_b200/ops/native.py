@@ -10,7 +10,7 @@ from __future__ import annotations
 import importlib.util
 import os
 import sys
-from typing import List, Optional, Sequence, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 

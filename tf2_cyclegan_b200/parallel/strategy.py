@@ -18,7 +18,7 @@ from __future__ import annotations
 
 import datetime
 import os
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, Optional, Sequence
 
 import torch
 import torch.distributed as dist

@@ -6,7 +6,7 @@ wspace 0.02 — reproduced here as a 1080×390 RGBA canvas.
 """
 from __future__ import annotations
 
-from typing import List, Sequence
+from typing import Sequence
 
 import numpy as np
 
