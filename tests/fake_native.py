@@ -78,11 +78,6 @@ class FakePlan:
     assert dw % 16 == 0 and ldw % 4 == 0
     return self._add("wgrad", name, len(taps), cin, cout)
 
-  def add_wgrad_row(self, name, dy_map, a_map, tiles_w, H, nimg, cin, cout, dw, ldw, ksplit):
-    assert decode(dy_map)["box"] == [64, 64, 1, 1] and decode(a_map)["box"] == [64, 66, 1, 1]
-    assert cin % 128 == 0 and cout % 256 == 0 and ksplit >= 1 and 9 * cin <= ldw
-    return self._add("wgrad", name, 9, cin, cout)
-
   def set_lane(self, lane):
     self.lane = lane
 
@@ -93,11 +88,11 @@ class FakePlan:
     return self._add("join", name)
 
   def add_event_record(self, name, lane):
-    assert 0 <= lane < 4
+    assert 0 <= lane < 5
     return self._add("record", name, lane)
 
   def add_event_wait(self, name, lane, ref):
-    assert 0 <= lane < 4 and self.ops[ref][0] == "record"
+    assert 0 <= lane < 5 and self.ops[ref][0] == "record"
     return self._add("wait", name, lane, ref)
 
   def __getattr__(self, item):

@@ -1,5 +1,7 @@
 """Fused peer-memory all-reduce + Adam kernel vs NCCL all_reduce + Keras-Adam oracle
-(SURVEY §4 'distributed (GPU)'). Needs >= 2 GPUs; skipped otherwise."""
+(SURVEY §4 'distributed (GPU)'): two-shot (ZeRO-1) region, one-shot replicated vector tail (bit-identical
+on every rank), loss-scalar side channel, and a 200-replay CUDA-graph stress of the cross-GPU flag
+protocol with a randomly delayed rank. Needs >= 2 GPUs; skipped otherwise."""
 import os
 import socket
 import subprocess
@@ -11,26 +13,43 @@ import torch
 pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
 
 WORKER = r'''
-import os, sys, torch, torch.distributed as dist
+import os, random, sys, torch, torch.distributed as dist
 sys.path.insert(0, os.environ["B2_ROOT"])
 from tf2_cyclegan_b200.parallel.strategy import Strategy
-from tf2_cyclegan_b200.parallel.fused_allreduce import SymmetricBuffers
+from tf2_cyclegan_b200.parallel.fused_allreduce import NUM_SCALARS, SymmetricBuffers
 from tf2_cyclegan_b200.ops import native as nv
 from tf2_cyclegan_b200.ops.keras_adam import KerasAdam
 st = Strategy(device="cuda")
 C = nv.load()
 sb = SymmetricBuffers(st)
 ok = True
-for n in (1024, 8 * 1000 + 8 * 3, 11_400_000 // 8 * 8):
-  g, wb = sb.alloc(f"t{n}", n)
-  torch.manual_seed(1)                       # identical initial weights on all ranks
-  w0 = torch.randn(n, device="cuda")
-  class S: pass
+stream = torch.cuda.current_stream().cuda_stream
+
+def same_on_all_ranks(t):
+  lo, hi = t.float().clone(), t.float().clone()
+  dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+  return torch.equal(lo, hi)
+
+class S: pass
+def state(n, w0):
   s = S(); s.n = n
   s.w = w0.clone(); s.m = torch.zeros(n, device="cuda"); s.v = torch.zeros(n, device="cuda")
   s.step = torch.zeros(1, dtype=torch.int32, device="cuda")
+  return s
+
+# ---- 1. two-shot (ZeRO-1) region + one-shot (replicated) vector tail + loss-scalar side channel
+for n, tail in ((1024, 0), (8 * 1000 + 8 * 3, 8 * 40), (11_400_000 // 8 * 8, 10_496)):
+  name = f"t{n}"
+  g, wb = sb.alloc(name, n)
+  vec_lo = n - tail
+  if tail:
+    sb.set_buckets(name, [(0, vec_lo)], vec_lo=vec_lo)
+  torch.manual_seed(1)                       # identical initial weights on all ranks
+  w0 = torch.randn(n, device="cuda")
+  s = state(n, w0)
+  wb.copy_(w0.to(torch.bfloat16))
   plan = C.Plan()
-  sb.emit_allreduce_adam(plan, f"t{n}", s, 2e-4, 0.5, 0.9, 1e-7)
+  sb.emit_allreduce_adam(plan, name, s, 2e-4, 0.5, 0.9, 1e-7, scalars=True)
   plan.add_step_increment("inc", s.step.data_ptr())
   ref_w = {"w": w0.clone()}
   opt = KerasAdam()
@@ -38,21 +57,81 @@ for n in (1024, 8 * 1000 + 8 * 3, 11_400_000 // 8 * 8):
     torch.manual_seed(100 + 10 * it + st.rank)   # different local gradients per rank
     gl = torch.randn(n, device="cuda")
     g.copy_(gl)
+    sl = torch.arange(NUM_SCALARS, device="cuda", dtype=torch.float32) * (st.rank + 1) + it
+    sb.scalars.copy_(sl)
     tot = gl.clone(); dist.all_reduce(tot)
+    sl_tot = sl.clone(); dist.all_reduce(sl_tot)
     opt.apply_gradients(ref_w, {"w": tot})
     torch.cuda.synchronize(); dist.barrier()
-    plan.run(0, -1, torch.cuda.current_stream().cuda_stream, False)
+    plan.run(0, -1, stream, False)
     torch.cuda.synchronize(); dist.barrier()
-    full = sb.gather_sharded(s.w)
+    full = sb.gather_sharded(s.w, name)
     e1 = (full - ref_w["w"]).abs().max().item()
     e2 = (wb.float() - ref_w["w"]).abs().max().item()
     gz = g.abs().max().item()
-    if not (e1 < 5e-5 and e2 < 2e-2 and gz == 0.0):   # fp32 sum order differs from NCCL
+    es = (sb.scalars_sum - sl_tot).abs().max().item()
+    if not (e1 < 5e-5 and e2 < 2e-2 and gz == 0.0 and es < 1e-3):   # fp32 sum order differs from NCCL
       ok = False
-      print(f"rank {st.rank} n={n} it={it}: master err {e1}, bf16 err {e2}, grad residue {gz}")
-print(f"rank {st.rank} multicast={sb.multicast_ptrs('t1024')[0] != 0} ok={ok}")
+      print(f"rank {st.rank} n={n} it={it}: master err {e1}, bf16 err {e2}, grad residue {gz}, scalar err {es}")
+    if tail:
+      # the replicated tail: fp32 master, moments and bf16 copy bit-identical on every rank and current
+      for nm, t in (("w", s.w[vec_lo:]), ("m", s.m[vec_lo:]), ("v", s.v[vec_lo:]), ("wb", wb[vec_lo:])):
+        if not same_on_all_ranks(t):
+          ok = False; print(f"rank {st.rank} n={n} it={it}: replicated tail {nm} diverges across ranks")
+      et = (s.w[vec_lo:] - ref_w["w"][vec_lo:]).abs().max().item()
+      if et > 5e-5 or not torch.equal(wb[vec_lo:], s.w[vec_lo:].to(torch.bfloat16)):
+        ok = False; print(f"rank {st.rank} n={n} it={it}: tail master err {et} / stale bf16 tail")
+    if not same_on_all_ranks(wb):
+      ok = False; print(f"rank {st.rank} n={n} it={it}: bf16 replicas diverge")
+
+# ---- 2. flag-protocol stress: 200 CUDA-graph replays of TWO chained launches (two networks sharing the
+# collective lane), a randomly chosen rank delayed by a randomly long spin before each replay
+iters = int(os.environ.get("B2_STRESS_ITERS", "200"))
+nA, nB = 8 * 4096 * 8, 8 * 1024 * 3
+gA, wbA = sb.alloc("sA", nA); gB, wbB = sb.alloc("sB", nB)
+sb.set_buckets("sA", [(0, nA // 2), (nA // 2, nA - 512)], vec_lo=nA - 512)
+torch.manual_seed(2)
+wA0, wB0 = torch.randn(nA, device="cuda"), torch.randn(nB, device="cuda")
+sA, sB = state(nA, wA0), state(nB, wB0)
+plan = C.Plan()
+sb.emit_allreduce_adam(plan, "sA", sA, 2e-4, 0.5, 0.9, 1e-7, bucket=0)
+sb.emit_allreduce_adam(plan, "sB", sB, 2e-4, 0.5, 0.9, 1e-7, scalars=True)
+sb.emit_allreduce_adam(plan, "sA", sA, 2e-4, 0.5, 0.9, 1e-7, bucket=1, vectors=True, exposed=True)
+plan.add_step_increment("incA", sA.step.data_ptr()); plan.add_step_increment("incB", sB.step.data_ptr())
+glA, glB = torch.empty(nA, device="cuda"), torch.empty(nB, device="cuda")
+side = torch.cuda.Stream()
+plan.run(0, -1, stream, False); torch.cuda.synchronize(); dist.barrier()      # lazy init outside capture
+sA.w.copy_(wA0); sA.m.zero_(); sA.v.zero_(); sA.step.zero_()
+sB.w.copy_(wB0); sB.m.zero_(); sB.v.zero_(); sB.step.zero_()
+gA.zero_(); gB.zero_()
+graph = torch.cuda.CUDAGraph()
+with torch.cuda.graph(graph):
+  gA.copy_(glA); gB.copy_(glB)                       # this step's local gradients
+  plan.run(0, -1, torch.cuda.current_stream().cuda_stream, False)
+refA, refB = {"w": wA0.clone()}, {"w": wB0.clone()}
+oA, oB = KerasAdam(), KerasAdam()
+rng = random.Random(7)                               # the same draws on every rank
+for it in range(iters):
+  torch.manual_seed(1000 + 17 * it + st.rank)
+  glA.normal_(); glB.normal_()
+  tA, tB = glA.clone(), glB.clone(); dist.all_reduce(tA); dist.all_reduce(tB)
+  oA.apply_gradients(refA, {"w": tA}); oB.apply_gradients(refB, {"w": tB})
+  slow, cycles = rng.randrange(st.world_size), rng.choice([0, 10_000, 300_000, 3_000_000])
+  if st.rank == slow and cycles:
+    torch.cuda._sleep(cycles)
+  graph.replay()
+torch.cuda.synchronize(); dist.barrier()
+for nm, sx, ref, wbx in (("sA", sA, refA, wbA), ("sB", sB, refB, wbB)):
+  full = sb.gather_sharded(sx.w, nm)
+  e1 = (full - ref["w"]).abs().max().item()
+  e2 = (wbx.float() - ref["w"]).abs().max().item()
+  if not (e1 < 2e-4 and e2 < 2e-2 and same_on_all_ranks(wbx) and int(sx.step.item()) == iters):
+    ok = False; print(f"rank {st.rank} stress {nm}: master err {e1}, bf16 err {e2}, step {int(sx.step.item())}")
+print(f"rank {st.rank} collective={sb.collective()} stress_iters={iters} ok={ok}")
+flag = torch.tensor([1 if ok else 0], device="cuda")
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 st.barrier(); st.shutdown()
-sys.exit(0 if ok else 1)
+sys.exit(0 if flag.item() == 1 else 1)
 '''
 
 

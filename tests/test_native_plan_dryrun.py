@@ -85,8 +85,9 @@ def test_fp8_plan_builds(monkeypatch):
 
 
 def test_allreduce_buckets_and_ownership(monkeypatch):
-  """Bucket plan of the fused all-reduce (CPU logic only): buckets tile the flat buffer in
-  backward order, and the per-bucket rank shards give every element exactly one owner."""
+  """Bucket plan of the fused all-reduce (CPU logic only): buckets tile the kernel part of the flat
+  buffer in backward order, the vector tail is one-shot (replicated), and the per-bucket rank shards
+  (+ rank 0 for the tail) give every element exactly one owner in a checkpoint gather."""
   fake_native.install(monkeypatch)
   monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
   from tf2_cyclegan_b200.engine.cyclegan import build_specs
@@ -97,8 +98,13 @@ def test_allreduce_buckets_and_ownership(monkeypatch):
   for n in NETS:
     bs = be.plan_buckets(n)
     st = be.state[n]
+    vec_lo = st.layout.vec_lo
+    # every vector parameter (bias / gamma / beta) lives in the tail, every kernel below it
+    for seg in st.layout.segments:
+      assert (seg.offset >= vec_lo) == (seg.kind == "vector"), seg.name
+    assert 0 < st.n - vec_lo <= 32 * 1024 and vec_lo % 8 == 0     # <= 128 KB: the one-shot form
     assert len(bs) == (4 if n in "GF" else 2)
-    assert bs[0][2] == st.n and bs[-1][0] == 0 and bs[-1][1] == 0
+    assert bs[0][2] == vec_lo and bs[-1][0] == 0 and bs[-1][1] == 0
     for (j0, lo0, hi0), (j1, lo1, hi1) in zip(bs, bs[1:]):
       assert j1 < j0 and hi1 == lo0 and lo0 % 8 == 0           # descending layers, contiguous
     if n in "GF":
@@ -108,27 +114,31 @@ def test_allreduce_buckets_and_ownership(monkeypatch):
       owners = torch.zeros(st.n, dtype=torch.int32)
       for rank in range(world):
         sb = SymmetricBuffers.__new__(SymmetricBuffers)
-        sb.rank, sb.world, sb.buckets = rank, world, {}
-        sb.set_buckets(n, sorted((lo, hi) for _, lo, hi in bs))
+        sb.rank, sb.world, sb.buckets, sb.vec_lo = rank, world, {}, {}
+        sb.set_buckets(n, sorted((lo, hi) for _, lo, hi in bs), vec_lo=vec_lo)
         for lo, hi in sb.owned_ranges(n, st.n):
           owners[lo:hi] += 1
       assert int(owners.min()) == 1 and int(owners.max()) == 1
 
 
 def test_bucketed_allreduce_plan_order(monkeypatch):
-  """Fused data-parallel plan (stub peer memory): every bucket's reduce + Adam launch sits on the
-  wgrad lane, after the wgrad GEMMs of all layers inside the bucket and after an event recorded on
-  the main lane once the bucket's lowest layer is done; buckets run in backward order and the
-  per-step tail (step counter, derived weights) follows the last bucket."""
+  """Fused data-parallel plan (stub peer memory): every cross-GPU launch sits on the dedicated
+  collective lane in ONE global order (comm_order: generators' buckets interleaved, then the
+  discriminators'), each after events recorded on the main AND the wgrad lane once every op that
+  writes the bucket's gradients has been issued; a network's last launch carries the vector tail
+  (and, for SCALAR_NET, the loss scalars) and is followed by the per-step tail."""
   fake_native.install(monkeypatch)
   monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
   from tf2_cyclegan_b200.engine.cyclegan import build_specs
-  from tf2_cyclegan_b200.engine.native_backend import NETS, NativeBackend
+  from tf2_cyclegan_b200.engine.native_backend import COMM_LANE, NETS, SCALAR_NET, NativeBackend
   from tf2_cyclegan_b200.parallel.strategy import Strategy
   be = NativeBackend(build_specs(A(3)), 2, Strategy(device="cpu"), seed=1, image_size=128, local_batch=2)
+  flags = {}
 
   class Symm:
-    def emit_allreduce_adam(self, plan, n, st, bucket=None, **kw):
+    def emit_allreduce_adam(self, plan, n, st, bucket=None, vectors=None, scalars=False, exposed=False, **kw):
+      assert set(kw) == {"lr", "b1", "b2", "eps"}
+      flags[(n, bucket)] = (vectors, scalars, exposed)
       plan.add_memset(f"opt.{n}.AR.b{bucket}", st.g.data_ptr(), 16)
 
   be.fused, be.symm = True, Symm()
@@ -149,25 +159,32 @@ def test_bucketed_allreduce_plan_order(monkeypatch):
   names = sp.names
   assert len(lanes) == len(names)
   pos = {nm: i for i, nm in enumerate(names)}
+  # one global order, all on the collective lane
+  ars = [i for i, nm in enumerate(names) if ".AR.b" in nm]
+  assert [names[i] for i in ars] == [f"opt.{n}.AR.b{k}" for n, k in be.comm_order()]
+  assert be.comm_order()[:4] == [("G", 0), ("F", 0), ("G", 1), ("F", 1)] and be.comm_order()[-1][0] == SCALAR_NET
+  assert all(lanes[i] == COMM_LANE for i in ars)
+  ops = sp.plan.ops
   for n, main_lane, wg_lane in (("G", 0, 2), ("Y", 0, 2), ("F", 1, 3), ("X", 1, 3)):
     layers = be.specs[n].layers
-    ars = [i for i, nm in enumerate(names) if nm.startswith(f"opt.{n}.AR.b")]
-    assert len(ars) == len(be.buckets[n]) and ars == sorted(ars)
-    assert [names[i] for i in ars] == [f"opt.{n}.AR.b{k}" for k in range(len(ars))]   # backward order
-    for k, i in enumerate(ars):
-      assert lanes[i] == wg_lane
+    nb = len(be.buckets[n])
+    for k in range(nb):
+      i = pos[f"opt.{n}.AR.b{k}"]
+      last = k == nb - 1
+      assert flags[(n, k)] == (last, last and n == SCALAR_NET, last)
       first_layer = be.buckets[n][k][0]
       last_layer = be.buckets[n][k - 1][0] - 1 if k else len(layers) - 1
-      # the wait just before the mask op pairs with a record on the main lane
-      w = max(j for j in range(i) if names[j].startswith(f"sync.wait.{n}.bucket{k}"))
-      r = pos[f"sync.rec.{n}.bucket{k}"]
-      assert r < w < i and lanes[r] == main_lane and lanes[w] == wg_lane
+      waits = [j for j in range(i) if names[j].startswith(f"sync.wait.{n}.bucket{k}")]
+      recs = [ops[j][2][1] for j in waits]                     # the record op each wait refers to
+      rec_lane = {r: ops[r][2][0] for r in recs}            # (lane,) of a record op
+      assert sorted(rec_lane.values()) == [main_lane, wg_lane] and all(ops[j][2][0] == COMM_LANE for j in waits)
       for j in range(first_layer, last_layer + 1):
         grads = [q for q, nm in enumerate(names)
                  if nm.startswith(f"{n}.{layers[j].name}.") and ("wgrad" in nm or ".bwd[" in nm or "in_bwd_apply" in nm
                                                                   or "act_bwd" in nm)
                  and q > sp.marks["test_end"] and f"[0:{2 * (3 if n in 'GF' else 2)}]" in nm]
-        assert grads and max(grads) < i, (n, k, layers[j].name)
-        assert all(q < r or lanes[q] == wg_lane for q in grads), (n, k, layers[j].name)
+        assert grads, (n, k, layers[j].name)
+        for q in grads:     # issued before the record op of its own lane
+          assert q < next(r for r in recs if rec_lane[r] == lanes[q]), (n, k, names[q])
     tail = pos[f"opt.{n}.step"]
-    assert tail > ars[-1] and lanes[tail] == wg_lane
+    assert tail > pos[f"opt.{n}.AR.b{nb - 1}"] and lanes[tail] == COMM_LANE

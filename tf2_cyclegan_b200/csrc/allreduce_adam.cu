@@ -6,6 +6,8 @@
 //     g  = sum_p grad_p[i]              P2P loads   | multimem.ld_reduce (in-switch sum)
 //     w,m,v = keras_adam(w,m,v,g)       fp32 master + moments live only on the owner (ZeRO-1)
 //     w_bf16_p[i] = bf16(w) for all p   P2P stores  | multimem.st (switch broadcast)
+//   (one-shot part, small vectors)      every rank reduces + updates its replica, no broadcast
+//   (scalars)                           every rank sums all ranks' loss slots
 //   barrier(peers)                      everyone's compute copy is complete
 //   grad_local[...] = 0                 ready for the next step's wgrad accumulation
 //
@@ -50,22 +52,25 @@ __device__ __forceinline__ void block_barrier(const AllreduceAdamParams& p, int 
   __syncthreads();
 }
 
+// peer loads: volatile (kept after the barrier, in program order) but without a memory clobber, so
+// the compiler may keep several of them — and the local master / moment loads — in flight together
 __device__ __forceinline__ float4 ld_f4(const float* p) {
   float4 v;
   asm volatile("ld.global.relaxed.sys.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
 __device__ __forceinline__ float4 mc_ld_reduce_f4(const float* p) {
   float4 v;
   asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
 __device__ __forceinline__ void mc_st_bf16x8(__nv_bfloat16* p, uint4 v) {
   asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(p),
                "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ void acc4(float4& a, const float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 
 __device__ __forceinline__ void adam4(float4& w, float4& m, float4& v, const float4 g, float lr_t,
                                       float b1, float b2, float eps) {
@@ -77,59 +82,125 @@ __device__ __forceinline__ void adam4(float4& w, float4& m, float4& v, const flo
 #undef B2_ADAM1
 }
 
-__global__ void __launch_bounds__(512) allreduce_adam_kernel(const AllreduceAdamParams p) {
+// Keras-Adam on 8 consecutive elements of the local fp32 master / moments; returns the packed bf16 weights
+__device__ __forceinline__ uint4 adam8(const AllreduceAdamParams& p, long long i, const float4 g0, const float4 g1,
+                                       float lr_t) {
+  float4 w0 = *reinterpret_cast<float4*>(p.w + i), w1 = *reinterpret_cast<float4*>(p.w + i + 4);
+  float4 m0 = *reinterpret_cast<float4*>(p.m + i), m1 = *reinterpret_cast<float4*>(p.m + i + 4);
+  float4 v0 = *reinterpret_cast<float4*>(p.v + i), v1 = *reinterpret_cast<float4*>(p.v + i + 4);
+  adam4(w0, m0, v0, g0, lr_t, p.beta1, p.beta2, p.eps);
+  adam4(w1, m1, v1, g1, lr_t, p.beta1, p.beta2, p.eps);
+  *reinterpret_cast<float4*>(p.w + i) = w0; *reinterpret_cast<float4*>(p.w + i + 4) = w1;
+  *reinterpret_cast<float4*>(p.m + i) = m0; *reinterpret_cast<float4*>(p.m + i + 4) = m1;
+  *reinterpret_cast<float4*>(p.v + i) = v0; *reinterpret_cast<float4*>(p.v + i + 4) = v1;
+  uint4 pk;
+  pk.x = pack_bf16x2(w0.x, w0.y); pk.y = pack_bf16x2(w0.z, w0.w);
+  pk.z = pack_bf16x2(w1.x, w1.y); pk.w = pack_bf16x2(w1.z, w1.w);
+  return pk;
+}
+
+constexpr int kArThreads = 256;
+constexpr int kArUnroll = 2;    // 8-element chunks per thread per iteration (independent peer loads in flight)
+
+__global__ void __launch_bounds__(kArThreads, 1) allreduce_adam_kernel(const AllreduceAdamParams p) {
   const int t = *p.step + 1;
   const float lr_t = p.lr * sqrtf(1.f - powf(p.beta2, static_cast<float>(t))) /
                      (1.f - powf(p.beta1, static_cast<float>(t)));
-  // shard of this rank, in units of 8 elements
+  // two-shot: shard of this rank, in units of 8 elements, and the slice of this block inside it
   const long long n8 = p.n / 8;
   const long long per_rank = (n8 + p.world - 1) / p.world;
   const long long r_begin = min(n8, per_rank * p.rank), r_end = min(n8, r_begin + per_rank);
-  // slice of this block inside the shard
   const long long per_blk = (r_end - r_begin + gridDim.x - 1) / gridDim.x;
   const long long b_begin = min(r_end, r_begin + per_blk * blockIdx.x);
   const long long b_end = min(r_end, b_begin + per_blk);
 
   block_barrier(p, 0);
 
-  for (long long i8 = b_begin + threadIdx.x; i8 < b_end; i8 += blockDim.x) {
-    const long long i = i8 * 8;
-    float4 g0, g1;
+  // ---- scalars (block 0): every rank sums all ranks' slots in rank order
+  if (blockIdx.x == 0 && threadIdx.x < p.sc_n) {
+    float acc = 0.f;
+    for (int q = 0; q < p.world; ++q) {
+      float v;
+      asm volatile("ld.global.relaxed.sys.f32 %0, [%1];" : "=f"(v) : "l"(p.sc_src[q] + threadIdx.x));
+      acc += v;
+    }
+    p.sc_dst[threadIdx.x] = acc;
+  }
+
+  // ---- two-shot region
+  for (long long i8 = b_begin + threadIdx.x; i8 < b_end; i8 += kArThreads * kArUnroll) {
+    float4 g0[kArUnroll], g1[kArUnroll];
+    long long idx[kArUnroll];
+#pragma unroll
+    for (int j = 0; j < kArUnroll; ++j) {
+      const long long c8 = i8 + j * kArThreads;
+      idx[j] = c8 < b_end ? p.lo + c8 * 8 : -1;
+    }
     if (p.mc_grad != nullptr) {
-      g0 = mc_ld_reduce_f4(p.mc_grad + i);
-      g1 = mc_ld_reduce_f4(p.mc_grad + i + 4);
+#pragma unroll
+      for (int j = 0; j < kArUnroll; ++j)
+        if (idx[j] >= 0) {
+          g0[j] = mc_ld_reduce_f4(p.mc_grad + idx[j]);
+          g1[j] = mc_ld_reduce_f4(p.mc_grad + idx[j] + 4);
+        }
     } else {
-      g0 = make_float4(0.f, 0.f, 0.f, 0.f);
-      g1 = g0;
-#pragma unroll 8
-      for (int q = 0; q < p.world; ++q) {
-        const int peer = (p.rank + q) % p.world;   // stagger so peers are hit evenly
-        const float4 a = ld_f4(p.grad[peer] + i);
-        const float4 b = ld_f4(p.grad[peer] + i + 4);
-        g0.x += a.x; g0.y += a.y; g0.z += a.z; g0.w += a.w;
-        g1.x += b.x; g1.y += b.y; g1.z += b.z; g1.w += b.w;
+#pragma unroll
+      for (int j = 0; j < kArUnroll; ++j) g0[j] = g1[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q0 = 0; q0 < p.world; q0 += 2) {     // two peers' loads in flight together
+        float4 a[2][kArUnroll], b[2][kArUnroll];
+        const int qa = (p.rank + q0) % p.world;     // staggered so that peers are hit evenly
+        const int qb = (p.rank + q0 + 1) % p.world;
+        const bool two = q0 + 1 < p.world;
+#pragma unroll
+        for (int j = 0; j < kArUnroll; ++j)
+          if (idx[j] >= 0) {
+            a[0][j] = ld_f4(p.grad[qa] + idx[j]);
+            b[0][j] = ld_f4(p.grad[qa] + idx[j] + 4);
+            if (two) {
+              a[1][j] = ld_f4(p.grad[qb] + idx[j]);
+              b[1][j] = ld_f4(p.grad[qb] + idx[j] + 4);
+            }
+          }
+#pragma unroll
+        for (int j = 0; j < kArUnroll; ++j)
+          if (idx[j] >= 0) {
+            acc4(g0[j], a[0][j]); acc4(g1[j], b[0][j]);
+            if (two) { acc4(g0[j], a[1][j]); acc4(g1[j], b[1][j]); }
+          }
       }
     }
-    float4 w0 = *reinterpret_cast<float4*>(p.w + i), w1 = *reinterpret_cast<float4*>(p.w + i + 4);
-    float4 m0 = *reinterpret_cast<float4*>(p.m + i), m1 = *reinterpret_cast<float4*>(p.m + i + 4);
-    float4 v0 = *reinterpret_cast<float4*>(p.v + i), v1 = *reinterpret_cast<float4*>(p.v + i + 4);
-    adam4(w0, m0, v0, g0, lr_t, p.beta1, p.beta2, p.eps);
-    adam4(w1, m1, v1, g1, lr_t, p.beta1, p.beta2, p.eps);
-    *reinterpret_cast<float4*>(p.w + i) = w0; *reinterpret_cast<float4*>(p.w + i + 4) = w1;
-    *reinterpret_cast<float4*>(p.m + i) = m0; *reinterpret_cast<float4*>(p.m + i + 4) = m1;
-    *reinterpret_cast<float4*>(p.v + i) = v0; *reinterpret_cast<float4*>(p.v + i + 4) = v1;
-    uint4 pk;
-    pk.x = pack_bf16x2(w0.x, w0.y); pk.y = pack_bf16x2(w0.z, w0.w);
-    pk.z = pack_bf16x2(w1.x, w1.y); pk.w = pack_bf16x2(w1.z, w1.w);
-    if (p.mc_w_bf16 != nullptr) {
-      mc_st_bf16x8(p.mc_w_bf16 + i, pk);
-    } else {
+#pragma unroll
+    for (int j = 0; j < kArUnroll; ++j) {
+      if (idx[j] < 0) continue;
+      const uint4 pk = adam8(p, idx[j], g0[j], g1[j], lr_t);
+      if (p.mc_w_bf16 != nullptr) {
+        mc_st_bf16x8(p.mc_w_bf16 + idx[j], pk);
+      } else {
 #pragma unroll 8
-      for (int q = 0; q < p.world; ++q) {
-        const int peer = (p.rank + q) % p.world;
-        *reinterpret_cast<uint4*>(p.w_bf16[peer] + i) = pk;
+        for (int q = 0; q < p.world; ++q) {
+          const int peer = (p.rank + q) % p.world;
+          *reinterpret_cast<uint4*>(p.w_bf16[peer] + idx[j]) = pk;
+        }
       }
     }
+  }
+
+  // ---- one-shot region: replicated update, bit-identical on every rank (fixed peer order 0..W-1)
+  const long long v8 = p.v_n / 8;
+  for (long long i8 = static_cast<long long>(blockIdx.x) * kArThreads + threadIdx.x; i8 < v8;
+       i8 += static_cast<long long>(gridDim.x) * kArThreads) {
+    const long long i = p.v_lo + i8 * 8;
+    float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+    for (int q = 0; q < p.world; q += 2) {
+      const bool two = q + 1 < p.world;
+      const float4 a0 = ld_f4(p.grad[q] + i), b0 = ld_f4(p.grad[q] + i + 4);
+      float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = a1;
+      if (two) { a1 = ld_f4(p.grad[q + 1] + i); b1 = ld_f4(p.grad[q + 1] + i + 4); }
+      acc4(g0, a0); acc4(g1, b0);     // ((g + r0) + r1) ...: the same order on every rank
+      acc4(g0, a1); acc4(g1, b1);
+    }
+    const uint4 pk = adam8(p, i, g0, g1, lr_t);
+    *reinterpret_cast<uint4*>(p.w_bf16[p.rank] + i) = pk;
   }
 
   block_barrier(p, 1);
@@ -137,14 +208,20 @@ __global__ void __launch_bounds__(512) allreduce_adam_kernel(const AllreduceAdam
   // zero the slices (peer, block) of the local gradient buffer: every peer's block with this
   // index has finished reading them (it passed the second barrier)
   float* gl = p.grad[p.rank];
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int q = 0; q < p.world; ++q) {
     const long long q_begin = min(n8, per_rank * q), q_end = min(n8, q_begin + per_rank);
     const long long pb = (q_end - q_begin + gridDim.x - 1) / gridDim.x;
     const long long s0 = min(q_end, q_begin + pb * blockIdx.x), s1 = min(q_end, s0 + pb);
-    for (long long i8 = s0 + threadIdx.x; i8 < s1; i8 += blockDim.x) {
-      *reinterpret_cast<float4*>(gl + i8 * 8) = make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(gl + i8 * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long i8 = s0 + threadIdx.x; i8 < s1; i8 += kArThreads) {
+      *reinterpret_cast<float4*>(gl + p.lo + i8 * 8) = z;
+      *reinterpret_cast<float4*>(gl + p.lo + i8 * 8 + 4) = z;
     }
+  }
+  for (long long i8 = static_cast<long long>(blockIdx.x) * kArThreads + threadIdx.x; i8 < v8;
+       i8 += static_cast<long long>(gridDim.x) * kArThreads) {
+    *reinterpret_cast<float4*>(gl + p.v_lo + i8 * 8) = z;
+    *reinterpret_cast<float4*>(gl + p.v_lo + i8 * 8 + 4) = z;
   }
 }
 
@@ -184,7 +261,7 @@ void launch_scatter_add(float* dst, const float* src, const int* idx, long long 
 }
 
 void launch_allreduce_adam(const AllreduceAdamParams& p, int num_blocks, cudaStream_t s) {
-  allreduce_adam_kernel<<<num_blocks, 512, 0, s>>>(p);
+  allreduce_adam_kernel<<<num_blocks, kArThreads, 0, s>>>(p);
 }
 
 void launch_gather_bf16(__nv_bfloat16* dst, const float* src, const int* idx, long long n,

@@ -87,13 +87,73 @@ __device__ __forceinline__ void gather_g(const View& g1, int fold, const View& g
   }
 }
 
+// ---------------------------------------------------------- InstanceNorm kernels
+// Shared structure of in_apply / in_bwd_reduce / in_bwd_apply. grid: (pixel chunks, N). A thread
+// owns ONE 8-channel group (16-byte vectors; its per-channel coefficients live in registers) and
+// walks the pixels ln, ln + lanes, ... of the block's chunk, U pixels (= U independent 16-byte
+// loads per tensor) in flight. Pixel -> (h, w) is one multiply-high with a host-computed
+// reciprocal (no division, no per-slot state); every in-image offset is 32-bit arithmetic; the
+// 64-bit image base is added once per block. Feature switches (activation kind, residual input,
+// reflect halo, second gradient, FP8 twin) are template parameters so that the unused paths cost
+// no instructions or registers: these kernels are issue-bound long before they are memory-bound
+// when written generically (round 1: ~500 SASS instructions per 16-byte vector, 34-50 % of HBM).
+constexpr int ACTK_NONE = 0, ACTK_RELU = 1, ACTK_SLOPE = 2;
+
+struct V32 {   // View with 32-bit in-image strides, image base resolved
+  const __nv_bfloat16* p;
+  int sh, sw;
+};
+__device__ __forceinline__ V32 v32(const View& v, int n, int c) {
+  V32 r;
+  r.p = reinterpret_cast<const __nv_bfloat16*>(v.p) + static_cast<long long>(n) * v.sn + c;
+  r.sh = static_cast<int>(v.sh);
+  r.sw = static_cast<int>(v.sw);
+  return r;
+}
+__device__ __forceinline__ uint4 ldv(const V32& v, int h, int w) {
+  return __ldg(reinterpret_cast<const uint4*>(v.p + (h * v.sh + w * v.sw)));
+}
+__device__ __forceinline__ void stv(const V32& v, int h, int w, const uint4& u) {
+  *reinterpret_cast<uint4*>(const_cast<__nv_bfloat16*>(v.p) + (h * v.sh + w * v.sw)) = u;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  // bf16 -> fp32 is a 16-bit shift: low half << 16, high half masked
+  f[0] = __uint_as_float(u.x << 16); f[1] = __uint_as_float(u.x & 0xffff0000u);
+  f[2] = __uint_as_float(u.y << 16); f[3] = __uint_as_float(u.y & 0xffff0000u);
+  f[4] = __uint_as_float(u.z << 16); f[5] = __uint_as_float(u.z & 0xffff0000u);
+  f[6] = __uint_as_float(u.w << 16); f[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+__device__ __forceinline__ void load_f8(const float* p, float (&f)[8]) {   // 32-byte aligned
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+// (mean, rstd) of the thread's 8 channels from the forward statistics [.. 2 * c ..] = (sum, sumsq)
+__device__ __forceinline__ void mean_rstd8(const float* st, float inv_count, float eps, float (&mean)[8],
+                                           float (&rstd)[8]) {
+  float a[8], b[8];
+  load_f8(st, a);
+  load_f8(st + 8, b);
+  const float s[16] = {a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7]};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    mean[j] = s[2 * j] * inv_count;
+    rstd[j] = rsqrtf(fmaxf(s[2 * j + 1] * inv_count - mean[j] * mean[j], 0.f) + eps);
+  }
+}
+template <int ACT>
+__device__ __forceinline__ float actk(float v, float slope) {
+  if constexpr (ACT == ACTK_RELU) return fmaxf(v, 0.f);
+  if constexpr (ACT == ACTK_SLOPE) return v > 0.f ? v : v * slope;
+  return v;
+}
+
 // ------------------------------------------------------------------ in_apply
-// grid: (pixel chunks, N). A thread owns one 8-channel group (coefficients live in
-// registers) and walks pixels, 4 at a time so that several 16-byte loads are in flight.
-// U = pixels in flight per thread, MINB = resident blocks per SM the register budget is set for
-// (variants are selected at run time, see ew_variant(); <4, 4> is the default)
-template <int U, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) in_apply_kernel(const InApplyParams p, int pix_per_block) {
+// dst = act(a * x + b) (+ skip), written into the (reflect-haloed) input buffer of the next conv
+template <int ACT, bool SKIP, bool HALO, bool HAS8>
+__global__ void __launch_bounds__(kThreads, (SKIP || HAS8) ? 3 : 4) in_apply_kernel(const InApplyParams p, int pix_per_block,
+                                                              uint32_t rcp_w) {
+  constexpr int U = 4;
   const int c8 = p.C >> 3;
   const int lanes = kThreads / c8;
   const int c = (threadIdx.x % c8) * 8;
@@ -102,104 +162,95 @@ __global__ void __launch_bounds__(kThreads, MINB) in_apply_kernel(const InApplyP
   const int HW = p.H * p.W;
   const int pix0 = blockIdx.x * pix_per_block;
   const int pix1 = min(HW, pix0 + pix_per_block);
-  // per-channel affine coefficients (a, b), computed once per block (thread t -> channel t) and
-  // read back from shared memory at use: few registers -> 4 blocks / SM -> more loads in flight
-  extern __shared__ float coef[];   // float2[C]
-  float2* ab = reinterpret_cast<float2*>(coef);
-  for (int ch = threadIdx.x; ch < p.C; ch += kThreads) {
-    float a = 1.f, b = 0.f;
-    if (p.stats != nullptr) {
-      const float* st = p.stats + (static_cast<long long>(n) * p.C + ch) * 2;
-      const float mean = st[0] * p.inv_count;
-      const float var = fmaxf(st[1] * p.inv_count - mean * mean, 0.f);
-      a = rsqrtf(var + p.eps) * __ldg(p.gamma + ch);
-      b = __ldg(p.beta + ch) - mean * a;
+  float ka[8], kb[8];
+  if (p.stats != nullptr) {
+    float mean[8], rstd[8], ga[8], be[8];
+    mean_rstd8(p.stats + (static_cast<long long>(n) * p.C + c) * 2, p.inv_count, p.eps, mean, rstd);
+    load_f8(p.gamma + c, ga);
+    load_f8(p.beta + c, be);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ka[j] = rstd[j] * ga[j];
+      kb[j] = be[j] - mean[j] * ka[j];
     }
-    ab[((ch & 7) >> 1) * 2 * c8 + (ch >> 3) * 2 + (ch & 1)] = make_float2(a, b);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ka[j] = 1.f; kb[j] = 0.f; }
   }
-  __syncthreads();
-  const bool has_skip = p.skip.p != nullptr;
+  const V32 X = v32(p.x, n, c), S = v32(p.skip, n, c), D = v32(p.dst, n, c);
+  uint8_t* d8 = nullptr;
+  int d8sh = 0, d8sw = 0;
+  float s8 = 1.f, amax = 0.f;
+  if constexpr (HAS8) {
+    d8 = reinterpret_cast<uint8_t*>(p.dst8.p) + static_cast<long long>(n) * p.dst8.sn + c;
+    d8sh = static_cast<int>(p.dst8.sh);
+    d8sw = static_cast<int>(p.dst8.sw);
+    s8 = __ldg(p.scale8);
+  }
   const float slope = act_slope(p.act);
-  const bool has8 = p.dst8.p != nullptr;
-  const float s8 = has8 ? __ldg(p.scale8) : 1.f;
-  float amax = 0.f;
-  int hh[U], ww[U];
-#pragma unroll
-  for (int u = 0; u < U; ++u) {   // one division per slot, then incremental (h, w) updates
-    const int pix = pix0 + ln + u * lanes;
-    hh[u] = pix / p.W;
-    ww[u] = pix - hh[u] * p.W;
-  }
-  const int step = lanes * U;
-  const int step_h = step / p.W, step_w = step - step_h * p.W;
-  for (int base = pix0 + ln; base < pix1; base += step) {
+  const int H = p.H, W = p.W, halo = p.halo;
+  for (int base = pix0 + ln; base < pix1; base += lanes * U) {
     uint4 xv[U], sv[U];
+    int hh[U], ww[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int pix = base + u * lanes;
+      hh[u] = static_cast<int>(__umulhi(static_cast<uint32_t>(pix), rcp_w));
+      ww[u] = pix - hh[u] * W;
       if (pix < pix1) {
-        xv[u] = __ldg(reinterpret_cast<const uint4*>(vptr(p.x, n, hh[u], ww[u]) + c));
-        if (has_skip) sv[u] = __ldg(reinterpret_cast<const uint4*>(vptr(p.skip, n, hh[u], ww[u]) + c));
+        xv[u] = ldv(X, hh[u], ww[u]);
+        if constexpr (SKIP) sv[u] = ldv(S, hh[u], ww[u]);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int pix = base + u * lanes;
-      if (pix >= pix1) continue;
-      const uint32_t xw[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
-      const uint32_t sw[4] = {sv[u].x, sv[u].y, sv[u].z, sv[u].w};
-      uint32_t ow[4];
-      uint16_t o8[4];
+      if (base + u * lanes >= pix1) continue;
+      float x[8], v[8];
+      unpack8(xv[u], x);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 t = unpack_bf16x2(xw[j]);
-        const float4 k = *reinterpret_cast<const float4*>(&ab[(j * c8 + (c >> 3)) * 2]);   // (a0, b0, a1, b1)
-        float v0 = apply_slope(fmaf(t.x, k.x, k.y), slope);
-        float v1 = apply_slope(fmaf(t.y, k.z, k.w), slope);
-        if (has_skip) {
-          const float2 q = unpack_bf16x2(sw[j]);
-          v0 += q.x;
-          v1 += q.y;
-        }
-        ow[j] = pack_bf16x2(v0, v1);
-        if (has8) {
-          amax = fmaxf(amax, fmaxf(fabsf(v0), fabsf(v1)));
-          o8[j] = __nv_cvt_float2_to_fp8x2(make_float2(v0 * s8, v1 * s8), __NV_SATFINITE, __NV_E4M3);
-        }
+      for (int j = 0; j < 8; ++j) v[j] = actk<ACT>(fmaf(x[j], ka[j], kb[j]), slope);
+      if constexpr (SKIP) {
+        float s[8];
+        unpack8(sv[u], s);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += s[j];
       }
-      const uint4 pk = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-      *reinterpret_cast<uint4*>(vptr_mut(p.dst, n, hh[u], ww[u]) + c) = pk;
+      const uint4 pk = pack8(v);
+      const int h = hh[u], w = ww[u];
+      stv(D, h, w, pk);
       uint2 pk8 = make_uint2(0u, 0u);
-      if (has8) {
+      if constexpr (HAS8) {
+        uint16_t o8[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          amax = fmaxf(amax, fmaxf(fabsf(v[2 * j]), fabsf(v[2 * j + 1])));
+          o8[j] = __nv_cvt_float2_to_fp8x2(make_float2(v[2 * j] * s8, v[2 * j + 1] * s8), __NV_SATFINITE, __NV_E4M3);
+        }
         pk8 = make_uint2(static_cast<uint32_t>(o8[0]) | (static_cast<uint32_t>(o8[1]) << 16),
                          static_cast<uint32_t>(o8[2]) | (static_cast<uint32_t>(o8[3]) << 16));
-        *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(p.dst8.p) + n * p.dst8.sn + hh[u] * p.dst8.sh +
-                                  ww[u] * p.dst8.sw + c) = pk8;
+        *reinterpret_cast<uint2*>(d8 + (h * d8sh + w * d8sw)) = pk8;
       }
-      if (p.halo > 0 && (hh[u] <= p.halo || hh[u] >= p.H - 1 - p.halo || ww[u] <= p.halo ||
-                         ww[u] >= p.W - 1 - p.halo)) {   // only border pixels have mirror images
-        int hs[2], ws[2];
-        const int nh = reflect_set(hh[u], p.H, p.halo, hs);
-        const int nw = reflect_set(ww[u], p.W, p.halo, ws);
-        if (nh + nw > 2)
-          for (int a = 0; a < nh; ++a)
-            for (int b = 0; b < nw; ++b)
-              if (a + b > 0) {
-                *reinterpret_cast<uint4*>(vptr_mut(p.dst, n, hs[a], ws[b]) + c) = pk;
-                if (has8)
-                  *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(p.dst8.p) + n * p.dst8.sn +
-                                            hs[a] * p.dst8.sh + ws[b] * p.dst8.sw + c) = pk8;
-              }
+      if constexpr (HALO) {
+        // mirror images of a border pixel: row hm and / or column wm (reflect: -i for 1 <= i <= halo,
+        // 2 (n - 1) - i for n - 1 - halo <= i <= n - 2)
+        const int hm = (h >= 1 && h <= halo) ? -h : ((h >= H - 1 - halo && h <= H - 2) ? 2 * (H - 1) - h : h);
+        const int wm = (w >= 1 && w <= halo) ? -w : ((w >= W - 1 - halo && w <= W - 2) ? 2 * (W - 1) - w : w);
+        if (hm != h) {
+          stv(D, hm, w, pk);
+          if constexpr (HAS8) *reinterpret_cast<uint2*>(d8 + (hm * d8sh + w * d8sw)) = pk8;
+        }
+        if (wm != w) {
+          stv(D, h, wm, pk);
+          if constexpr (HAS8) *reinterpret_cast<uint2*>(d8 + (h * d8sh + wm * d8sw)) = pk8;
+          if (hm != h) {
+            stv(D, hm, wm, pk);
+            if constexpr (HAS8) *reinterpret_cast<uint2*>(d8 + (hm * d8sh + wm * d8sw)) = pk8;
+          }
+        }
       }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      hh[u] += step_h;
-      ww[u] += step_w;
-      if (ww[u] >= p.W) { ww[u] -= p.W; ++hh[u]; }
     }
   }
-  if (has8) {   // delayed-scaling statistics: one atomic per warp (values are >= 0, so int order == float order)
+  if constexpr (HAS8) {   // delayed-scaling statistics: one atomic per warp (values are >= 0, so int order == float order)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(p.amax8), __float_as_int(amax));
@@ -207,135 +258,136 @@ __global__ void __launch_bounds__(kThreads, MINB) in_apply_kernel(const InApplyP
 }
 
 // ------------------------------------------------------------ in_bwd_reduce
-// grid: (pixel chunks, N). Threads: (C/8 channel groups) x (256 / (C/8) pixel lanes).
-template <int U, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) in_bwd_reduce_kernel(const InBwdReduceParams p,
-                                                                    int pix_per_block) {
+// dy = (fold(g1) + g2) * act'(y); bstats[n][c] += (sum dy, sum dy * xhat). The sums run over the raw
+// x (sum dy * x); xhat = (x - mean) * rstd is applied once per block at the end.
+template <int ACT, bool FOLD, bool G2, bool HAS_IN>
+__global__ void __launch_bounds__(kThreads, 3) in_bwd_reduce_kernel(const InBwdReduceParams p, int pix_per_block,
+                                                                   uint32_t rcp_w) {
+  constexpr int U = 2;
   extern __shared__ float red[];   // [lanes][C][2]
   const int c8 = p.C >> 3;
   const int lanes = kThreads / c8;
-  const int cg = threadIdx.x % c8;
+  const int c = (threadIdx.x % c8) * 8;
   const int ln = threadIdx.x / c8;
-  const int c = cg * 8;
   const int n = blockIdx.y;
   const int HW = p.H * p.W;
   const int pix0 = blockIdx.x * pix_per_block;
   const int pix1 = min(HW, pix0 + pix_per_block);
-
-  const bool has_in = p.stats != nullptr;
-  float4* mrgb = reinterpret_cast<float4*>(red + lanes * p.C * 2);   // float4[C] = (mean, rstd, gamma, beta)
-  if (has_in) {
-    for (int ch = threadIdx.x; ch < p.C; ch += kThreads) {
-      const float* st = p.stats + (static_cast<long long>(n) * p.C + ch) * 2;
-      const float mu = st[0] * p.inv_count;
-      const float var = fmaxf(st[1] * p.inv_count - mu * mu, 0.f);
-      mrgb[(ch & 7) * c8 + (ch >> 3)] = make_float4(mu, rsqrtf(var + p.eps), __ldg(p.gamma + ch), __ldg(p.beta + ch));
+  float ka[8], kb[8];   // y = ka * x + kb: only its sign is needed (act')
+  if constexpr (HAS_IN && ACT != ACTK_NONE) {
+    float mean[8], rstd[8], ga[8], be[8];
+    mean_rstd8(p.stats + (static_cast<long long>(n) * p.C + c) * 2, p.inv_count, p.eps, mean, rstd);
+    load_f8(p.gamma + c, ga);
+    load_f8(p.beta + c, be);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ka[j] = rstd[j] * ga[j];
+      kb[j] = be[j] - mean[j] * ka[j];
     }
-    __syncthreads();
   }
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
-
-  const bool has_g2 = p.g2.p != nullptr;
+  const V32 G1 = v32(p.g1, n, c), G2v = v32(p.g2, n, c), X = v32(p.x, n, c), DY = v32(p.dy, n, c);
   const float slope = act_slope(p.act);
-  int hh[U], ww[U];
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const int pix = pix0 + ln + u * lanes;
-    hh[u] = pix / p.W;
-    ww[u] = pix - hh[u] * p.W;
-  }
-  const int step = lanes * U;
-  const int step_h = step / p.W, step_w = step - step_h * p.W;
-  for (int base = pix0 + ln; base < pix1; base += step) {
+  const int H = p.H, W = p.W, fold = p.fold1;
+  for (int base = pix0 + ln; base < pix1; base += lanes * U) {
     uint4 gv[U], g2v[U], xv[U];
+    int hh[U], ww[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int pix = base + u * lanes;
+      hh[u] = static_cast<int>(__umulhi(static_cast<uint32_t>(pix), rcp_w));
+      ww[u] = pix - hh[u] * W;
       if (pix < pix1) {
-        gv[u] = __ldg(reinterpret_cast<const uint4*>(vptr(p.g1, n, hh[u], ww[u]) + c));
-        if (has_g2) g2v[u] = __ldg(reinterpret_cast<const uint4*>(vptr(p.g2, n, hh[u], ww[u]) + c));
-        if (has_in) xv[u] = __ldg(reinterpret_cast<const uint4*>(vptr(p.x, n, hh[u], ww[u]) + c));
+        gv[u] = ldv(G1, hh[u], ww[u]);
+        if constexpr (G2) g2v[u] = ldv(G2v, hh[u], ww[u]);
+        if constexpr (HAS_IN) xv[u] = ldv(X, hh[u], ww[u]);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int pix = base + u * lanes;
-      if (pix >= pix1) continue;
+      if (base + u * lanes >= pix1) continue;
       const int h = hh[u], w = ww[u];
       float g[8];
-      {
-        const uint32_t a[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
-        const uint32_t b[4] = {g2v[u].x, g2v[u].y, g2v[u].z, g2v[u].w};
+      unpack8(gv[u], g);
+      if constexpr (G2) {
+        float t[8];
+        unpack8(g2v[u], t);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 t = unpack_bf16x2(a[j]);
-          g[2 * j] = t.x; g[2 * j + 1] = t.y;
-          if (has_g2) { const float2 k = unpack_bf16x2(b[j]); g[2 * j] += k.x; g[2 * j + 1] += k.y; }
-        }
+        for (int j = 0; j < 8; ++j) g[j] += t[j];
       }
-      if (p.fold1 > 0 && (h <= p.fold1 || h >= p.H - 1 - p.fold1 || w <= p.fold1 ||
-                          w >= p.W - 1 - p.fold1)) {   // rare: pixels whose mirror images live in the halo of g1
-        int hs[2], ws[2];
-        const int nh = reflect_set(h, p.H, p.fold1, hs);
-        const int nw = reflect_set(w, p.W, p.fold1, ws);
-        if (nh + nw > 2)
-          for (int a = 0; a < nh; ++a)
-            for (int b = 0; b < nw; ++b)
-              if (a + b > 0) {
-                float t[8];
-                load8(vptr(p.g1, n, hs[a], ws[b]) + c, t);
+      if constexpr (FOLD) {   // border pixels also collect the gradient of their mirror images in g1's halo
+        const int hm = (h >= 1 && h <= fold) ? -h : ((h >= H - 1 - fold && h <= H - 2) ? 2 * (H - 1) - h : h);
+        const int wm = (w >= 1 && w <= fold) ? -w : ((w >= W - 1 - fold && w <= W - 2) ? 2 * (W - 1) - w : w);
+        if (hm != h || wm != w) {
+          float t[8];
+          if (hm != h) {
+            unpack8(ldv(G1, hm, w), t);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) g[j] += t[j];
-              }
-      }
-      if (has_in) {
-        const uint32_t xw[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+            for (int j = 0; j < 8; ++j) g[j] += t[j];
+          }
+          if (wm != w) {
+            unpack8(ldv(G1, h, wm), t);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 t = unpack_bf16x2(xw[j]);
-          const float xs[2] = {t.x, t.y};
+            for (int j = 0; j < 8; ++j) g[j] += t[j];
+            if (hm != h) {
+              unpack8(ldv(G1, hm, wm), t);
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            const int jj = 2 * j + q;
-            const float4 k = mrgb[jj * c8 + (c >> 3)];
-            const float xh = (xs[q] - k.x) * k.y;
-            const float y = xh * k.z + k.w;
-            g[jj] *= act_grad_from_pre(y, slope);
-            const float gq = __bfloat162float(__float2bfloat16(g[jj]));   // stats of the stored value
-            s1[jj] += gq;
-            s2[jj] += gq * xh;
+              for (int j = 0; j < 8; ++j) g[j] += t[j];
+            }
           }
         }
       }
-      store8(vptr_mut(p.dy, n, h, w) + c, g);
-    }
+      if constexpr (HAS_IN) {
+        float x[8];
+        unpack8(xv[u], x);
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      hh[u] += step_h;
-      ww[u] += step_w;
-      if (ww[u] >= p.W) { ww[u] -= p.W; ++hh[u]; }
+        for (int j = 0; j < 8; ++j) {
+          if constexpr (ACT != ACTK_NONE) g[j] = fmaf(x[j], ka[j], kb[j]) > 0.f ? g[j] : g[j] * slope;
+        }
+        const uint4 pk = pack8(g);
+        float gq[8];
+        unpack8(pk, gq);   // statistics of the STORED (bf16) value: in_bwd_apply reads that
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += gq[j];
+          s2[j] = fmaf(gq[j], x[j], s2[j]);
+        }
+        stv(DY, h, w, pk);
+      } else {
+        stv(DY, h, w, pack8(g));
+      }
     }
   }
-  if (!has_in || p.bstats == nullptr) return;
+  if (!HAS_IN || p.bstats == nullptr) return;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     red[(ln * p.C + c + j) * 2 + 0] = s1[j];
     red[(ln * p.C + c + j) * 2 + 1] = s2[j];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < p.C * 2; i += kThreads) {
-    float acc = 0.f;
-    for (int l = 0; l < lanes; ++l) acc += red[l * p.C * 2 + i];
-    atomicAdd(p.bstats + static_cast<long long>(n) * p.C * 2 + i, acc);
+  for (int ch = threadIdx.x; ch < p.C; ch += kThreads) {
+    float a1 = 0.f, a2 = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      const float2 t = *reinterpret_cast<const float2*>(&red[(l * p.C + ch) * 2]);
+      a1 += t.x;
+      a2 += t.y;
+    }
+    const float* st = p.stats + (static_cast<long long>(n) * p.C + ch) * 2;
+    const float mean = st[0] * p.inv_count;
+    const float rstd = rsqrtf(fmaxf(st[1] * p.inv_count - mean * mean, 0.f) + p.eps);
+    float* bs = p.bstats + (static_cast<long long>(n) * p.C + ch) * 2;
+    atomicAdd(bs, a1);
+    atomicAdd(bs + 1, rstd * (a2 - mean * a1));
   }
 }
 
 // ------------------------------------------------------------- in_bwd_apply
 // dx = A*dy + B*x + C per channel (A = gamma*rstd, B = -gamma*rstd^2*m2, C = gamma*rstd*(mean*rstd*m2 - m1))
-template <int U, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) in_bwd_apply_kernel(const InBwdApplyParams p, int pix_per_block) {
+__global__ void __launch_bounds__(kThreads, 3) in_bwd_apply_kernel(const InBwdApplyParams p, int pix_per_block,
+                                                                  uint32_t rcp_w) {
+  constexpr int U = 4;
   const int c8 = p.C >> 3;
   const int lanes = kThreads / c8;
   const int c = (threadIdx.x % c8) * 8;
@@ -356,150 +408,49 @@ __global__ void __launch_bounds__(kThreads, MINB) in_bwd_apply_kernel(const InBw
       p.dbeta[cc] += db;
     }
   }
-  extern __shared__ float coef[];   // float4[C] = (A, B, C, -)
-  float4* abc = reinterpret_cast<float4*>(coef);
-  for (int ch = threadIdx.x; ch < p.C; ch += kThreads) {
-    const float* st = p.stats + (static_cast<long long>(n) * p.C + ch) * 2;
-    const float* bs = p.bstats + (static_cast<long long>(n) * p.C + ch) * 2;
-    const float mean = st[0] * p.inv_count;
-    const float var = fmaxf(st[1] * p.inv_count - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + p.eps);
-    const float m1 = bs[0] * p.inv_count;
-    const float m2 = bs[1] * p.inv_count;
-    const float gr = __ldg(p.gamma + ch) * rstd;
-    abc[(ch & 7) * c8 + (ch >> 3)] = make_float4(gr, -gr * rstd * m2, gr * (mean * rstd * m2 - m1), 0.f);
-  }
-  __syncthreads();
-  int hh[U], ww[U];
+  float kA[8], kB[8], kC[8];
+  {
+    float mean[8], rstd[8], ga[8], b0[8], b1[8];
+    mean_rstd8(p.stats + (static_cast<long long>(n) * p.C + c) * 2, p.inv_count, p.eps, mean, rstd);
+    load_f8(p.gamma + c, ga);
+    load_f8(p.bstats + (static_cast<long long>(n) * p.C + c) * 2, b0);
+    load_f8(p.bstats + (static_cast<long long>(n) * p.C + c) * 2 + 8, b1);
+    const float bs[16] = {b0[0], b0[1], b0[2], b0[3], b0[4], b0[5], b0[6], b0[7],
+                          b1[0], b1[1], b1[2], b1[3], b1[4], b1[5], b1[6], b1[7]};
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const int pix = pix0 + ln + u * lanes;
-    hh[u] = pix / p.W;
-    ww[u] = pix - hh[u] * p.W;
+    for (int j = 0; j < 8; ++j) {
+      const float m1 = bs[2 * j] * p.inv_count, m2 = bs[2 * j + 1] * p.inv_count;
+      const float gr = ga[j] * rstd[j];
+      kA[j] = gr;
+      kB[j] = -gr * rstd[j] * m2;
+      kC[j] = gr * (mean[j] * rstd[j] * m2 - m1);
+    }
   }
-  const int step = lanes * U;
-  const int step_h = step / p.W, step_w = step - step_h * p.W;
-  for (int base = pix0 + ln; base < pix1; base += step) {
+  const V32 DYv = v32(p.dy, n, c), X = v32(p.x, n, c), DX = v32(p.dx, n, c);
+  const int W = p.W;
+  for (int base = pix0 + ln; base < pix1; base += lanes * U) {
     uint4 dv[U], xv[U];
+    int hh[U], ww[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int pix = base + u * lanes;
+      hh[u] = static_cast<int>(__umulhi(static_cast<uint32_t>(pix), rcp_w));
+      ww[u] = pix - hh[u] * W;
       if (pix < pix1) {
-        dv[u] = __ldg(reinterpret_cast<const uint4*>(vptr(p.dy, n, hh[u], ww[u]) + c));
-        xv[u] = __ldg(reinterpret_cast<const uint4*>(vptr(p.x, n, hh[u], ww[u]) + c));
+        dv[u] = ldv(DYv, hh[u], ww[u]);
+        xv[u] = ldv(X, hh[u], ww[u]);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int pix = base + u * lanes;
-      if (pix >= pix1) continue;
-      const uint32_t dw[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
-      const uint32_t xw[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
-      uint32_t ow[4];
+      if (base + u * lanes >= pix1) continue;
+      float d[8], x[8], o[8];
+      unpack8(dv[u], d);
+      unpack8(xv[u], x);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 d = unpack_bf16x2(dw[j]);
-        const float2 x = unpack_bf16x2(xw[j]);
-        const float4 k0 = abc[(2 * j) * c8 + (c >> 3)], k1 = abc[(2 * j + 1) * c8 + (c >> 3)];
-        ow[j] = pack_bf16x2(fmaf(k0.x, d.x, fmaf(k0.y, x.x, k0.z)), fmaf(k1.x, d.y, fmaf(k1.y, x.y, k1.z)));
-      }
-      *reinterpret_cast<uint4*>(vptr_mut(p.dx, n, hh[u], ww[u]) + c) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(kA[j], d[j], fmaf(kB[j], x[j], kC[j]));
+      stv(DX, hh[u], ww[u], pack8(o));
     }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      hh[u] += step_h;
-      ww[u] += step_w;
-      if (ww[u] >= p.W) { ww[u] -= p.W; ++hh[u]; }
-    }
-  }
-}
-
-// Register double-buffered variant of in_bwd_apply (experiment, ew_variant() == 3): the loads of the
-// next U pixels are issued before the current U are consumed, so a thread always has loads in
-// flight while it computes. Same arithmetic as in_bwd_apply_kernel.
-template <int U, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) in_bwd_apply_pf_kernel(const InBwdApplyParams p, int pix_per_block) {
-  const int c8 = p.C >> 3;
-  const int lanes = kThreads / c8;
-  const int c = (threadIdx.x % c8) * 8;
-  const int ln = threadIdx.x / c8;
-  const int n = blockIdx.y;
-  const int HW = p.H * p.W;
-  const int pix0 = blockIdx.x * pix_per_block;
-  const int pix1 = min(HW, pix0 + pix_per_block);
-  if (blockIdx.x == 0 && blockIdx.y == 0 && p.dgamma != nullptr) {
-    for (int cc = threadIdx.x; cc < p.C; cc += blockDim.x) {
-      float dg = 0.f, db = 0.f;
-      for (int nn = 0; nn < p.N; ++nn) {
-        const float* bs = p.bstats + (static_cast<long long>(nn) * p.C + cc) * 2;
-        db += bs[0];
-        dg += bs[1];
-      }
-      p.dgamma[cc] += dg;
-      p.dbeta[cc] += db;
-    }
-  }
-  extern __shared__ float coef[];   // float4[C] = (A, B, C, -)
-  float4* abc = reinterpret_cast<float4*>(coef);
-  for (int ch = threadIdx.x; ch < p.C; ch += kThreads) {
-    const float* st = p.stats + (static_cast<long long>(n) * p.C + ch) * 2;
-    const float* bs = p.bstats + (static_cast<long long>(n) * p.C + ch) * 2;
-    const float mean = st[0] * p.inv_count;
-    const float var = fmaxf(st[1] * p.inv_count - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + p.eps);
-    const float m1 = bs[0] * p.inv_count;
-    const float m2 = bs[1] * p.inv_count;
-    const float gr = __ldg(p.gamma + ch) * rstd;
-    abc[(ch & 7) * c8 + (ch >> 3)] = make_float4(gr, -gr * rstd * m2, gr * (mean * rstd * m2 - m1), 0.f);
-  }
-  __syncthreads();
-  const int step = lanes * U;
-  const int step2 = 2 * step;
-  const int s2h = step2 / p.W, s2w = step2 - s2h * p.W;
-  int hA[U], wA[U], hB[U], wB[U];
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const int pa = pix0 + ln + u * lanes, pb = pa + step;
-    hA[u] = pa / p.W; wA[u] = pa - hA[u] * p.W;
-    hB[u] = pb / p.W; wB[u] = pb - hB[u] * p.W;
-  }
-  uint4 dA[U], xA[U], dB[U], xB[U];
-  auto load = [&](uint4 (&dv)[U], uint4 (&xv)[U], const int (&hh)[U], const int (&ww)[U], int base) {
-#pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (base + u * lanes < pix1) {
-        dv[u] = __ldg(reinterpret_cast<const uint4*>(vptr(p.dy, n, hh[u], ww[u]) + c));
-        xv[u] = __ldg(reinterpret_cast<const uint4*>(vptr(p.x, n, hh[u], ww[u]) + c));
-      }
-  };
-  auto consume = [&](const uint4 (&dv)[U], const uint4 (&xv)[U], int (&hh)[U], int (&ww)[U], int base) {
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (base + u * lanes < pix1) {
-        const uint32_t dw[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
-        const uint32_t xw[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
-        uint32_t ow[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 d = unpack_bf16x2(dw[j]);
-          const float2 x = unpack_bf16x2(xw[j]);
-          const float4 k0 = abc[(2 * j) * c8 + (c >> 3)], k1 = abc[(2 * j + 1) * c8 + (c >> 3)];
-          ow[j] = pack_bf16x2(fmaf(k0.x, d.x, fmaf(k0.y, x.x, k0.z)), fmaf(k1.x, d.y, fmaf(k1.y, x.y, k1.z)));
-        }
-        *reinterpret_cast<uint4*>(vptr_mut(p.dx, n, hh[u], ww[u]) + c) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-      }
-      hh[u] += s2h;                       // this buffer is next used 2 * step pixels further on
-      ww[u] += s2w;
-      if (ww[u] >= p.W) { ww[u] -= p.W; ++hh[u]; }
-    }
-  };
-  int base = pix0 + ln;
-  load(dA, xA, hA, wA, base);
-  for (; base < pix1; base += step2) {
-    load(dB, xB, hB, wB, base + step);
-    consume(dA, xA, hA, wA, base);
-    load(dA, xA, hA, wA, base + step2);
-    consume(dB, xB, hB, wB, base + step);
   }
 }
 
@@ -825,11 +776,6 @@ inline int grid_for_fixed_c(long long total, int c8) {
 
 }  // namespace
 
-static int ew_env(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
-
 static int ew_num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -842,19 +788,12 @@ static int ew_num_sms() {
 }
 
 // Pixels per block of the (pixel chunks, N) grids. The kernels keep `blocks_per_sm` blocks
-// resident, so the grid is sized to fill whole waves of the machine: with B2_EW_WAVES = w
-// (default 1) every image gets floor(w * slots / N) chunks (chunk length need not be a power of
-// two, only a multiple of the pixel lanes), e.g. 12 images x 37 chunks = 444 blocks = exactly one
-// wave of 148 x 3. Longer chunks also amortise the per-block coefficient table / reduction.
+// resident, so the grid is sized to fill whole waves of the machine: every image gets
+// floor(slots / N) chunks (chunk length need not be a power of two, only a multiple of the pixel
+// lanes), e.g. 12 images x 49 chunks = 588 blocks on the 148 x 4 = 592 resident slots. Longer chunks
+// also amortise the per-block coefficient set-up / reduction.
 static int pick_pix_per_block(int HW, int N, int lanes, int blocks_per_sm) {
-  static const int legacy = ew_env("B2_EW_BLOCKS", 0);
-  if (legacy > 0) {   // old heuristic: power-of-two chunks until >= B2_EW_BLOCKS blocks
-    int ppb = lanes * 32;
-    while (ppb > lanes * 4 && static_cast<long long>((HW + ppb - 1) / ppb) * N < legacy) ppb /= 2;
-    return ppb > HW ? HW : ppb;
-  }
-  static const int waves = ew_env("B2_EW_WAVES", 1);
-  const int slots = ew_num_sms() * blocks_per_sm * (waves > 0 ? waves : 1);
+  const int slots = ew_num_sms() * blocks_per_sm;
   int chunks = slots / (N > 0 ? N : 1);
   if (chunks < 1) chunks = 1;
   int ppb = (HW + chunks - 1) / chunks;
@@ -864,67 +803,69 @@ static int pick_pix_per_block(int HW, int N, int lanes, int blocks_per_sm) {
   return ppb > HW ? HW : ppb;
 }
 
-// Tuning variants of the three InstanceNorm kernels (pixels in flight per thread / resident blocks
-// per SM / register double buffering); 0 = default. Same arithmetic in every variant.
-static int g_ew_variant = -1;
-int ew_variant() {
-  if (g_ew_variant < 0) g_ew_variant = ew_env("B2_EW_VARIANT", 0);
-  return g_ew_variant;
+// reciprocal for pixel -> row: floor(pix / W) == umulhi(pix, ceil(2^32 / W)) for pix * W < 2^32
+static uint32_t rcp_for(int H, int W, int C, const char* who) {
+  if (W < 2 || C % 8 != 0 || kThreads % (C / 8) != 0 ||
+      static_cast<unsigned long long>(H) * W * W >= (1ull << 32)) {
+    fprintf(stderr, "%s: unsupported shape H=%d W=%d C=%d\n", who, H, W, C);
+    abort();
+  }
+  return static_cast<uint32_t>(((1ull << 32) + W - 1) / W);
 }
-void set_ew_variant(int v) { g_ew_variant = v < 0 ? 0 : v; }
 
-template <int U, int MINB>
-static void launch_in_apply_t(const InApplyParams& p, cudaStream_t s) {
-  const int HW = p.H * p.W;
-  const int lanes = kThreads / (p.C / 8);
-  const int ppb = pick_pix_per_block(HW, p.N, lanes, MINB);
-  dim3 grid((HW + ppb - 1) / ppb, p.N);
-  in_apply_kernel<U, MINB><<<grid, kThreads, 2 * p.C * sizeof(float), s>>>(p, ppb);
+template <int ACT, bool SKIP, bool HALO>
+static void launch_in_apply_t(const InApplyParams& p, dim3 grid, int ppb, uint32_t rcp, cudaStream_t s) {
+  if (p.dst8.p != nullptr) in_apply_kernel<ACT, SKIP, HALO, true><<<grid, kThreads, 0, s>>>(p, ppb, rcp);
+  else in_apply_kernel<ACT, SKIP, HALO, false><<<grid, kThreads, 0, s>>>(p, ppb, rcp);
+}
+template <int ACT>
+static void launch_in_apply_a(const InApplyParams& p, dim3 grid, int ppb, uint32_t rcp, cudaStream_t s) {
+  const bool skip = p.skip.p != nullptr, halo = p.halo > 0;
+  if (skip) { if (halo) launch_in_apply_t<ACT, true, true>(p, grid, ppb, rcp, s); else launch_in_apply_t<ACT, true, false>(p, grid, ppb, rcp, s); }
+  else { if (halo) launch_in_apply_t<ACT, false, true>(p, grid, ppb, rcp, s); else launch_in_apply_t<ACT, false, false>(p, grid, ppb, rcp, s); }
 }
 void launch_in_apply(const InApplyParams& p, cudaStream_t s) {
-  switch (ew_variant()) {
-    case 1: return launch_in_apply_t<2, 6>(p, s);
-    case 2: return launch_in_apply_t<8, 3>(p, s);
-    case 3: return launch_in_apply_t<4, 3>(p, s);
-    default: return launch_in_apply_t<4, 4>(p, s);
-  }
-}
-
-template <int U, int MINB>
-static void launch_in_bwd_reduce_t(const InBwdReduceParams& p, cudaStream_t s) {
-  const int HW = p.H * p.W;
-  const int c8 = p.C / 8;
-  const int lanes = kThreads / c8;
-  const int pix_per_block = pick_pix_per_block(HW, p.N, lanes, MINB);
-  dim3 grid((HW + pix_per_block - 1) / pix_per_block, p.N);
-  const size_t smem = (static_cast<size_t>(lanes) * p.C * 2 + 4 * p.C) * sizeof(float);
-  in_bwd_reduce_kernel<U, MINB><<<grid, kThreads, smem, s>>>(p, pix_per_block);
-}
-void launch_in_bwd_reduce(const InBwdReduceParams& p, cudaStream_t s) {
-  switch (ew_variant()) {
-    case 1: return launch_in_bwd_reduce_t<4, 2>(p, s);
-    case 2: return launch_in_bwd_reduce_t<2, 4>(p, s);
-    case 3: return launch_in_bwd_reduce_t<2, 2>(p, s);
-    default: return launch_in_bwd_reduce_t<2, 3>(p, s);
-  }
-}
-
-template <int U, int MINB, bool PF>
-static void launch_in_bwd_apply_t(const InBwdApplyParams& p, cudaStream_t s) {
+  const uint32_t rcp = rcp_for(p.H, p.W, p.C, "launch_in_apply");
   const int HW = p.H * p.W;
   const int lanes = kThreads / (p.C / 8);
-  const int ppb = pick_pix_per_block(HW, p.N, lanes, MINB);
+  const int ppb = pick_pix_per_block(HW, p.N, lanes, (p.skip.p != nullptr || p.dst8.p != nullptr) ? 3 : 4);
   dim3 grid((HW + ppb - 1) / ppb, p.N);
-  if constexpr (PF) in_bwd_apply_pf_kernel<U, MINB><<<grid, kThreads, 4 * p.C * sizeof(float), s>>>(p, ppb);
-  else in_bwd_apply_kernel<U, MINB><<<grid, kThreads, 4 * p.C * sizeof(float), s>>>(p, ppb);
+  if (p.act == ACT_RELU) launch_in_apply_a<ACTK_RELU>(p, grid, ppb, rcp, s);
+  else if (p.act == ACT_NONE) launch_in_apply_a<ACTK_NONE>(p, grid, ppb, rcp, s);
+  else launch_in_apply_a<ACTK_SLOPE>(p, grid, ppb, rcp, s);
 }
+
+template <int ACT, bool FOLD, bool G2>
+static void launch_in_bwd_reduce_t(const InBwdReduceParams& p, dim3 grid, size_t smem, int ppb, uint32_t rcp,
+                                   cudaStream_t s) {
+  if (p.stats != nullptr) in_bwd_reduce_kernel<ACT, FOLD, G2, true><<<grid, kThreads, smem, s>>>(p, ppb, rcp);
+  else in_bwd_reduce_kernel<ACTK_NONE, FOLD, G2, false><<<grid, kThreads, smem, s>>>(p, ppb, rcp);
+}
+template <int ACT>
+static void launch_in_bwd_reduce_a(const InBwdReduceParams& p, dim3 grid, size_t smem, int ppb, uint32_t rcp,
+                                   cudaStream_t s) {
+  const bool fold = p.fold1 > 0, g2 = p.g2.p != nullptr;
+  if (fold) { if (g2) launch_in_bwd_reduce_t<ACT, true, true>(p, grid, smem, ppb, rcp, s); else launch_in_bwd_reduce_t<ACT, true, false>(p, grid, smem, ppb, rcp, s); }
+  else { if (g2) launch_in_bwd_reduce_t<ACT, false, true>(p, grid, smem, ppb, rcp, s); else launch_in_bwd_reduce_t<ACT, false, false>(p, grid, smem, ppb, rcp, s); }
+}
+void launch_in_bwd_reduce(const InBwdReduceParams& p, cudaStream_t s) {
+  const uint32_t rcp = rcp_for(p.H, p.W, p.C, "launch_in_bwd_reduce");
+  const int HW = p.H * p.W;
+  const int lanes = kThreads / (p.C / 8);
+  const int ppb = pick_pix_per_block(HW, p.N, lanes, 3);
+  dim3 grid((HW + ppb - 1) / ppb, p.N);
+  const size_t smem = static_cast<size_t>(lanes) * p.C * 2 * sizeof(float);
+  if (p.act == ACT_NONE) launch_in_bwd_reduce_a<ACTK_NONE>(p, grid, smem, ppb, rcp, s);
+  else launch_in_bwd_reduce_a<ACTK_SLOPE>(p, grid, smem, ppb, rcp, s);
+}
+
 void launch_in_bwd_apply(const InBwdApplyParams& p, cudaStream_t s) {
-  switch (ew_variant()) {
-    case 1: return launch_in_bwd_apply_t<2, 6, false>(p, s);
-    case 2: return launch_in_bwd_apply_t<8, 3, false>(p, s);
-    case 3: return launch_in_bwd_apply_t<2, 4, true>(p, s);
-    default: return launch_in_bwd_apply_t<4, 4, false>(p, s);
-  }
+  const uint32_t rcp = rcp_for(p.H, p.W, p.C, "launch_in_bwd_apply");
+  const int HW = p.H * p.W;
+  const int lanes = kThreads / (p.C / 8);
+  const int ppb = pick_pix_per_block(HW, p.N, lanes, 3);
+  dim3 grid((HW + ppb - 1) / ppb, p.N);
+  in_bwd_apply_kernel<<<grid, kThreads, 0, s>>>(p, ppb, rcp);
 }
 
 void launch_act_bwd(const ActBwdParams& p, cudaStream_t s) {

@@ -32,9 +32,6 @@ struct InApplyParams {
   float* amax8;
 };
 void launch_in_apply(const InApplyParams& p, cudaStream_t s);
-// tuning variant of the InstanceNorm kernels (0 = default; env B2_EW_VARIANT), see elementwise.cu
-int ew_variant();
-void set_ew_variant(int v);
 
 struct InBwdReduceParams {
   View g1;              // bf16 gradient source 1 (may be a padded-domain dgrad output)

@@ -24,10 +24,6 @@
 namespace py = pybind11;
 using namespace b2;
 
-namespace b2 {
-void launch_shift_probe(const CUtensorMap& tmA, const CUtensorMap& tmB, float* out, cudaStream_t s);
-}
-
 namespace {
 
 void check(cudaError_t e, const char* what) {
@@ -119,13 +115,15 @@ void fill_taps(const std::vector<TapT>& taps, Tap* dst, int* n) {
 
 class Plan {
  public:
-  // Lanes: lane 0 runs on the caller's stream, lanes 1..3 on the plan's side streams. Sync ops:
+  // Lanes: lane 0 runs on the caller's stream, lanes 1..4 on the plan's side streams (by convention
+  // 0 / 1 = the two network pairs, 2 / 3 = their weight-gradient GEMMs, 4 = cross-GPU collectives in
+  // ONE global order). Sync ops:
   //   kind 1 fork  : every side lane waits for lane 0
   //   kind 2 join  : lane 0 waits for every side lane that ran something since the last join
   //   kind 3 record: record event `ev` on lane `lane`
   //   kind 4 wait  : lane `lane` waits for the event recorded by op `ref`
   // All of it is plain event record / wait, so it also works under stream capture (CUDA graph).
-  static constexpr int kLanes = 4;
+  static constexpr int kLanes = 5;
   struct Op {
     std::string name;
     std::function<void(cudaStream_t)> fn;
@@ -183,8 +181,15 @@ class Plan {
 
   cudaStream_t lane_stream(int lane, cudaStream_t main) {
     if (lane == 0) return main;
-    if (side_[lane] == nullptr)
-      check(cudaStreamCreateWithFlags(&side_[lane], cudaStreamNonBlocking), "side stream");
+    if (side_[lane] == nullptr) {
+      if (lane == kLanes - 1) {   // collectives: highest priority, so that their few CTAs are placed first
+        int lo = 0, hi = 0;
+        check(cudaDeviceGetStreamPriorityRange(&lo, &hi), "cudaDeviceGetStreamPriorityRange");
+        check(cudaStreamCreateWithPriority(&side_[lane], cudaStreamNonBlocking, hi), "comm stream");
+      } else {
+        check(cudaStreamCreateWithFlags(&side_[lane], cudaStreamNonBlocking), "side stream");
+      }
+    }
     return side_[lane];
   }
 
@@ -203,7 +208,7 @@ class Plan {
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (end < 0 || end > size()) end = size();
     bool forked = false;
-    bool dirty[kLanes] = {false, false, false, false};
+    bool dirty[kLanes] = {};
     for (int i = begin; i < end; ++i) {
       Op& o = ops_[i];
       if (o.kind != 0) {
@@ -324,18 +329,6 @@ class Plan {
     });
   }
 
-  int add_wgrad_row(std::string name, py::bytes dy_map, py::bytes a_map, int tiles_w, int H,
-                    int num_images, int cin, int cout, uint64_t dw, long long ldw, int ksplit) {
-    auto p = std::make_shared<WgradRowParams>();
-    memset(p.get(), 0, sizeof(WgradRowParams));
-    p->tmDY = tmap_from(dy_map);
-    p->tmA = tmap_from(a_map);
-    if (cin % 128 || cout % 256) throw std::runtime_error("wgrad_row: cin % 128 / cout % 256");
-    p->tiles_w = tiles_w; p->H = H; p->num_images = num_images; p->cin = cin; p->cout = cout;
-    p->dw = P<float>(dw); p->ldw = ldw;
-    return add(std::move(name), [p, ksplit](cudaStream_t s) { launch_wgrad_row(*p, ksplit, s); });
-  }
-
   // ------------------------------------------------------ elementwise ops
   int add_in_apply(std::string name, ViewT x, uint64_t stats, uint64_t gamma, uint64_t beta,
                    float inv_count, float eps, int act, ViewT skip, ViewT dst, int halo, int N,
@@ -454,21 +447,34 @@ class Plan {
       if (wgrad) launch_d4_wgrad(p, s);
     });
   }
+  // grad / wbf16 / w / m / v are BUFFER BASES; [lo, lo + n) is the two-shot (sharded) region, [v_lo, v_lo + v_n)
+  // the one-shot (replicated) region, sc_* the loss-scalar side channel (see allreduce_adam.cuh)
   int add_allreduce_adam(std::string name, std::vector<uint64_t> grad_ptrs,
                          std::vector<uint64_t> wbf16_ptrs, std::vector<uint64_t> signal_ptrs,
                          uint64_t w, uint64_t m, uint64_t v, uint64_t step, float lr, float b1,
-                         float b2, float eps, long long n, int rank, int world, int num_blocks,
-                         uint64_t mc_grad, uint64_t mc_wbf16) {
+                         float b2, float eps, long long lo, long long n, long long v_lo, long long v_n,
+                         std::vector<uint64_t> sc_src, uint64_t sc_dst, int sc_n, int rank, int world,
+                         int num_blocks, uint64_t mc_grad, uint64_t mc_wbf16) {
     auto p = std::make_shared<AllreduceAdamParams>();
     memset(p.get(), 0, sizeof(AllreduceAdamParams));
-    if (world > kMaxRanks) throw std::runtime_error("world too large");
+    if (world > kMaxRanks || world < 1) throw std::runtime_error("bad world size");
+    if (static_cast<int>(grad_ptrs.size()) != world || static_cast<int>(wbf16_ptrs.size()) != world ||
+        static_cast<int>(signal_ptrs.size()) != world)
+      throw std::runtime_error("allreduce_adam: need one pointer per rank");
+    if ((lo | n | v_lo | v_n) % 8 != 0 || n < 0 || v_n < 0) throw std::runtime_error("allreduce_adam: regions must be multiples of 8");
+    if (sc_n < 0 || sc_n > kMaxScalars || (sc_n > 0 && static_cast<int>(sc_src.size()) != world))
+      throw std::runtime_error("allreduce_adam: bad scalar side channel");
+    if (num_blocks < 1 || num_blocks > 148) throw std::runtime_error("allreduce_adam: 1..148 blocks");
     for (int r = 0; r < world; ++r) {
       p->grad[r] = P<float>(grad_ptrs[r]);
       p->w_bf16[r] = P<__nv_bfloat16>(wbf16_ptrs[r]);
       p->signal[r] = P<uint32_t>(signal_ptrs[r]);
+      if (sc_n > 0) p->sc_src[r] = P<const float>(sc_src[r]);
     }
     p->w = P<float>(w); p->m = P<float>(m); p->v = P<float>(v); p->step = P<const int>(step);
-    p->lr = lr; p->beta1 = b1; p->beta2 = b2; p->eps = eps; p->n = n; p->rank = rank;
+    p->lr = lr; p->beta1 = b1; p->beta2 = b2; p->eps = eps;
+    p->lo = lo; p->n = n; p->v_lo = v_lo; p->v_n = v_n;
+    p->sc_dst = P<float>(sc_dst); p->sc_n = sc_n; p->rank = rank;
     p->world = world; p->mc_grad = P<float>(mc_grad); p->mc_w_bf16 = P<__nv_bfloat16>(mc_wbf16);
     return add(std::move(name), [p, num_blocks](cudaStream_t s) {
       launch_allreduce_adam(*p, num_blocks, s);
@@ -480,8 +486,8 @@ class Plan {
   int lane_ = 0;
   // NVTX range per op (name = the op label) for timeline tools; on by B2_NVTX=1 or set_nvtx()
   bool nvtx_ = [] { const char* e = getenv("B2_NVTX"); return e && e[0] == '1'; }();
-  cudaStream_t side_[kLanes] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t lane_ev_[kLanes] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t side_[kLanes] = {};
+  cudaEvent_t lane_ev_[kLanes] = {};
 };
 
 }  // namespace
@@ -490,12 +496,6 @@ PYBIND11_MODULE(_C, m) {
   m.doc() = "b200-cyclegan native runtime (sm_100a kernels + plan executor)";
   m.def("encode_tmap", &encode_tmap, py::arg("ptr"), py::arg("dtype"), py::arg("dims"),
         py::arg("strides_bytes"), py::arg("box"), py::arg("swizzle") = 3);
-  m.def("set_ew_variant", &b2::set_ew_variant, "tuning variant of the InstanceNorm kernels (0 = default)");
-  m.def("ew_variant", &b2::ew_variant);
-  m.def("shift_probe", [](py::bytes a, py::bytes b, uint64_t out) {
-    b2::launch_shift_probe(tmap_from(a), tmap_from(b), P<float>(out), nullptr);
-    check(cudaDeviceSynchronize(), "shift_probe");
-  });
   m.def("device_sync", []() { check(cudaDeviceSynchronize(), "cudaDeviceSynchronize"); });
   m.attr("MAX_TAPS") = kMaxTaps;
   py::class_<Plan>(m, "Plan")
@@ -519,7 +519,6 @@ PYBIND11_MODULE(_C, m) {
            py::arg("b_mn"), py::arg("num_images"), py::arg("phases"), py::arg("out_scale") = 0,
            py::arg("fp8") = false, py::arg("ts_map") = py::bytes(), py::arg("ts") = std::vector<int>())
       .def("add_wgrad", &Plan::add_wgrad)
-      .def("add_wgrad_row", &Plan::add_wgrad_row)
       .def("add_in_apply", &Plan::add_in_apply, py::arg("name"), py::arg("x"), py::arg("stats"),
            py::arg("gamma"), py::arg("beta"), py::arg("inv_count"), py::arg("eps"), py::arg("act"),
            py::arg("skip"), py::arg("dst"), py::arg("halo"), py::arg("N"), py::arg("H"), py::arg("W"),

@@ -100,8 +100,11 @@ class CycleGAN:
     return self.backend.test_step(x, y)
 
   def reduce_dict(self, d: dict):
-    """SUM-reduce result scalars over replicas (main.py:264-267)."""
-    return self.strategy.reduce_dict(d)
+    """SUM-reduce result scalars over replicas (main.py:264-267). The native fused path has already
+    summed them on the device (loss-scalar side channel of the last fused reduce + Adam launch): no
+    collective call and no host synchronisation per step."""
+    reduce = getattr(self.backend, "reduce_results", None)
+    return reduce(d) if reduce is not None else self.strategy.reduce_dict(d)
 
   def distributed_train_step(self, x, y):
     return self.reduce_dict(self.train_step(x, y))

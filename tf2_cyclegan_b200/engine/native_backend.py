@@ -34,6 +34,8 @@ SLOT = {"G_loss": 0, "G_cycle": 1, "G_identity": 2, "F_loss": 3, "F_cycle": 4, "
         "X_loss": 6, "Y_loss": 7, "err_x_cycle": 8, "err_y_cycle": 9, "err_x_same": 10,
         "err_y_same": 11}
 NUM_SLOTS = 16
+COMM_LANE = 4          # csrc/plan.cu: the high-priority stream that carries every cross-GPU launch
+SCALAR_NET = "X"       # the network whose last fused launch also carries the loss-scalar sums
 ADAM = dict(lr=2e-4, b1=0.5, b2=0.9, eps=1e-7)   # main.py:134-145 (+ Keras default epsilon)
 
 
@@ -47,7 +49,7 @@ class StepPlan:
     S = be.image_size
     self.x_in = torch.zeros(b, S, S, 3, device=dev)
     self.y_in = torch.zeros(b, S, S, 3, device=dev)
-    self.slots = torch.zeros(NUM_SLOTS, device=dev)
+    self.slots = be.slots          # loss / metric accumulators (peer-readable on the fused path)
     self.ex: Dict[str, NetExec] = {
         "G": NetExec(be.specs["G"], be.state["G"], 3 * b, S, dev, "G", fp8=be.fp8),
         "F": NetExec(be.specs["F"], be.state["F"], 3 * b, S, dev, "F", fp8=be.fp8),
@@ -150,39 +152,39 @@ class StepPlan:
                  gout_view=self.gd_adv[D].view(0), gout_is_dy=True)
       plan.add_memset(f"zero.{D}.bstats2", e.bstat_arena.data_ptr(), e.bstat_arena.numel() * 4)
 
-    # With wgrad lanes and the fused all-reduce the optimizer (cross-GPU reduce + Adam + weight
-    # broadcast) is issued in BUCKETS on the WGRAD lane while the backward pass is still running:
-    # only the last bucket (the first layers of the network) is exposed.
-    opt_on_wgrad_lane = two and be.fused and be.wgrad_lanes and os.environ.get("B2_OPT_LANE", "1") != "0"
+    # Fused multi-GPU path: the optimizer (cross-GPU reduce + Adam + weight broadcast) is issued in
+    # BUCKETS while the backward pass is still running. Every cross-GPU launch goes to ONE dedicated
+    # lane (COMM_LANE) in ONE global order that is identical on every rank — including ranks with an
+    # empty share of the batch, which replay just this sequence — so two ranks can never wait on each
+    # other's not-yet-launched kernel in opposite orders. Only the last launch of each network (its
+    # first layers, the one-shot vector tail and, for the last network, the loss scalars) is exposed.
+    bucketed = two and be.fused
+    comm_requests = []   # (network, bucket index, [event ops])
 
     def full(n, lanes=None):
       e = self.ex[n]
-      detach = opt_on_wgrad_lane and lanes is not None
       hook = None
-      if detach:
-        # bucketed: as soon as the lowest layer of a bucket has been processed, its reduce +
-        # Adam + broadcast kernel is queued on the wgrad lane (behind that layer's wgrad GEMMs,
-        # after an event that covers the norm / bias gradients written on the main lane)
+      if bucketed:
         bs = be.buckets[n]
         first = {j: k for k, (j, _, _) in enumerate(bs)}
+        main_lane = lanes[0] if lanes is not None else (0 if n in ("G", "Y") else 1)
 
         def hook(j):
           k = first.get(j)
           if k is None:
             return
-          ev = plan.add_event_record(f"sync.rec.{n}.bucket{k}", lanes[0])
-          plan.set_lane(lanes[1])
-          plan.add_event_wait(f"sync.wait.{n}.bucket{k}", lanes[1], ev)
-          be.emit_optimizer(plan, n, bucket=k, finish=(k == len(bs) - 1))
-          plan.set_lane(lanes[0])
+          evs = [plan.add_event_record(f"sync.rec.{n}.bucket{k}.main", main_lane)]
+          if lanes is not None:
+            evs.append(plan.add_event_record(f"sync.rec.{n}.bucket{k}.wgrad", lanes[1]))
+          comm_requests.append((n, k, evs))
 
       if n in ("G", "F"):
-        e.backward(plan, 0, 3 * b, wgrad=True, lanes=lanes, join_wgrad=not detach, on_layer_done=hook)
+        e.backward(plan, 0, 3 * b, wgrad=True, lanes=lanes, join_wgrad=not bucketed, on_layer_done=hook)
       else:
-        e.backward(plan, 0, 2 * b, wgrad=True, gout_is_dy=True, lanes=lanes, join_wgrad=not detach,
+        e.backward(plan, 0, 2 * b, wgrad=True, gout_is_dy=True, lanes=lanes, join_wgrad=not bucketed,
                    on_layer_done=hook)
       self.marks[f"{n}_bwd_end"] = plan.size()
-      if not detach:
+      if not bucketed:
         be.emit_optimizer(plan, n)
       self.marks[f"{n}_opt_end"] = plan.size()
 
@@ -191,6 +193,14 @@ class StepPlan:
       wl = be.wgrad_lanes
       lane(0); adv("Y", "G"); full("G", (0, 2) if wl else None); full("Y", (0, 2) if wl else None)
       lane(1); adv("X", "F"); full("F", (1, 3) if wl else None); full("X", (1, 3) if wl else None)
+      if bucketed:
+        ready = {(n, k): evs for n, k, evs in comm_requests}
+        assert len(ready) == len(be.comm_order()), (sorted(ready), be.comm_order())
+        plan.set_lane(COMM_LANE)
+        for n, k in be.comm_order():
+          for ev in ready[(n, k)]:
+            plan.add_event_wait(f"sync.wait.{n}.bucket{k}", COMM_LANE, ev)
+          be.emit_optimizer(plan, n, bucket=k)
       join("bwd")
     else:
       adv("Y", "G"); adv("X", "F")
@@ -260,10 +270,14 @@ class NativeBackend:
       for n in NETS:
         bs = self.plan_buckets(n)
         asc = sorted((lo, hi) for _, lo, hi in bs)
-        self.symm.set_buckets(n, asc)
+        self.symm.set_buckets(n, asc, vec_lo=self.state[n].layout.vec_lo)
         self.buckets[n] = bs
         self.bucket_index[n] = [asc.index((lo, hi)) for _, lo, hi in bs]
+    # loss / metric slots: on the fused path they live in peer-readable memory and the last fused
+    # launch of a step leaves their sums over ranks in symm.scalars_sum (no NCCL call, no host sync)
+    self.slots = self.symm.scalars if self.fused else torch.zeros(NUM_SLOTS, device=self.device)
     self._opt_only_plan = None
+    self._scalar_plan = None
     self._plans: Dict[int, StepPlan] = {}
     self._launches = 0
     torch.cuda.synchronize(self.device)
@@ -276,37 +290,51 @@ class NativeBackend:
     is reduced as soon as its first (lowest) layer has been processed."""
     st = self.state[n]
     layers = st.layout.spec.layers
-    offs = [st.layout.seg(l, "kernel").offset for l in layers] + [st.n]
-    want = int(os.environ.get("B2_AR_BUCKETS", "4" if n in ("G", "F") else "2"))
-    target = st.n / max(1, want)
-    out, hi = [], st.n
+    end = st.layout.vec_lo                      # kernels only; the vector tail is one-shot
+    offs = [st.layout.seg(l, "kernel").offset for l in layers] + [end]
+    want = 4 if n in ("G", "F") else 2
+    target = end / max(1, want)
+    out, hi = [], end
     for j in range(len(layers) - 1, -1, -1):
       if j == 0 or (hi - offs[j] >= target and len(out) < want - 1):
         out.append((j, offs[j] if j else 0, hi))
         hi = offs[j]
     return out
 
-  def emit_optimizer(self, plan, n: str, bucket: Optional[int] = None, finish: bool = True):
+  def comm_order(self) -> List[tuple]:
+    """Global order of the fused cross-GPU launches of one step: [(network, bucket index)], the
+    generators' buckets interleaved (they become ready alternately on the two main lanes), then
+    the discriminators'. Identical on every rank by construction."""
+    out = []
+    for pair in (("G", "F"), ("Y", "X")):
+      for k in range(max(len(self.buckets[n]) for n in pair)):
+        out += [(n, k) for n in pair if k < len(self.buckets[n])]
+    return out
+
+  def emit_optimizer(self, plan, n: str, bucket: Optional[int] = None):
     """Optimizer ops of network n. Fused path: ``bucket`` selects ONE all-reduce bucket (index into
-    plan_buckets(n)); ``finish`` adds the per-step tail (step counter, derived weights)."""
+    plan_buckets(n)); the network's last bucket also updates the one-shot vector tail, carries the
+    loss-scalar sums (SCALAR_NET) and is followed by the per-step tail (step counter, derived weights)."""
     st = self.state[n]
-    fused = self.fused and os.environ.get("B2_AR_SKIP", "0") != "1"   # B2_AR_SKIP: timing experiment only
-    if fused and bucket is not None:
-      _, lo, hi = self.buckets[n][bucket]
-      plan.add_mask_grad(f"opt.{n}.mask[{lo}:{hi}]", st.g.data_ptr() + 4 * lo, st.mask.data_ptr() + lo, hi - lo)
-      self.symm.emit_allreduce_adam(plan, n, st, bucket=self.bucket_index[n][bucket], **ADAM)
-    else:
-      plan.add_mask_grad(f"opt.{n}.mask", st.g.data_ptr(), st.mask.data_ptr(), st.n)
-      if fused:
-        self.symm.emit_allreduce_adam(plan, n, st, **ADAM)
-      else:
-        plan.add_adam(f"opt.{n}.adam", st.w.data_ptr(), st.m.data_ptr(), st.v.data_ptr(), st.g.data_ptr(),
-                      st.wb.data_ptr(), st.step.data_ptr(), ADAM["lr"], ADAM["b1"], ADAM["b2"], ADAM["eps"],
-                      1.0, st.n)
-        plan.add_memset(f"zero.{n}.grads", st.g.data_ptr(), st.n * 4)
-    if finish:
-      plan.add_step_increment(f"opt.{n}.step", st.step.data_ptr())
-      st.refresh_derived_ops(plan, f"opt.{n}")
+    if self.fused:
+      ks = range(len(self.buckets[n])) if bucket is None else [bucket]
+      for k in ks:
+        finish = k == len(self.buckets[n]) - 1
+        _, lo, hi = self.buckets[n][k]
+        plan.add_mask_grad(f"opt.{n}.mask[{lo}:{hi}]", st.g.data_ptr() + 4 * lo, st.mask.data_ptr() + lo, hi - lo)
+        self.symm.emit_allreduce_adam(plan, n, st, bucket=self.bucket_index[n][k], vectors=finish,
+                                      scalars=finish and n == SCALAR_NET, exposed=finish, **ADAM)
+        if finish:
+          plan.add_step_increment(f"opt.{n}.step", st.step.data_ptr())
+          st.refresh_derived_ops(plan, f"opt.{n}")
+      return
+    plan.add_mask_grad(f"opt.{n}.mask", st.g.data_ptr(), st.mask.data_ptr(), st.n)
+    plan.add_adam(f"opt.{n}.adam", st.w.data_ptr(), st.m.data_ptr(), st.v.data_ptr(), st.g.data_ptr(),
+                  st.wb.data_ptr(), st.step.data_ptr(), ADAM["lr"], ADAM["b1"], ADAM["b2"], ADAM["eps"],
+                  1.0, st.n)
+    plan.add_memset(f"zero.{n}.grads", st.g.data_ptr(), st.n * 4)
+    plan.add_step_increment(f"opt.{n}.step", st.step.data_ptr())
+    st.refresh_derived_ops(plan, f"opt.{n}")
 
   # ---------------------------------------------------------------- plans
   def plan_for(self, b: int) -> StepPlan:
@@ -320,8 +348,25 @@ class NativeBackend:
   def _stream(self) -> int:
     return torch.cuda.current_stream(self.device).cuda_stream
 
-  def _results(self, sp: StepPlan, with_errors: bool) -> Dict[str, torch.Tensor]:
-    s = sp.slots.clone()
+  @property
+  def reduces_internally(self) -> bool:
+    """True when step results are already summed over replicas (fused path: loss-scalar side
+    channel of the last fused launch) — callers must not reduce them again."""
+    return self.fused
+
+  def reduce_results(self, d: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """SUM step results over replicas (main.py:264-267): a no-op on the fused path, one packed
+    NCCL all-reduce on the baseline path."""
+    return d if self.fused else self.strategy.reduce_dict(d)
+
+  def collective(self) -> str:
+    """'fused-nvls' | 'fused-p2p' | 'nccl' | 'none' — what the gradient path of this run is."""
+    if self.world == 1:
+      return "none"
+    return self.symm.collective() if self.fused else "nccl"
+
+  def _results(self, sp: Optional[StepPlan], with_errors: bool, reduced: bool = True) -> Dict[str, torch.Tensor]:
+    s = (self.symm.scalars_sum if (self.fused and reduced) else self.slots).clone()
     r = OrderedDict([
         ("loss_G/loss", s[0]), ("loss_G/cycle", s[1]), ("loss_G/identity", s[2]),
         ("loss_G/total", s[0:3].sum()),
@@ -386,37 +431,50 @@ class NativeBackend:
 
   def _empty_train_step(self):
     """A replica with an empty share of a partial batch still joins the collectives."""
-    for n in NETS:
-      st = self.state[n]
-      if self.world > 1 and not self.fused:
-        self.strategy.all_reduce_sum(st.g)
-      # run just the optimizer ops of any existing plan (gradients are zero locally)
     s = self._stream()
     if self.fused:
-      # the bucketed optimizer launches are interleaved with the backward pass in the step plan:
-      # replay them from an optimizer-only plan, bucket by bucket in the same order as the peers
+      # replay exactly the cross-GPU launch sequence of the step plan (comm_order), on one stream:
+      # local gradients and loss slots are zero, the results are the sums over the other replicas
       if self._opt_only_plan is None:
         plan = nv.load().Plan()
-        for n in NETS:
-          for k in range(len(self.buckets[n])):
-            self.emit_optimizer(plan, n, bucket=k, finish=(k == len(self.buckets[n]) - 1))
+        plan.add_memset("zero.slots", self.slots.data_ptr(), NUM_SLOTS * 4)
+        for n, k in self.comm_order():
+          self.emit_optimizer(plan, n, bucket=k)
         self._opt_only_plan = plan
       self._opt_only_plan.run(0, -1, s, False)
-      return self._zero_results(False)
+      return self._results(None, with_errors=False)
+    for n in NETS:
+      if self.world > 1:
+        self.strategy.all_reduce_sum(self.state[n].g)
+    # run just the optimizer ops of any existing plan (gradients are zero locally)
     sp = self.plan_for(max(self._plans.keys(), default=1))
     for n in NETS:
       sp.plan.run(sp.marks[f"{n}_bwd_end"], sp.marks[f"{n}_opt_end"], s, False)
     return self._zero_results(False)
 
+  def _reduce_slots(self):
+    """Fused path, steps without an optimizer launch (test step): stand-alone one-shot SUM of the
+    loss slots over ranks (same peer-memory kernel, scalar side channel only)."""
+    if self._scalar_plan is None:
+      plan = nv.load().Plan()
+      self.symm.emit_scalar_reduce(plan)
+      self._scalar_plan = plan
+    self._scalar_plan.run(0, -1, self._stream(), False)
+
   @torch.no_grad()
   def test_step(self, x: torch.Tensor, y: torch.Tensor) -> Dict[str, torch.Tensor]:
     b = x.shape[0]
     if b == 0:
-      return self._zero_results(True)
-    sp = self.plan_for(b)
-    self._load_inputs(sp, x, y)
-    sp.plan.run(0, sp.marks["test_end"], self._stream(), False)
-    return self._results(sp, with_errors=True)
+      if not self.fused:
+        return self._zero_results(True)
+      self.slots.zero_()
+    else:
+      sp = self.plan_for(b)
+      self._load_inputs(sp, x, y)
+      sp.plan.run(0, sp.marks["test_end"], self._stream(), False)
+    if self.fused:
+      self._reduce_slots()
+    return self._results(None, with_errors=True)
 
   @torch.no_grad()
   def cycle_step(self, x: torch.Tensor, y: torch.Tensor):

@@ -494,9 +494,6 @@ class NetExec:
       _, idx = st.derived[f"{self.tag}.L{j}.dgradW"]
       plan.add_scatter_add(f"{name}.scatter", st.g.data_ptr(), scratch.data_ptr(), idx.data_ptr(), idx.numel())
       return
-    if no.wgrad_row_ok(l, wo):
-      no.add_wgrad_row(plan, name, dY, src, n0, nimg, l.cin, l.cout, dw, ldw)
-      return
     kbw, kbh = nv.tile_shape(ho, wo, 64)
     dy_map = dY.tmap_interior(kbw, kbh, n0, nimg)
     if is_small_cin(l):

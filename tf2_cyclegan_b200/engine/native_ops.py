@@ -190,24 +190,3 @@ def add_wgrad(plan, name: str, dy_map, a_maps: Sequence[bytes], taps: Sequence[T
 
 def fptr(t: Optional[torch.Tensor]) -> int:
   return 0 if t is None else t.data_ptr()
-
-
-def add_wgrad_row(plan, name: str, dY: Buf, src: Buf, n0: int, nimg: int, cin: int, cout: int,
-                  dw_ptr: int, ldw: int, target_ctas: Optional[int] = None):
-  """Tap-shared 2-CTA wgrad of a 3x3 stride-1 reflect-padded conv (csrc/wgrad_row.cu)."""
-  import os
-  target_ctas = target_ctas or int(os.environ.get("B2_WGRAD_CTAS", "0"))
-  base = 2 * (cout // 256) * (cin // 128) * 3
-  total_kt = (dY.w // 64) * dY.h * nimg
-  ksplit = (max(1, min(total_kt, (target_ctas + base - 1) // base)) if target_ctas
-            else pick_ksplit(base, total_kt))
-  return plan.add_wgrad_row(name, dY.tmap_interior(64, 1, n0, nimg), src.tmap_padded(66, 1, n0, nimg),
-                            dY.w // 64, dY.h, nimg, cin, cout, dw_ptr, ldw, ksplit)
-
-
-def wgrad_row_ok(l, wo: int) -> bool:
-  import os
-  # measured on B200 (profiles/): correct, but ~8% slower than the generic 2-CTA kernel because both
-  # are bound by shared-memory operand bandwidth, not by L2 bytes -> opt-in only
-  return (os.environ.get("B2_WGRAD_ROW", "0") == "1" and l.kind == "conv" and l.k == 3 and l.stride == 1
-          and l.pad == "reflect" and l.cin % 128 == 0 and l.cout % 256 == 0 and wo % 64 == 0)

@@ -96,10 +96,19 @@ class FlatLayout:
       off = seg.offset + seg.numel
       off = (off + ALIGN - 1) // ALIGN * ALIGN
 
+    # kernels first (layer order: the gradient all-reduce buckets are cut at layer boundaries), then
+    # every small vector (biases, InstanceNorm gamma / beta) in ONE tail region [vec_lo, numel): on
+    # the fused multi-GPU path the kernels are ZeRO-1 sharded (two-shot), the tail is updated by
+    # every rank on its own replica (one-shot), so gamma / beta / bias fp32 masters stay current on
+    # every rank (csrc/allreduce_adam.cuh)
     for l in spec.layers:
       p = f"layer_with_weights-{l.lw_index}"
       kind, shape = kernel_flat_shape(l)
       add(Segment(f"{p}/kernel", kind, off, shape, l.kernel_shape, l))
+    off = (off + 127) // 128 * 128
+    self.vec_lo = off
+    for l in spec.layers:
+      p = f"layer_with_weights-{l.lw_index}"
       if l.bias:
         add(Segment(f"{p}/bias", "vector", off, (l.cout,), (l.cout,), l))
       if l.norm:

@@ -21,7 +21,19 @@ import torch.distributed as dist
 
 from .strategy import Strategy
 
-NUM_BLOCKS = int(os.environ.get("B2_ALLREDUCE_BLOCKS", "24"))
+MAX_BLOCKS = 148        # signal-pad sizing: one flag set per block and phase
+NUM_SCALARS = 16        # loss / metric slots reduced through the side channel
+
+
+def default_blocks(nbytes: int, exposed: bool) -> int:
+  """CTAs (256 threads) of one fused reduce + Adam launch. Launches that run under the backward pass
+  stay small (they compete with the GEMMs for SMs and only need to keep ~1 MB of peer loads in
+  flight); the last, exposed launch of a network may use more."""
+  env = os.environ.get("B2_ALLREDUCE_BLOCKS")
+  if env:
+    return max(1, min(MAX_BLOCKS, int(env)))
+  want = max(4, min(64, nbytes // (256 * 1024)))     # >= 256 KB of fp32 gradients per CTA
+  return min(MAX_BLOCKS, want * 2) if exposed else want
 
 
 class SymmetricBuffers:
@@ -33,12 +45,19 @@ class SymmetricBuffers:
     self.rank, self.world = strategy.rank, strategy.world_size
     if self.world > 8:
       raise RuntimeError("fused all-reduce supports up to 8 ranks (one NVSwitch domain)")
-    need = 2 * NUM_BLOCKS * self.world * 4
+    need = 2 * MAX_BLOCKS * self.world * 4
     if symm_mem.get_signal_pad_size() < need:
       symm_mem.set_signal_pad_size(max(need, 16384))
     self.handles: Dict[str, Tuple[object, object]] = {}
     self.buckets: Dict[str, List[Tuple[int, int]]] = {}
+    self.vec_lo: Dict[str, int] = {}
     self.use_multicast = os.environ.get("B2_NVLS", "auto")
+    # loss-scalar side channel: every rank's slots are peer-readable; the sums land in `scalars_sum`
+    self.scalars = symm_mem.empty(NUM_SCALARS, dtype=torch.float32, device=strategy.device)
+    self.scalars.zero_()
+    self.h_scalars = symm_mem.rendezvous(self.scalars, dist.group.WORLD)
+    self.scalars_sum = torch.zeros(NUM_SCALARS, device=strategy.device)
+    self._dummy: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
 
   def alloc(self, name: str, numel: int):
     sm = self.symm_mem
@@ -52,6 +71,12 @@ class SymmetricBuffers:
     self.handles[name] = (hg, hw)
     return g, wb
 
+  def collective(self) -> str:
+    """What the gradient path of this run is: 'fused-nvls' | 'fused-p2p'."""
+    for name in self.handles:
+      return "fused-nvls" if self.multicast_ptrs(name)[0] else "fused-p2p"
+    return "fused-p2p"
+
   def multicast_ptrs(self, name: str) -> Tuple[int, int]:
     hg, hw = self.handles[name]
     if self.use_multicast in ("0", "off"):
@@ -64,38 +89,70 @@ class SymmetricBuffers:
       return 0, 0
     return mg, mw
 
-  def set_buckets(self, name: str, bounds):
-    """Split network ``name``'s flat buffer into all-reduce buckets [lo, hi) (multiples of 8
-    elements, ascending, covering [0, n)). Every bucket is reduced / updated by its own kernel
-    launch as soon as its gradients are final, and is sharded over the ranks on its own — so the
-    optimizer-state ownership map (ZeRO-1) is per bucket: see :meth:`owned_ranges`."""
+  def set_buckets(self, name: str, bounds, vec_lo: Optional[int] = None):
+    """Split the two-shot part [0, vec_lo) of network ``name``'s flat buffer into all-reduce buckets
+    [lo, hi) (multiples of 8 elements, ascending, covering it). Every bucket is reduced / updated
+    by its own kernel launch as soon as its gradients are final, and is sharded over the ranks on
+    its own — so the optimizer-state ownership map (ZeRO-1) is per bucket: see :meth:`owned_ranges`.
+    [vec_lo, n) is the one-shot (replicated) tail."""
     bounds = [(int(lo), int(hi)) for lo, hi in bounds]
     assert all(lo % 8 == 0 and hi % 8 == 0 and lo < hi for lo, hi in bounds), bounds
     assert bounds[0][0] == 0 and all(a[1] == b[0] for a, b in zip(bounds, bounds[1:])), bounds
+    if vec_lo is not None:
+      assert bounds[-1][1] == vec_lo and vec_lo % 8 == 0, (bounds, vec_lo)
+      self.vec_lo[name] = int(vec_lo)
     self.buckets[name] = bounds
 
   def bucket_list(self, name: str, n: int):
-    return self.buckets.get(name) or [(0, n)]
+    return self.buckets.get(name) or [(0, self.vec_lo.get(name, n))]
 
   def emit_allreduce_adam(self, plan, name: str, st, lr: float, b1: float, b2: float, eps: float,
-                          bucket: Optional[int] = None):
-    """One fused reduce + Adam + broadcast launch over the whole buffer (``bucket`` None: all
-    buckets, back to back) or over one bucket (pointers offset to the bucket start)."""
+                          bucket: Optional[int] = None, vectors: Optional[bool] = None,
+                          scalars: bool = False, exposed: bool = False):
+    """Fused reduce + Adam + broadcast launches of network ``name``: every bucket back to back
+    (``bucket`` None) or ONE bucket. ``vectors``: also update the one-shot tail [vec_lo, n) in the
+    (last) launch (default: when all buckets are emitted); ``scalars``: carry the loss-scalar sums."""
     hg, hw = self.handles[name]
     mg, mw = self.multicast_ptrs(name)
     todo = self.bucket_list(name, st.n)
+    if vectors is None:
+      vectors = bucket is None
     if bucket is not None:
       todo = [todo[bucket]]
-    for lo, hi in todo:
-      plan.add_allreduce_adam(f"opt.{name}.fused_allreduce_adam[{lo}:{hi}]",
-                              [int(p) + 4 * lo for p in hg.buffer_ptrs],
-                              [int(p) + 2 * lo for p in hw.buffer_ptrs], [int(p) for p in hg.signal_pad_ptrs],
-                              st.w.data_ptr() + 4 * lo, st.m.data_ptr() + 4 * lo, st.v.data_ptr() + 4 * lo,
-                              st.step.data_ptr(), lr, b1, b2, eps, hi - lo, self.rank, self.world,
-                              NUM_BLOCKS, mg + 4 * lo if mg else 0, mw + 2 * lo if mw else 0)
+    v_lo = self.vec_lo.get(name, st.n)
+    for k, (lo, hi) in enumerate(todo):
+      last = k == len(todo) - 1
+      vec = (v_lo, st.n - v_lo) if (vectors and last) else (0, 0)
+      sc = scalars and last
+      plan.add_allreduce_adam(f"opt.{name}.fused_allreduce_adam[{lo}:{hi}]" + ("+vec" if vec[1] else "") +
+                              ("+scalars" if sc else ""),
+                              [int(p) for p in hg.buffer_ptrs], [int(p) for p in hw.buffer_ptrs],
+                              [int(p) for p in hg.signal_pad_ptrs],
+                              st.w.data_ptr(), st.m.data_ptr(), st.v.data_ptr(), st.step.data_ptr(),
+                              lr, b1, b2, eps, lo, hi - lo, vec[0], vec[1],
+                              [int(p) for p in self.h_scalars.buffer_ptrs] if sc else [],
+                              self.scalars_sum.data_ptr() if sc else 0, NUM_SCALARS if sc else 0,
+                              self.rank, self.world, default_blocks(4 * (hi - lo), exposed), mg, mw)
+
+  def emit_scalar_reduce(self, plan, name: str = "scalars.allreduce"):
+    """Stand-alone one-shot SUM of the loss slots (test step: no optimizer launch to ride on)."""
+    if self._dummy is None:
+      self._dummy = self.alloc("__scalars__", 128)
+    hg, hw = self.handles["__scalars__"]
+    z = self.scalars_sum
+    plan.add_allreduce_adam(name, [int(p) for p in hg.buffer_ptrs], [int(p) for p in hw.buffer_ptrs],
+                            [int(p) for p in hg.signal_pad_ptrs], z.data_ptr(), z.data_ptr(), z.data_ptr(),
+                            self._zero_step().data_ptr(), 0.0, 0.5, 0.9, 1e-7, 0, 0, 0, 0,
+                            [int(p) for p in self.h_scalars.buffer_ptrs], self.scalars_sum.data_ptr(),
+                            NUM_SCALARS, self.rank, self.world, 1, 0, 0)
+
+  def _zero_step(self) -> torch.Tensor:
+    if not hasattr(self, "_zstep"):
+      self._zstep = torch.zeros(1, dtype=torch.int32, device=self.strategy.device)
+    return self._zstep
 
   def shard_bounds(self, n: int, rank: Optional[int] = None) -> Tuple[int, int]:
-    """This rank's shard of a buffer (or bucket) of n elements — mirrors the kernel."""
+    """This rank's shard of a bucket of n elements — mirrors the kernel."""
     rank = self.rank if rank is None else rank
     n8 = n // 8
     per = (n8 + self.world - 1) // self.world
@@ -103,13 +160,16 @@ class SymmetricBuffers:
     return lo * 8, min(n8, lo + per) * 8
 
   def owned_ranges(self, name: str, n: int):
-    """[lo, hi) ranges of network ``name``'s flat buffers whose fp32 master / moments live on
-    this rank: its shard of every bucket."""
+    """[lo, hi) ranges of network ``name``'s flat buffers whose fp32 master / moments this rank
+    contributes to a gather: its shard of every bucket; the replicated tail is taken from rank 0."""
     out = []
     for lo, hi in self.bucket_list(name, n):
       a, b = self.shard_bounds(hi - lo)
       if b > a:
         out.append((lo + a, lo + b))
+    v_lo = self.vec_lo.get(name, n) if name is not None else n
+    if v_lo < n and self.rank == 0:
+      out.append((v_lo, n))
     return out
 
   def gather_sharded(self, t: torch.Tensor, name: Optional[str] = None) -> torch.Tensor:

@@ -8,14 +8,9 @@ from tf2_cyclegan_b200.ops import native as nv
 ap = argparse.ArgumentParser()
 ap.add_argument("--images", type=int, default=12)
 ap.add_argument("--iters", type=int, default=20)
-ap.add_argument("--variant", type=int, default=None,
-                help="tuning variant of the InstanceNorm kernels (csrc/elementwise.cu: U / blocks per SM / "
-                     "register double buffering); default: B2_EW_VARIANT or 0. Sweep: for v in 0 1 2 3")
+ap.add_argument("--no_flush", action="store_true", help="keep L2 warm between iterations (in-step behaviour)")
 a = ap.parse_args()
 C = nv.load()
-if a.variant is not None:
-  C.set_ew_variant(a.variant)
-print(f"B2_EW_VARIANT={C.ew_variant()}")
 n, h, c = a.images, 64, 256
 hbm = 6572.9
 try:
@@ -43,12 +38,13 @@ p = C.Plan(); p.add_in_bwd_reduce("r2", g1.view(), 1, g2.view(), x.view(), stats
 p = C.Plan(); p.add_in_bwd_apply("ap", dy.view(), x.view(), stats.data_ptr(), bst.data_ptr(), gam.data_ptr(), inv, 1e-3, dx.view(), dg.data_ptr(), db.data_ptr(), n, h, h, c); plans["in_bwd_apply"] = (p, 3 * E)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 s = torch.cuda.current_stream().cuda_stream
-print(f"B2_EW_BLOCKS={os.environ.get('B2_EW_BLOCKS', 'default')}")
+print(f"l2_flush={not a.no_flush}")
 for name, (plan, nbytes) in plans.items():
   for _ in range(3): plan.run(0, -1, s, False)
   ts = []
   for _ in range(a.iters):
-    flush.zero_()
+    if not a.no_flush:
+      flush.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); plan.run(0, -1, s, False); e1.record(); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))

@@ -60,9 +60,7 @@ no.add_conv_flat(p, "dgrad", dy.tmap_flat(), taps, c, w2, dxp.ptr(padded=True), 
 plans["dgrad"] = (p, 2.0 * n * h * h * 9 * c * c)
 kbw, kbh = nv.tile_shape(h, h, 64)
 p = C.Plan()
-if os.environ.get("B2_WGRAD_ROW", "0") == "1":
-  no.add_wgrad_row(p, "wgrad", dy, x, 0, n, c, c, dw.data_ptr(), 9 * c)
-else:
+if True:
   no.add_wgrad(p, "wgrad", dy.tmap_interior(kbw, kbh), [x.tmap_padded(kbw, kbh)], no.taps_conv(3, c),
                h // kbw, h // kbh, kbw, kbh, n, c, c, dw.data_ptr(), 9 * c)
 plans["wgrad"] = (p, 2.0 * n * h * h * 9 * c * c)
