@@ -16,7 +16,8 @@ MirroredStrategy(NCCL) + cuDNN build, tuned the way a careful PyTorch user would
     network (the zero-copy form of ``NcclAllReduce(num_packs=1)``), then a multi-tensor
     (``torch._foreach``) Keras-formula Adam (lr 2e-4, beta1 0.5, beta2 0.9, eps 1e-7 outside the
     bias correction) and a foreach refresh of the bf16 copies;
-  * the whole step (forward, backward, 4 all-reduces, 4 optimizers) captured in ONE CUDA graph.
+  * the whole step captured in CUDA graphs (one graph on 1 GPU; forward + backward and the optimizers
+    as two graphs around the four NCCL calls on several GPUs).
 
 It shares no code with the product engine (``tf2_cyclegan_b200``): plain ``torch.nn.functional``
 calls only. Architecture per cyclegan/model.py:129-213 (TF-SAME asymmetric padding, transposed-conv
@@ -185,7 +186,8 @@ class StandinCycleGAN:
   def _mse(self, target, d):
     return ((target - d.float()) ** 2).mean(dim=(1, 2, 3)).sum() / self.gbs
 
-  def _step_body(self):
+  def _fwd_bwd(self):
+    """Forward + the four backward passes; gradients land in the flat fp32 buffers."""
     N = self.nets
     G = lambda t: generator_forward(N["G"].P, t, self.n_res)
     Fn = lambda t: generator_forward(N["F"].P, t, self.n_res)
@@ -204,13 +206,26 @@ class StandinCycleGAN:
       net = N[name]
       grads = torch.autograd.grad(loss, net.leaves, retain_graph=True)
       torch._foreach_copy_(net.grad_views, list(grads))          # bf16 -> flat fp32 gradient buffer
-      if self.world > 1:
-        dist.all_reduce(net.grad)                                  # one packed SUM per network
-      net.adam()
     self.losses.copy_(torch.stack([G_loss, G_cycle, G_id, G_total, F_loss, F_cycle, F_id, F_total, X_loss, Y_loss]).detach())
 
+  def _reduce(self):
+    if self.world > 1:
+      for name in ("G", "F", "X", "Y"):
+        dist.all_reduce(self.nets[name].grad)                      # one packed SUM per network
+
+  def _optimize(self):
+    for name in ("G", "F", "X", "Y"):
+      self.nets[name].adam()
+
+  def _step_body(self):
+    self._fwd_bwd()
+    self._reduce()
+    self._optimize()
+
   def capture(self) -> bool:
-    """Warm up on a side stream (cuDNN autotune, lazy init), then capture the step in a CUDA graph."""
+    """Warm up on a side stream (cuDNN autotune, lazy init), then capture the step in CUDA graphs:
+    one graph on a single GPU; on several GPUs two graphs (forward + backward, optimizers) with the
+    four packed NCCL all-reduces issued between them (NCCL calls are kept out of the capture)."""
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
@@ -219,12 +234,20 @@ class StandinCycleGAN:
     torch.cuda.current_stream().wait_stream(s)
     torch.cuda.synchronize()
     try:
-      g = torch.cuda.CUDAGraph()
-      with torch.cuda.graph(g):
-        self._step_body()
-      self.graph = g
+      if self.world == 1:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+          self._step_body()
+        self.graph = (g,)
+      else:
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+          self._fwd_bwd()
+        with torch.cuda.graph(g2, pool=g1.pool()):
+          self._optimize()
+        self.graph = (g1, g2)
       return True
-    except Exception as e:  # pragma: no cover - depends on the NCCL / torch build
+    except Exception as e:  # pragma: no cover - depends on the torch build
       print(f"[standin] CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly")
       self.graph = None
       torch.cuda.synchronize()
@@ -235,8 +258,12 @@ class StandinCycleGAN:
     # NHWC fp32 -> logical NCHW bf16 in channels_last memory: a cast, no transpose
     self.x.copy_(x_nhwc.permute(0, 3, 1, 2))
     self.y.copy_(y_nhwc.permute(0, 3, 1, 2))
-    if self.graph is not None:
-      self.graph.replay()
-    else:
+    if self.graph is None:
       self._step_body()
+    elif len(self.graph) == 1:
+      self.graph[0].replay()
+    else:
+      self.graph[0].replay()
+      self._reduce()
+      self.graph[1].replay()
     return self.losses

@@ -175,6 +175,8 @@ def main():
   ap.add_argument("--fused_allreduce", default="on", choices=["auto", "on", "off"],
                   help="gradient path on > 1 GPU: 'on' (default) = the fused peer-memory reduce + Adam kernel or "
                        "fail loudly; 'off' = packed NCCL all-reduce + Adam kernel (baseline path)")
+  ap.add_argument("--ar_mode", default=None, choices=["push", "pull"],
+                  help="form of the fused gradient reduction (default: parallel.fused_allreduce.DEFAULT_MODE)")
   ap.add_argument("--no_e2e", action="store_true")
   a = ap.parse_args()
   if a.impl == "reference":
@@ -198,6 +200,9 @@ def main():
       return subprocess.call(cmd)
     raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}")
 
+  if a.ar_mode:
+    from tf2_cyclegan_b200.parallel import fused_allreduce
+    fused_allreduce.DEFAULT_MODE = a.ar_mode
   strategy = Strategy(device="cuda")
   dev = strategy.device
   gbs = a.batch_size * world
@@ -314,7 +319,7 @@ def main():
     }
     if a.impl == "native":
       names = be.plan_for(a.batch_size).names
-      out["collective"] = be.collective()              # fused-nvls | fused-p2p | nccl | none
+      out["collective"] = be.collective()              # fused-<push|pull>-<nvls|p2p> | nccl | none
       out["allreduce_adam_launches_per_step"] = sum(1 for n in names if "fused_allreduce_adam" in n)
       out["nccl_calls_per_step"] = 0 if (world == 1 or be.fused) else 5   # 4 gradient + 1 scalar all-reduce
       out["config"]["collective"] = out["collective"]

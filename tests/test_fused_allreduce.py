@@ -38,8 +38,10 @@ def state(n, w0):
   return s
 
 # ---- 1. two-shot (ZeRO-1) region + one-shot (replicated) vector tail + loss-scalar side channel
-for n, tail in ((1024, 0), (8 * 1000 + 8 * 3, 8 * 40), (11_400_000 // 8 * 8, 10_496)):
-  name = f"t{n}"
+cases = [(mode, n, tail) for mode in ("push", "pull")
+         for n, tail in ((1024, 0), (8 * 1000 + 8 * 3, 8 * 40), (11_400_000 // 8 * 8, 10_496))]
+for mode, n, tail in cases:
+  name = f"t{n}{mode}"
   g, wb = sb.alloc(name, n)
   vec_lo = n - tail
   if tail:
@@ -49,7 +51,7 @@ for n, tail in ((1024, 0), (8 * 1000 + 8 * 3, 8 * 40), (11_400_000 // 8 * 8, 10_
   s = state(n, w0)
   wb.copy_(w0.to(torch.bfloat16))
   plan = C.Plan()
-  sb.emit_allreduce_adam(plan, name, s, 2e-4, 0.5, 0.9, 1e-7, scalars=True)
+  sb.emit_allreduce_adam(plan, name, s, 2e-4, 0.5, 0.9, 1e-7, scalars=True, mode=mode)
   plan.add_step_increment("inc", s.step.data_ptr())
   ref_w = {"w": w0.clone()}
   opt = KerasAdam()
@@ -72,7 +74,7 @@ for n, tail in ((1024, 0), (8 * 1000 + 8 * 3, 8 * 40), (11_400_000 // 8 * 8, 10_
     es = (sb.scalars_sum - sl_tot).abs().max().item()
     if not (e1 < 5e-5 and e2 < 2e-2 and gz == 0.0 and es < 1e-3):   # fp32 sum order differs from NCCL
       ok = False
-      print(f"rank {st.rank} n={n} it={it}: master err {e1}, bf16 err {e2}, grad residue {gz}, scalar err {es}")
+      print(f"rank {st.rank} {mode} n={n} it={it}: master err {e1}, bf16 err {e2}, grad residue {gz}, scalar err {es}")
     if tail:
       # the replicated tail: fp32 master, moments and bf16 copy bit-identical on every rank and current
       for nm, t in (("w", s.w[vec_lo:]), ("m", s.m[vec_lo:]), ("v", s.v[vec_lo:]), ("wb", wb[vec_lo:])):

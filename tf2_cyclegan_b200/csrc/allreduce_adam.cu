@@ -1,9 +1,10 @@
 // Two-shot all-reduce fused with the optimizer, executed from inside ONE kernel
 // with peer-to-peer (or NVLS multimem) loads and stores over NVLink/NVSwitch:
 //
-//   barrier(peers)                      all ranks' gradients are final
+//   (push form) stage_q[me][..] = my grad of shard q, for every peer q: posted peer stores
+//   barrier(peers)                      all ranks' gradients are final (pull) / have landed (push)
 //   for i in my shard:                  rank r owns elements [r*n/W, (r+1)*n/W)
-//     g  = sum_p grad_p[i]              P2P loads   | multimem.ld_reduce (in-switch sum)
+//     g  = sum_p grad_p[i]              pull: P2P loads | multimem.ld_reduce; push: local staging reads
 //     w,m,v = keras_adam(w,m,v,g)       fp32 master + moments live only on the owner (ZeRO-1)
 //     w_bf16_p[i] = bf16(w) for all p   P2P stores  | multimem.st (switch broadcast)
 //   (one-shot part, small vectors)      every rank reduces + updates its replica, no broadcast
@@ -72,12 +73,20 @@ __device__ __forceinline__ void mc_st_bf16x8(__nv_bfloat16* p, uint4 v) {
 }
 __device__ __forceinline__ void acc4(float4& a, const float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 
+// Keras-Adam, 4 elements. sqrt / divide use the SFU approximations (2 MUFU + a few FMAs per element
+// instead of ~25 instructions for the IEEE forms): with a handful of CTAs the fused kernel is otherwise
+// bound by this arithmetic, not by NVLink or HBM. Relative error ~2^-22, far below the bf16 weights.
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void adam4(float4& w, float4& m, float4& v, const float4 g, float lr_t,
                                       float b1, float b2, float eps) {
 #define B2_ADAM1(c)                                  \
   m.c = b1 * m.c + (1.f - b1) * g.c;                 \
   v.c = b2 * v.c + (1.f - b2) * g.c * g.c;           \
-  w.c = w.c - lr_t * m.c / (sqrtf(v.c) + eps);
+  w.c = w.c - __fdividef(lr_t * m.c, fast_sqrt(v.c) + eps);
   B2_ADAM1(x) B2_ADAM1(y) B2_ADAM1(z) B2_ADAM1(w)
 #undef B2_ADAM1
 }
@@ -99,20 +108,72 @@ __device__ __forceinline__ uint4 adam8(const AllreduceAdamParams& p, long long i
   return pk;
 }
 
-constexpr int kArThreads = 256;
-constexpr int kArUnroll = 2;    // 8-element chunks per thread per iteration (independent peer loads in flight)
+// pull form: 256 threads x up to 128 registers (many peer loads in flight per thread).
+// push form: a CTA of the collective owns its SM anyway (the conv GEMMs use the whole register file, so
+// nothing co-resides with it), therefore it uses ALL of it: 1024 threads x 64 registers — four times
+// the loads in flight per occupied SM, so a launch needs a quarter of the SMs for the same rate.
+constexpr int kPullThreads = 256;
+constexpr int kPushThreads = 1024;
+constexpr int kPushUnroll = 4;  // push phase: chunks per thread per iteration (local loads in flight)
 
-__global__ void __launch_bounds__(kArThreads, 1) allreduce_adam_kernel(const AllreduceAdamParams p) {
+__device__ __forceinline__ void st_peer_f4(float* p, const float4 v) {
+  asm volatile("st.global.relaxed.sys.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w) : "memory");
+}
+
+template <bool PUSH>
+__global__ void __launch_bounds__(PUSH ? kPushThreads : kPullThreads, 1)
+allreduce_adam_kernel(const AllreduceAdamParams p) {
+  constexpr int kArThreads = PUSH ? kPushThreads : kPullThreads;
+  constexpr int kArUnroll = PUSH ? 1 : 2;   // 8-element chunks per thread per iteration in the reduce / Adam loop
   const int t = *p.step + 1;
   const float lr_t = p.lr * sqrtf(1.f - powf(p.beta2, static_cast<float>(t))) /
                      (1.f - powf(p.beta1, static_cast<float>(t)));
-  // two-shot: shard of this rank, in units of 8 elements, and the slice of this block inside it
+  // two-shot: shard of this rank, in units of 8 elements, and the slice of this block inside it.
+  // Block b of every rank works on sub-slice b of every shard, so the per-block pairwise barriers
+  // below order exactly the data that block exchanges.
   const long long n8 = p.n / 8;
   const long long per_rank = (n8 + p.world - 1) / p.world;
   const long long r_begin = min(n8, per_rank * p.rank), r_end = min(n8, r_begin + per_rank);
-  const long long per_blk = (r_end - r_begin + gridDim.x - 1) / gridDim.x;
+  const long long per_blk = (per_rank + gridDim.x - 1) / gridDim.x;
   const long long b_begin = min(r_end, r_begin + per_blk * blockIdx.x);
   const long long b_end = min(r_end, b_begin + per_blk);
+  float* gl = p.grad[p.rank];
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  if constexpr (PUSH) {
+    // ---- push: my gradients of shard q, sub-slice b -> rank q's staging slot [me]; then zero them.
+    // Safe without an opening barrier: the closing barrier of the PREVIOUS launch on this lane (all
+    // cross-GPU launches share one lane and one global order) proves every peer has finished
+    // reading its staging buffer.
+    for (int dq = 1; dq < p.world; ++dq) {
+      const int q = (p.rank + dq) % p.world;          // staggered: at any time every rank targets another peer
+      const long long q_begin = min(n8, per_rank * q), q_end = min(n8, q_begin + per_rank);
+      const long long s0 = min(q_end, q_begin + per_blk * blockIdx.x), s1 = min(q_end, s0 + per_blk);
+      float* dst = p.stage[q] + (static_cast<long long>(p.rank) * per_rank - q_begin) * 8;   // + i8 * 8
+      for (long long i8 = s0 + threadIdx.x; i8 < s1; i8 += kArThreads * kPushUnroll) {
+        float4 a[kPushUnroll], b[kPushUnroll];
+#pragma unroll
+        for (int j = 0; j < kPushUnroll; ++j) {
+          const long long c8 = i8 + j * kArThreads;
+          if (c8 < s1) {
+            a[j] = *reinterpret_cast<const float4*>(gl + p.lo + c8 * 8);
+            b[j] = *reinterpret_cast<const float4*>(gl + p.lo + c8 * 8 + 4);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < kPushUnroll; ++j) {
+          const long long c8 = i8 + j * kArThreads;
+          if (c8 < s1) {
+            st_peer_f4(dst + c8 * 8, a[j]);
+            st_peer_f4(dst + c8 * 8 + 4, b[j]);
+            *reinterpret_cast<float4*>(gl + p.lo + c8 * 8) = z;
+            *reinterpret_cast<float4*>(gl + p.lo + c8 * 8 + 4) = z;
+          }
+        }
+      }
+    }
+  }
 
   block_barrier(p, 0);
 
@@ -127,7 +188,7 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_adam_kernel(const All
     p.sc_dst[threadIdx.x] = acc;
   }
 
-  // ---- two-shot region
+  // ---- two-shot region: reduce my shard, Adam, broadcast the bf16 weights
   for (long long i8 = b_begin + threadIdx.x; i8 < b_end; i8 += kArThreads * kArUnroll) {
     float4 g0[kArUnroll], g1[kArUnroll];
     long long idx[kArUnroll];
@@ -136,7 +197,28 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_adam_kernel(const All
       const long long c8 = i8 + j * kArThreads;
       idx[j] = c8 < b_end ? p.lo + c8 * 8 : -1;
     }
-    if (p.mc_grad != nullptr) {
+    if constexpr (PUSH) {
+      // local reads only: my own gradients + the world - 1 staging slots the peers filled
+      const float* st = p.stage[p.rank] - r_begin * 8 - p.lo;      // + slot * per_rank * 8 + idx
+#pragma unroll
+      for (int j = 0; j < kArUnroll; ++j)
+        if (idx[j] >= 0) {
+          g0[j] = *reinterpret_cast<const float4*>(gl + idx[j]);
+          g1[j] = *reinterpret_cast<const float4*>(gl + idx[j] + 4);
+          *reinterpret_cast<float4*>(gl + idx[j]) = z;
+          *reinterpret_cast<float4*>(gl + idx[j] + 4) = z;
+        }
+      for (int q = 0; q < p.world; ++q) {             // rank order: the sum does not depend on who owns it
+        if (q == p.rank) continue;
+        const float* sq = st + static_cast<long long>(q) * per_rank * 8;
+#pragma unroll
+        for (int j = 0; j < kArUnroll; ++j)
+          if (idx[j] >= 0) {
+            acc4(g0[j], *reinterpret_cast<const float4*>(sq + idx[j]));
+            acc4(g1[j], *reinterpret_cast<const float4*>(sq + idx[j] + 4));
+          }
+      }
+    } else if (p.mc_grad != nullptr) {
 #pragma unroll
       for (int j = 0; j < kArUnroll; ++j)
         if (idx[j] >= 0) {
@@ -145,7 +227,7 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_adam_kernel(const All
         }
     } else {
 #pragma unroll
-      for (int j = 0; j < kArUnroll; ++j) g0[j] = g1[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < kArUnroll; ++j) g0[j] = g1[j] = z;
       for (int q0 = 0; q0 < p.world; q0 += 2) {     // two peers' loads in flight together
         float4 a[2][kArUnroll], b[2][kArUnroll];
         const int qa = (p.rank + q0) % p.world;     // staggered so that peers are hit evenly
@@ -190,11 +272,11 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_adam_kernel(const All
   for (long long i8 = static_cast<long long>(blockIdx.x) * kArThreads + threadIdx.x; i8 < v8;
        i8 += static_cast<long long>(gridDim.x) * kArThreads) {
     const long long i = p.v_lo + i8 * 8;
-    float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+    float4 g0 = z, g1 = z;
     for (int q = 0; q < p.world; q += 2) {
       const bool two = q + 1 < p.world;
       const float4 a0 = ld_f4(p.grad[q] + i), b0 = ld_f4(p.grad[q] + i + 4);
-      float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = a1;
+      float4 a1 = z, b1 = z;
       if (two) { a1 = ld_f4(p.grad[q + 1] + i); b1 = ld_f4(p.grad[q + 1] + i + 4); }
       acc4(g0, a0); acc4(g1, b0);     // ((g + r0) + r1) ...: the same order on every rank
       acc4(g0, a1); acc4(g1, b1);
@@ -205,17 +287,16 @@ __global__ void __launch_bounds__(kArThreads, 1) allreduce_adam_kernel(const All
 
   block_barrier(p, 1);
 
-  // zero the slices (peer, block) of the local gradient buffer: every peer's block with this
-  // index has finished reading them (it passed the second barrier)
-  float* gl = p.grad[p.rank];
-  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int q = 0; q < p.world; ++q) {
-    const long long q_begin = min(n8, per_rank * q), q_end = min(n8, q_begin + per_rank);
-    const long long pb = (q_end - q_begin + gridDim.x - 1) / gridDim.x;
-    const long long s0 = min(q_end, q_begin + pb * blockIdx.x), s1 = min(q_end, s0 + pb);
-    for (long long i8 = s0 + threadIdx.x; i8 < s1; i8 += kArThreads) {
-      *reinterpret_cast<float4*>(gl + p.lo + i8 * 8) = z;
-      *reinterpret_cast<float4*>(gl + p.lo + i8 * 8 + 4) = z;
+  if constexpr (!PUSH) {
+    // zero the slices (peer, block) of the local gradient buffer: every peer's block with this
+    // index has finished reading them (it passed the second barrier)
+    for (int q = 0; q < p.world; ++q) {
+      const long long q_begin = min(n8, per_rank * q), q_end = min(n8, q_begin + per_rank);
+      const long long s0 = min(q_end, q_begin + per_blk * blockIdx.x), s1 = min(q_end, s0 + per_blk);
+      for (long long i8 = s0 + threadIdx.x; i8 < s1; i8 += kArThreads) {
+        *reinterpret_cast<float4*>(gl + p.lo + i8 * 8) = z;
+        *reinterpret_cast<float4*>(gl + p.lo + i8 * 8 + 4) = z;
+      }
     }
   }
   for (long long i8 = static_cast<long long>(blockIdx.x) * kArThreads + threadIdx.x; i8 < v8;
@@ -261,7 +342,24 @@ void launch_scatter_add(float* dst, const float* src, const int* idx, long long 
 }
 
 void launch_allreduce_adam(const AllreduceAdamParams& p, int num_blocks, cudaStream_t s) {
-  allreduce_adam_kernel<<<num_blocks, kArThreads, 0, s>>>(p);
+  if (p.stage[0] == nullptr) {
+    allreduce_adam_kernel<false><<<num_blocks, kPullThreads, 0, s>>>(p);
+    return;
+  }
+  // push form: CTA pairs (cluster of 2) share a TPC, so g CTAs displace g / 2 of the GEMMs' CTA pairs
+  // instead of up to g
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(num_blocks);
+  cfg.blockDim = dim3(kPushThreads);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (num_blocks % 2 == 0) ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, allreduce_adam_kernel<true>, p);
 }
 
 void launch_gather_bf16(__nv_bfloat16* dst, const float* src, const int* idx, long long n,

@@ -8,6 +8,10 @@ namespace b2 {
 constexpr int kMaxRanks = 8;
 constexpr int kMaxScalars = 32;
 
+// Two forms of the two-shot part (chosen per launch by the host, see parallel/fused_allreduce.py):
+//   pull: barrier | owner loads the peers' shards (P2P ld / multimem.ld_reduce) -> Adam -> broadcast | barrier
+//   push: every rank stores the shards it does not own into the owners' staging slots (posted writes)
+//         | barrier | owner sums local staging + its own gradients -> Adam -> broadcast | barrier
 // One launch covers up to three regions of ONE network's flat buffers (all offsets in elements from
 // the buffer bases, multiples of 8):
 //   two-shot  [lo, lo + n):      rank r owns shard r (ZeRO-1): reduce peers' gradients -> Adam on the
@@ -35,6 +39,11 @@ struct AllreduceAdamParams {
   int rank, world;
   float* mc_grad;                    // NVLS multicast alias of the gradient buffer, or nullptr
   __nv_bfloat16* mc_w_bf16;          // NVLS multicast alias of the bf16 weights, or nullptr
+  // push mode (stage[0] != nullptr): instead of PULLING the peers' gradients (latency bound: the
+  // kernel needs megabytes of loads in flight), every rank PUSHES the shards it does not own into
+  // the owner's staging slot with posted peer stores (bandwidth bound with a few CTAs), and the
+  // owner reduces local memory. stage[q] = rank q's staging buffer: [world][ceil(n/8/world)*8] floats.
+  float* stage[kMaxRanks];
 };
 
 void launch_allreduce_adam(const AllreduceAdamParams& p, int num_blocks, cudaStream_t s);

@@ -454,6 +454,343 @@ __global__ void __launch_bounds__(kThreads, 3) in_bwd_apply_kernel(const InBwdAp
   }
 }
 
+// ------------------------------------------------ streamed InstanceNorm kernels
+// The same three kernels with their INPUT tensors streamed through a shared-memory ring by the
+// bulk-copy engine: one producer warp issues 1-D cp.async.bulk copies (pixel rows are contiguous
+// in every NHWC view, so a stage of kSpx pixels is one or two copies per tensor) into a ring of
+// kStages stages guarded by full / empty mbarriers; eight consumer warps read their 16-byte
+// vectors from the ring (a warp reads 512 consecutive bytes: conflict-free), do the arithmetic and
+// store straight to global memory. Loads in flight per SM = ring size (up to ~190 KB with two
+// resident blocks) instead of what fits in registers, and they stay in flight while the consumers
+// compute: the direct kernels above spend most of their ~15 us in three or four serialised
+// load -> compute -> store rounds (latency bound, 12 us at zero bytes), these are bandwidth bound.
+constexpr int kConsumers = 256;                // 8 consumer warps
+constexpr int kStreamThreads = kConsumers + 32;   // + 1 producer warp
+constexpr int kPxT = 2;                        // pixels per consumer thread per stage
+constexpr int kStageBytes = kConsumers * 16 * kPxT;   // per tensor and stage: 8 KB
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct StreamGeom {
+  int W, C, pix0, pix1, spx;   // chunk [pix0, pix1) of one image, spx pixels per stage
+  uint32_t rcp_w;
+};
+
+// producer: copy pixels [pix, pix + npix) of one image view (pixel stride == C) to `dst`, row by row
+__device__ __forceinline__ void stream_issue(uint8_t* dst, const V32& v, int pix, int npix, const StreamGeom& g,
+                                             uint64_t* bar) {
+  while (npix > 0) {
+    const int h = static_cast<int>(__umulhi(static_cast<uint32_t>(pix), g.rcp_w));
+    const int w = pix - h * g.W;
+    const int run = min(npix, g.W - w);
+    const uint32_t bytes = static_cast<uint32_t>(run) * g.C * 2;
+    bulk_g2s(dst, v.p + (h * v.sh + w * g.C), bytes, bar);
+    dst += bytes;
+    pix += run;
+    npix -= run;
+  }
+}
+
+// Runs the ring. `views`: the NT streamed tensors (channel offset 0). Consumers call
+// f(pix, h, w, vec[NT]) for each of their pixels; everything else (stores, statistics) is in f.
+// smem: [kStages][NT][kStageBytes] data, then 2 * kStages mbarriers.
+template <int NT, int STAGES, class F>
+__device__ __forceinline__ void stream_run(uint8_t* smem, const V32 (&views)[NT], const StreamGeom& g, int c, int ln,
+                                           int lanes, F&& f) {
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * NT * kStageBytes);
+  uint64_t* empty = full + STAGES;
+  const int total = (g.pix1 - g.pix0 + g.spx - 1) / g.spx;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], kConsumers / 32);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x >= kConsumers) {
+    // ===== producer warp (one elected lane issues) =====
+    if (threadIdx.x == kConsumers) {
+      for (int it = 0; it < total; ++it) {
+        const int s = it % STAGES, fill = it / STAGES;
+        if (fill > 0) mbar_wait(&empty[s], (fill - 1) & 1);
+        const int pix = g.pix0 + it * g.spx;
+        const int npix = min(g.spx, g.pix1 - pix);
+        mbar_arrive_expect_tx(&full[s], static_cast<uint32_t>(npix) * g.C * 2 * NT);
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+          stream_issue(smem + (s * NT + t) * kStageBytes, views[t], pix, npix, g, &full[s]);
+      }
+    }
+    return;
+  }
+  // ===== consumers =====
+  for (int it = 0; it < total; ++it) {
+    const int s = it % STAGES;
+    mbar_wait(&full[s], (it / STAGES) & 1);
+    const int pstage = g.pix0 + it * g.spx;
+    const int npix = min(g.spx, g.pix1 - pstage);
+    uint4 v[kPxT][NT];
+#pragma unroll
+    for (int k = 0; k < kPxT; ++k) {
+      const int lp = ln + k * lanes;
+      if (lp < npix) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+          v[k][t] = *reinterpret_cast<const uint4*>(smem + (s * NT + t) * kStageBytes + (lp * g.C + c) * 2);
+      }
+    }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&empty[s]);   // the stage is in registers: hand it back
+#pragma unroll
+    for (int k = 0; k < kPxT; ++k) {
+      const int lp = ln + k * lanes;
+      if (lp < npix) {
+        const int pix = pstage + lp;
+        const int h = static_cast<int>(__umulhi(static_cast<uint32_t>(pix), g.rcp_w));
+        f(pix, h, pix - h * g.W, v[k]);
+      }
+    }
+  }
+}
+
+template <int ACT, bool SKIP, bool HALO>
+__global__ void __launch_bounds__(kStreamThreads, 2) in_apply_stream_kernel(const InApplyParams p, int pix_per_block,
+                                                                           uint32_t rcp_w) {
+  extern __shared__ __align__(128) uint8_t ring[];
+  constexpr int NT = SKIP ? 2 : 1;
+  constexpr int STAGES = SKIP ? 6 : 8;
+  const int c8 = p.C >> 3;
+  const int lanes = kConsumers / c8;
+  const int tid = threadIdx.x < kConsumers ? threadIdx.x : 0;
+  const int c = (tid % c8) * 8;
+  const int ln = tid / c8;
+  const int n = blockIdx.y;
+  StreamGeom g;
+  g.W = p.W; g.C = p.C; g.rcp_w = rcp_w; g.spx = lanes * kPxT;
+  g.pix0 = blockIdx.x * pix_per_block;
+  g.pix1 = min(p.H * p.W, g.pix0 + pix_per_block);
+  V32 views[NT];
+  views[0] = v32(p.x, n, 0);
+  if constexpr (SKIP) views[1] = v32(p.skip, n, 0);
+  float ka[8], kb[8];
+  if (threadIdx.x < kConsumers) {   // overlaps with the producer's first copies
+    if (p.stats != nullptr) {
+      float mean[8], rstd[8], ga[8], be[8];
+      mean_rstd8(p.stats + (static_cast<long long>(n) * p.C + c) * 2, p.inv_count, p.eps, mean, rstd);
+      load_f8(p.gamma + c, ga);
+      load_f8(p.beta + c, be);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        ka[j] = rstd[j] * ga[j];
+        kb[j] = be[j] - mean[j] * ka[j];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { ka[j] = 1.f; kb[j] = 0.f; }
+    }
+  }
+  const V32 D = v32(p.dst, n, c);
+  const float slope = act_slope(p.act);
+  const int H = p.H, W = p.W, halo = p.halo;
+  stream_run<NT, STAGES>(ring, views, g, c, ln, lanes, [&](int, int h, int w, const uint4 (&v)[NT]) {
+    float x[8], o[8];
+    unpack8(v[0], x);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = actk<ACT>(fmaf(x[j], ka[j], kb[j]), slope);
+    if constexpr (SKIP) {
+      float s[8];
+      unpack8(v[1], s);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += s[j];
+    }
+    const uint4 pk = pack8(o);
+    stv(D, h, w, pk);
+    if constexpr (HALO) {
+      const int hm = (h >= 1 && h <= halo) ? -h : ((h >= H - 1 - halo && h <= H - 2) ? 2 * (H - 1) - h : h);
+      const int wm = (w >= 1 && w <= halo) ? -w : ((w >= W - 1 - halo && w <= W - 2) ? 2 * (W - 1) - w : w);
+      if (hm != h) stv(D, hm, w, pk);
+      if (wm != w) {
+        stv(D, h, wm, pk);
+        if (hm != h) stv(D, hm, wm, pk);
+      }
+    }
+  });
+}
+
+template <int ACT, bool FOLD, bool G2>
+__global__ void __launch_bounds__(kStreamThreads, 2) in_bwd_reduce_stream_kernel(const InBwdReduceParams p,
+                                                                                int pix_per_block, uint32_t rcp_w) {
+  extern __shared__ __align__(128) uint8_t ring[];
+  constexpr int NT = G2 ? 3 : 2;       // g1, x, (g2)
+  constexpr int STAGES = G2 ? 4 : 6;
+  const int c8 = p.C >> 3;
+  const int lanes = kConsumers / c8;
+  const int tid = threadIdx.x < kConsumers ? threadIdx.x : 0;
+  const int c = (tid % c8) * 8;
+  const int ln = tid / c8;
+  const int n = blockIdx.y;
+  StreamGeom g;
+  g.W = p.W; g.C = p.C; g.rcp_w = rcp_w; g.spx = lanes * kPxT;
+  g.pix0 = blockIdx.x * pix_per_block;
+  g.pix1 = min(p.H * p.W, g.pix0 + pix_per_block);
+  V32 views[NT];
+  views[0] = v32(p.g1, n, 0);
+  views[1] = v32(p.x, n, 0);
+  if constexpr (G2) views[2] = v32(p.g2, n, 0);
+  float ka[8], kb[8];
+  if constexpr (ACT != ACTK_NONE) {
+    if (threadIdx.x < kConsumers) {
+      float mean[8], rstd[8], ga[8], be[8];
+      mean_rstd8(p.stats + (static_cast<long long>(n) * p.C + c) * 2, p.inv_count, p.eps, mean, rstd);
+      load_f8(p.gamma + c, ga);
+      load_f8(p.beta + c, be);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        ka[j] = rstd[j] * ga[j];
+        kb[j] = be[j] - mean[j] * ka[j];
+      }
+    }
+  }
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  const V32 G1 = v32(p.g1, n, c), DY = v32(p.dy, n, c);
+  const float slope = act_slope(p.act);
+  const int H = p.H, W = p.W, fold = p.fold1;
+  stream_run<NT, STAGES>(ring, views, g, c, ln, lanes, [&](int, int h, int w, const uint4 (&v)[NT]) {
+    float gr[8], x[8];
+    unpack8(v[0], gr);
+    unpack8(v[1], x);
+    if constexpr (G2) {
+      float t[8];
+      unpack8(v[2], t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gr[j] += t[j];
+    }
+    if constexpr (FOLD) {   // border pixels also collect the gradient of their mirror images in g1's halo
+      const int hm = (h >= 1 && h <= fold) ? -h : ((h >= H - 1 - fold && h <= H - 2) ? 2 * (H - 1) - h : h);
+      const int wm = (w >= 1 && w <= fold) ? -w : ((w >= W - 1 - fold && w <= W - 2) ? 2 * (W - 1) - w : w);
+      if (hm != h || wm != w) {
+        float t[8];
+        if (hm != h) {
+          unpack8(ldv(G1, hm, w), t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gr[j] += t[j];
+        }
+        if (wm != w) {
+          unpack8(ldv(G1, h, wm), t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) gr[j] += t[j];
+          if (hm != h) {
+            unpack8(ldv(G1, hm, wm), t);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gr[j] += t[j];
+          }
+        }
+      }
+    }
+    if constexpr (ACT != ACTK_NONE) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gr[j] = fmaf(x[j], ka[j], kb[j]) > 0.f ? gr[j] : gr[j] * slope;
+    }
+    const uint4 pk = pack8(gr);
+    float gq[8];
+    unpack8(pk, gq);   // statistics of the STORED (bf16) value: in_bwd_apply reads that
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s1[j] += gq[j];
+      s2[j] = fmaf(gq[j], x[j], s2[j]);
+    }
+    stv(DY, h, w, pk);
+  });
+  if (threadIdx.x >= kConsumers) return;          // (consumers only from here: named barrier 1)
+  // the ring is drained: reuse its first bytes as the [lanes][C][2] reduction scratch
+  float* red = reinterpret_cast<float*>(ring);
+  named_bar_sync(1, kConsumers);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[(ln * p.C + c + j) * 2 + 0] = s1[j];
+    red[(ln * p.C + c + j) * 2 + 1] = s2[j];
+  }
+  named_bar_sync(1, kConsumers);
+  for (int ch = threadIdx.x; ch < p.C; ch += kConsumers) {
+    float a1 = 0.f, a2 = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      const float2 t = *reinterpret_cast<const float2*>(&red[(l * p.C + ch) * 2]);
+      a1 += t.x;
+      a2 += t.y;
+    }
+    const float* st = p.stats + (static_cast<long long>(n) * p.C + ch) * 2;
+    const float mean = st[0] * p.inv_count;
+    const float rstd = rsqrtf(fmaxf(st[1] * p.inv_count - mean * mean, 0.f) + p.eps);
+    float* bs = p.bstats + (static_cast<long long>(n) * p.C + ch) * 2;
+    atomicAdd(bs, a1);
+    atomicAdd(bs + 1, rstd * (a2 - mean * a1));
+  }
+}
+
+__global__ void __launch_bounds__(kStreamThreads, 2) in_bwd_apply_stream_kernel(const InBwdApplyParams p,
+                                                                               int pix_per_block, uint32_t rcp_w) {
+  extern __shared__ __align__(128) uint8_t ring[];
+  constexpr int NT = 2, STAGES = 6;
+  const int c8 = p.C >> 3;
+  const int lanes = kConsumers / c8;
+  const int tid = threadIdx.x < kConsumers ? threadIdx.x : 0;
+  const int c = (tid % c8) * 8;
+  const int ln = tid / c8;
+  const int n = blockIdx.y;
+  StreamGeom g;
+  g.W = p.W; g.C = p.C; g.rcp_w = rcp_w; g.spx = lanes * kPxT;
+  g.pix0 = blockIdx.x * pix_per_block;
+  g.pix1 = min(p.H * p.W, g.pix0 + pix_per_block);
+  V32 views[NT];
+  views[0] = v32(p.dy, n, 0);
+  views[1] = v32(p.x, n, 0);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && p.dgamma != nullptr && threadIdx.x < kConsumers) {
+    for (int cc = threadIdx.x; cc < p.C; cc += kConsumers) {   // parameter gradients: sum over images
+      float dg = 0.f, db = 0.f;
+      for (int nn = 0; nn < p.N; ++nn) {
+        const float* bs = p.bstats + (static_cast<long long>(nn) * p.C + cc) * 2;
+        db += bs[0];
+        dg += bs[1];
+      }
+      p.dgamma[cc] += dg;
+      p.dbeta[cc] += db;
+    }
+  }
+  float kA[8], kB[8], kC[8];
+  if (threadIdx.x < kConsumers) {
+    float mean[8], rstd[8], ga[8], b0[8], b1[8];
+    mean_rstd8(p.stats + (static_cast<long long>(n) * p.C + c) * 2, p.inv_count, p.eps, mean, rstd);
+    load_f8(p.gamma + c, ga);
+    load_f8(p.bstats + (static_cast<long long>(n) * p.C + c) * 2, b0);
+    load_f8(p.bstats + (static_cast<long long>(n) * p.C + c) * 2 + 8, b1);
+    const float bs[16] = {b0[0], b0[1], b0[2], b0[3], b0[4], b0[5], b0[6], b0[7],
+                          b1[0], b1[1], b1[2], b1[3], b1[4], b1[5], b1[6], b1[7]};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float m1 = bs[2 * j] * p.inv_count, m2 = bs[2 * j + 1] * p.inv_count;
+      const float gr = ga[j] * rstd[j];
+      kA[j] = gr;
+      kB[j] = -gr * rstd[j] * m2;
+      kC[j] = gr * (mean[j] * rstd[j] * m2 - m1);
+    }
+  }
+  const V32 DX = v32(p.dx, n, c);
+  stream_run<NT, STAGES>(ring, views, g, c, ln, lanes, [&](int, int h, int w, const uint4 (&v)[NT]) {
+    float d[8], x[8], o[8];
+    unpack8(v[0], d);
+    unpack8(v[1], x);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(kA[j], d[j], fmaf(kB[j], x[j], kC[j]));
+    stv(DX, h, w, pack8(o));
+  });
+}
+
 // ------------------------------------------------------------------ act_bwd
 __global__ void __launch_bounds__(kThreads) act_bwd_kernel(const ActBwdParams p) {
   __shared__ float sb[64];
@@ -813,6 +1150,43 @@ static uint32_t rcp_for(int H, int W, int C, const char* who) {
   return static_cast<uint32_t>(((1ull << 32) + W - 1) / W);
 }
 
+// ---- streamed variants: used whenever every streamed view has pixel stride == C (true for every
+// buffer of the engine); the direct kernels remain for the FP8-twin output and odd strides.
+static bool g_ew_stream = true;
+void set_ew_stream(bool on) { g_ew_stream = on; }
+bool ew_stream() { return g_ew_stream; }
+
+static bool streamable(const View& v, int C) { return v.p == nullptr || v.sw == C; }
+
+static int stream_ppb(int HW, int N, int C) {
+  const int spx = (kConsumers / (C / 8)) * kPxT;
+  int chunks = ew_num_sms() * 2 / (N > 0 ? N : 1);      // two resident blocks per SM, one wave
+  if (chunks < 1) chunks = 1;
+  int ppb = (HW + chunks - 1) / chunks;
+  ppb = (ppb + spx - 1) / spx * spx;
+  if (ppb < 2 * spx) ppb = 2 * spx;
+  return ppb > HW ? HW : ppb;
+}
+template <class K>
+static void stream_smem(K kernel, size_t bytes) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+}
+constexpr size_t ring_bytes(int nt, int stages) { return static_cast<size_t>(stages) * nt * kStageBytes + 2 * stages * 8; }
+
+template <int ACT, bool SKIP, bool HALO>
+static void launch_in_apply_stream_t(const InApplyParams& p, dim3 grid, int ppb, uint32_t rcp, cudaStream_t s) {
+  constexpr size_t smem = ring_bytes(SKIP ? 2 : 1, SKIP ? 6 : 8);
+  static bool once = (stream_smem(in_apply_stream_kernel<ACT, SKIP, HALO>, smem), true);
+  (void)once;
+  in_apply_stream_kernel<ACT, SKIP, HALO><<<grid, kStreamThreads, smem, s>>>(p, ppb, rcp);
+}
+template <int ACT>
+static void launch_in_apply_stream_a(const InApplyParams& p, dim3 grid, int ppb, uint32_t rcp, cudaStream_t s) {
+  const bool skip = p.skip.p != nullptr, halo = p.halo > 0;
+  if (skip) { if (halo) launch_in_apply_stream_t<ACT, true, true>(p, grid, ppb, rcp, s); else launch_in_apply_stream_t<ACT, true, false>(p, grid, ppb, rcp, s); }
+  else { if (halo) launch_in_apply_stream_t<ACT, false, true>(p, grid, ppb, rcp, s); else launch_in_apply_stream_t<ACT, false, false>(p, grid, ppb, rcp, s); }
+}
+
 template <int ACT, bool SKIP, bool HALO>
 static void launch_in_apply_t(const InApplyParams& p, dim3 grid, int ppb, uint32_t rcp, cudaStream_t s) {
   if (p.dst8.p != nullptr) in_apply_kernel<ACT, SKIP, HALO, true><<<grid, kThreads, 0, s>>>(p, ppb, rcp);
@@ -827,6 +1201,14 @@ static void launch_in_apply_a(const InApplyParams& p, dim3 grid, int ppb, uint32
 void launch_in_apply(const InApplyParams& p, cudaStream_t s) {
   const uint32_t rcp = rcp_for(p.H, p.W, p.C, "launch_in_apply");
   const int HW = p.H * p.W;
+  if (g_ew_stream && p.dst8.p == nullptr && streamable(p.x, p.C) && streamable(p.skip, p.C)) {
+    const int ppb = stream_ppb(HW, p.N, p.C);
+    dim3 grid((HW + ppb - 1) / ppb, p.N);
+    if (p.act == ACT_RELU) launch_in_apply_stream_a<ACTK_RELU>(p, grid, ppb, rcp, s);
+    else if (p.act == ACT_NONE) launch_in_apply_stream_a<ACTK_NONE>(p, grid, ppb, rcp, s);
+    else launch_in_apply_stream_a<ACTK_SLOPE>(p, grid, ppb, rcp, s);
+    return;
+  }
   const int lanes = kThreads / (p.C / 8);
   const int ppb = pick_pix_per_block(HW, p.N, lanes, (p.skip.p != nullptr || p.dst8.p != nullptr) ? 3 : 4);
   dim3 grid((HW + ppb - 1) / ppb, p.N);
@@ -835,6 +1217,19 @@ void launch_in_apply(const InApplyParams& p, cudaStream_t s) {
   else launch_in_apply_a<ACTK_SLOPE>(p, grid, ppb, rcp, s);
 }
 
+template <int ACT, bool FOLD, bool G2>
+static void launch_in_bwd_reduce_stream_t(const InBwdReduceParams& p, dim3 grid, int ppb, uint32_t rcp, cudaStream_t s) {
+  constexpr size_t smem = ring_bytes(G2 ? 3 : 2, G2 ? 4 : 6);
+  static bool once = (stream_smem(in_bwd_reduce_stream_kernel<ACT, FOLD, G2>, smem), true);
+  (void)once;
+  in_bwd_reduce_stream_kernel<ACT, FOLD, G2><<<grid, kStreamThreads, smem, s>>>(p, ppb, rcp);
+}
+template <int ACT>
+static void launch_in_bwd_reduce_stream_a(const InBwdReduceParams& p, dim3 grid, int ppb, uint32_t rcp, cudaStream_t s) {
+  const bool fold = p.fold1 > 0, g2 = p.g2.p != nullptr;
+  if (fold) { if (g2) launch_in_bwd_reduce_stream_t<ACT, true, true>(p, grid, ppb, rcp, s); else launch_in_bwd_reduce_stream_t<ACT, true, false>(p, grid, ppb, rcp, s); }
+  else { if (g2) launch_in_bwd_reduce_stream_t<ACT, false, true>(p, grid, ppb, rcp, s); else launch_in_bwd_reduce_stream_t<ACT, false, false>(p, grid, ppb, rcp, s); }
+}
 template <int ACT, bool FOLD, bool G2>
 static void launch_in_bwd_reduce_t(const InBwdReduceParams& p, dim3 grid, size_t smem, int ppb, uint32_t rcp,
                                    cudaStream_t s) {
@@ -852,6 +1247,14 @@ void launch_in_bwd_reduce(const InBwdReduceParams& p, cudaStream_t s) {
   const uint32_t rcp = rcp_for(p.H, p.W, p.C, "launch_in_bwd_reduce");
   const int HW = p.H * p.W;
   const int lanes = kThreads / (p.C / 8);
+  if (g_ew_stream && p.stats != nullptr && p.bstats != nullptr && streamable(p.g1, p.C) && streamable(p.g2, p.C) &&
+      streamable(p.x, p.C) && static_cast<size_t>(lanes) * p.C * 8 <= 4 * kStageBytes) {
+    const int ppb = stream_ppb(HW, p.N, p.C);
+    dim3 grid((HW + ppb - 1) / ppb, p.N);
+    if (p.act == ACT_NONE) launch_in_bwd_reduce_stream_a<ACTK_NONE>(p, grid, ppb, rcp, s);
+    else launch_in_bwd_reduce_stream_a<ACTK_SLOPE>(p, grid, ppb, rcp, s);
+    return;
+  }
   const int ppb = pick_pix_per_block(HW, p.N, lanes, 3);
   dim3 grid((HW + ppb - 1) / ppb, p.N);
   const size_t smem = static_cast<size_t>(lanes) * p.C * 2 * sizeof(float);
@@ -862,6 +1265,15 @@ void launch_in_bwd_reduce(const InBwdReduceParams& p, cudaStream_t s) {
 void launch_in_bwd_apply(const InBwdApplyParams& p, cudaStream_t s) {
   const uint32_t rcp = rcp_for(p.H, p.W, p.C, "launch_in_bwd_apply");
   const int HW = p.H * p.W;
+  if (g_ew_stream && streamable(p.dy, p.C) && streamable(p.x, p.C)) {
+    constexpr size_t smem = ring_bytes(2, 6);
+    static bool once = (stream_smem(in_bwd_apply_stream_kernel, smem), true);
+    (void)once;
+    const int ppb = stream_ppb(HW, p.N, p.C);
+    dim3 grid((HW + ppb - 1) / ppb, p.N);
+    in_bwd_apply_stream_kernel<<<grid, kStreamThreads, smem, s>>>(p, ppb, rcp);
+    return;
+  }
   const int lanes = kThreads / (p.C / 8);
   const int ppb = pick_pix_per_block(HW, p.N, lanes, 3);
   dim3 grid((HW + ppb - 1) / ppb, p.N);

@@ -32,6 +32,11 @@ struct InApplyParams {
   float* amax8;
 };
 void launch_in_apply(const InApplyParams& p, cudaStream_t s);
+// The InstanceNorm kernels stream their inputs through a shared-memory ring filled by the bulk-copy
+// engine (default); `set_ew_stream(false)` selects the direct (register-landing) kernels, which also
+// serve the FP8-twin output and views whose pixel stride is not C. For A/B tests and benchmarks.
+void set_ew_stream(bool on);
+bool ew_stream();
 
 struct InBwdReduceParams {
   View g1;              // bf16 gradient source 1 (may be a padded-domain dgrad output)

@@ -454,7 +454,8 @@ class Plan {
                          uint64_t w, uint64_t m, uint64_t v, uint64_t step, float lr, float b1,
                          float b2, float eps, long long lo, long long n, long long v_lo, long long v_n,
                          std::vector<uint64_t> sc_src, uint64_t sc_dst, int sc_n, int rank, int world,
-                         int num_blocks, uint64_t mc_grad, uint64_t mc_wbf16) {
+                         int num_blocks, uint64_t mc_grad, uint64_t mc_wbf16,
+                         std::vector<uint64_t> stage_ptrs) {
     auto p = std::make_shared<AllreduceAdamParams>();
     memset(p.get(), 0, sizeof(AllreduceAdamParams));
     if (world > kMaxRanks || world < 1) throw std::runtime_error("bad world size");
@@ -465,11 +466,14 @@ class Plan {
     if (sc_n < 0 || sc_n > kMaxScalars || (sc_n > 0 && static_cast<int>(sc_src.size()) != world))
       throw std::runtime_error("allreduce_adam: bad scalar side channel");
     if (num_blocks < 1 || num_blocks > 148) throw std::runtime_error("allreduce_adam: 1..148 blocks");
+    if (!stage_ptrs.empty() && static_cast<int>(stage_ptrs.size()) != world)
+      throw std::runtime_error("allreduce_adam: push mode needs one staging pointer per rank");
     for (int r = 0; r < world; ++r) {
       p->grad[r] = P<float>(grad_ptrs[r]);
       p->w_bf16[r] = P<__nv_bfloat16>(wbf16_ptrs[r]);
       p->signal[r] = P<uint32_t>(signal_ptrs[r]);
       if (sc_n > 0) p->sc_src[r] = P<const float>(sc_src[r]);
+      if (!stage_ptrs.empty()) p->stage[r] = P<float>(stage_ptrs[r]);
     }
     p->w = P<float>(w); p->m = P<float>(m); p->v = P<float>(v); p->step = P<const int>(step);
     p->lr = lr; p->beta1 = b1; p->beta2 = b2; p->eps = eps;
@@ -496,6 +500,8 @@ PYBIND11_MODULE(_C, m) {
   m.doc() = "b200-cyclegan native runtime (sm_100a kernels + plan executor)";
   m.def("encode_tmap", &encode_tmap, py::arg("ptr"), py::arg("dtype"), py::arg("dims"),
         py::arg("strides_bytes"), py::arg("box"), py::arg("swizzle") = 3);
+  m.def("set_ew_stream", &b2::set_ew_stream, "InstanceNorm kernels: true = bulk-copy ring (default), false = direct");
+  m.def("ew_stream", &b2::ew_stream);
   m.def("device_sync", []() { check(cudaDeviceSynchronize(), "cudaDeviceSynchronize"); });
   m.attr("MAX_TAPS") = kMaxTaps;
   py::class_<Plan>(m, "Plan")
@@ -539,5 +545,10 @@ PYBIND11_MODULE(_C, m) {
       .def("add_scatter_add", &Plan::add_scatter_add)
       .def("add_memset", &Plan::add_memset)
       .def("add_d4_bwd", &Plan::add_d4_bwd)
-      .def("add_allreduce_adam", &Plan::add_allreduce_adam);
+      .def("add_allreduce_adam", &Plan::add_allreduce_adam, py::arg("name"), py::arg("grad_ptrs"),
+           py::arg("wbf16_ptrs"), py::arg("signal_ptrs"), py::arg("w"), py::arg("m"), py::arg("v"), py::arg("step"),
+           py::arg("lr"), py::arg("b1"), py::arg("b2"), py::arg("eps"), py::arg("lo"), py::arg("n"),
+           py::arg("v_lo"), py::arg("v_n"), py::arg("sc_src"), py::arg("sc_dst"), py::arg("sc_n"), py::arg("rank"),
+           py::arg("world"), py::arg("num_blocks"), py::arg("mc_grad"), py::arg("mc_wbf16"),
+           py::arg("stage_ptrs") = std::vector<uint64_t>());
 }

@@ -273,6 +273,8 @@ class NativeBackend:
         self.symm.set_buckets(n, asc, vec_lo=self.state[n].layout.vec_lo)
         self.buckets[n] = bs
         self.bucket_index[n] = [asc.index((lo, hi)) for _, lo, hi in bs]
+      # push-mode staging buffer, sized once for the largest bucket (symmetric allocation: collective)
+      self.symm.stage_ptrs(max(hi - lo for n in NETS for _, lo, hi in self.buckets[n]))
     # loss / metric slots: on the fused path they live in peer-readable memory and the last fused
     # launch of a step leaves their sums over ranks in symm.scalars_sum (no NCCL call, no host sync)
     self.slots = self.symm.scalars if self.fused else torch.zeros(NUM_SLOTS, device=self.device)
@@ -360,7 +362,7 @@ class NativeBackend:
     return d if self.fused else self.strategy.reduce_dict(d)
 
   def collective(self) -> str:
-    """'fused-nvls' | 'fused-p2p' | 'nccl' | 'none' — what the gradient path of this run is."""
+    """'fused-<push|pull>-<nvls|p2p>' | 'nccl' | 'none' — what the gradient path of this run is."""
     if self.world == 1:
       return "none"
     return self.symm.collective() if self.fused else "nccl"

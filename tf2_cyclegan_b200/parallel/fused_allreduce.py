@@ -23,17 +23,26 @@ from .strategy import Strategy
 
 MAX_BLOCKS = 148        # signal-pad sizing: one flag set per block and phase
 NUM_SCALARS = 16        # loss / metric slots reduced through the side channel
+# Form of the two-shot part: "push" (posted peer stores into the owner's staging slots, then local
+# reduction: bandwidth bound with a few CTAs) or "pull" (owner loads the peers' shards / NVLS
+# multimem.ld_reduce: needs megabytes of loads in flight). See csrc/allreduce_adam.cuh.
+DEFAULT_MODE = "push"
 
 
-def default_blocks(nbytes: int, exposed: bool) -> int:
-  """CTAs (256 threads) of one fused reduce + Adam launch. Launches that run under the backward pass
-  stay small (they compete with the GEMMs for SMs and only need to keep ~1 MB of peer loads in
-  flight); the last, exposed launch of a network may use more."""
-  env = os.environ.get("B2_ALLREDUCE_BLOCKS")
-  if env:
-    return max(1, min(MAX_BLOCKS, int(env)))
-  want = max(4, min(64, nbytes // (256 * 1024)))     # >= 256 KB of fp32 gradients per CTA
-  return min(MAX_BLOCKS, want * 2) if exposed else want
+def default_blocks(nbytes: int, exposed: bool, world: int = 2, mode: Optional[str] = None) -> int:
+  """CTAs of one fused reduce + Adam launch. Push form: 1024-thread CTAs in pairs (one TPC per pair),
+  ~128 KB of loads in flight each; launches that run under the backward pass use few (they displace
+  GEMM CTA pairs one for one), the last, exposed launch of a network more. Pull form: 256-thread
+  CTAs, one 8-element chunk pair per thread and iteration."""
+  mode = mode or DEFAULT_MODE
+  if mode == "push":
+    want = max(2, min(8, -(-nbytes // (2 << 20))))
+    if exposed:
+      want = max(want, min(32, -(-nbytes // (512 << 10))))
+    return want + (want & 1)
+  shard = max(1, nbytes // max(1, world))
+  want = max(2, min(24, -(-shard // (64 * 1024))))
+  return min(MAX_BLOCKS, max(want, min(64, -(-shard // (32 * 1024))))) if exposed else want
 
 
 class SymmetricBuffers:
@@ -58,6 +67,18 @@ class SymmetricBuffers:
     self.h_scalars = symm_mem.rendezvous(self.scalars, dist.group.WORLD)
     self.scalars_sum = torch.zeros(NUM_SCALARS, device=strategy.device)
     self._dummy: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+    self._stages: List[Tuple[torch.Tensor, object]] = []     # push-mode staging buffers (grow-only)
+
+  def stage_ptrs(self, n: int) -> List[int]:
+    """Peer pointers of a staging buffer with room for a two-shot region of n elements:
+    [world][ceil(n / 8 / world) * 8] floats. Collective (symmetric allocation) when it has to grow;
+    launches that were planned against an older, smaller buffer keep it alive."""
+    need = self.world * (-(-(n // 8) // self.world)) * 8
+    if not self._stages or self._stages[-1][0].numel() < need:
+      t = self.symm_mem.empty(max(need, 1 << 20), dtype=torch.float32, device=self.strategy.device)
+      t.zero_()
+      self._stages.append((t, self.symm_mem.rendezvous(t, dist.group.WORLD)))
+    return [int(p) for p in self._stages[-1][1].buffer_ptrs]
 
   def alloc(self, name: str, numel: int):
     sm = self.symm_mem
@@ -72,10 +93,11 @@ class SymmetricBuffers:
     return g, wb
 
   def collective(self) -> str:
-    """What the gradient path of this run is: 'fused-nvls' | 'fused-p2p'."""
+    """What the gradient path of this run is: 'fused-<push|pull>-<nvls|p2p>' (nvls: the weight
+    broadcast — and, in pull form, the reduction — goes through the NVSwitch multicast object)."""
     for name in self.handles:
-      return "fused-nvls" if self.multicast_ptrs(name)[0] else "fused-p2p"
-    return "fused-p2p"
+      return f"fused-{DEFAULT_MODE}-" + ("nvls" if self.multicast_ptrs(name)[0] else "p2p")
+    return f"fused-{DEFAULT_MODE}-p2p"
 
   def multicast_ptrs(self, name: str) -> Tuple[int, int]:
     hg, hw = self.handles[name]
@@ -108,7 +130,8 @@ class SymmetricBuffers:
 
   def emit_allreduce_adam(self, plan, name: str, st, lr: float, b1: float, b2: float, eps: float,
                           bucket: Optional[int] = None, vectors: Optional[bool] = None,
-                          scalars: bool = False, exposed: bool = False):
+                          scalars: bool = False, exposed: bool = False, mode: Optional[str] = None,
+                          blocks: Optional[int] = None):
     """Fused reduce + Adam + broadcast launches of network ``name``: every bucket back to back
     (``bucket`` None) or ONE bucket. ``vectors``: also update the one-shot tail [vec_lo, n) in the
     (last) launch (default: when all buckets are emitted); ``scalars``: carry the loss-scalar sums."""
@@ -120,6 +143,8 @@ class SymmetricBuffers:
     if bucket is not None:
       todo = [todo[bucket]]
     v_lo = self.vec_lo.get(name, st.n)
+    mode = mode or DEFAULT_MODE
+    assert mode in ("push", "pull"), mode
     for k, (lo, hi) in enumerate(todo):
       last = k == len(todo) - 1
       vec = (v_lo, st.n - v_lo) if (vectors and last) else (0, 0)
@@ -132,7 +157,8 @@ class SymmetricBuffers:
                               lr, b1, b2, eps, lo, hi - lo, vec[0], vec[1],
                               [int(p) for p in self.h_scalars.buffer_ptrs] if sc else [],
                               self.scalars_sum.data_ptr() if sc else 0, NUM_SCALARS if sc else 0,
-                              self.rank, self.world, default_blocks(4 * (hi - lo), exposed), mg, mw)
+                              self.rank, self.world, blocks or default_blocks(4 * (hi - lo), exposed, self.world, mode),
+                              mg, mw, self.stage_ptrs(hi - lo) if mode == "push" else [])
 
   def emit_scalar_reduce(self, plan, name: str = "scalars.allreduce"):
     """Stand-alone one-shot SUM of the loss slots (test step: no optimizer launch to ride on)."""

@@ -9,8 +9,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--images", type=int, default=12)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--no_flush", action="store_true", help="keep L2 warm between iterations (in-step behaviour)")
+ap.add_argument("--direct", action="store_true", help="direct (register-landing) kernels instead of the bulk-copy ring")
 a = ap.parse_args()
 C = nv.load()
+C.set_ew_stream(not a.direct)
 n, h, c = a.images, 64, 256
 hbm = 6572.9
 try:
@@ -38,7 +40,7 @@ p = C.Plan(); p.add_in_bwd_reduce("r2", g1.view(), 1, g2.view(), x.view(), stats
 p = C.Plan(); p.add_in_bwd_apply("ap", dy.view(), x.view(), stats.data_ptr(), bst.data_ptr(), gam.data_ptr(), inv, 1e-3, dx.view(), dg.data_ptr(), db.data_ptr(), n, h, h, c); plans["in_bwd_apply"] = (p, 3 * E)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 s = torch.cuda.current_stream().cuda_stream
-print(f"l2_flush={not a.no_flush}")
+print(f"l2_flush={not a.no_flush} kernels={'direct' if a.direct else 'stream'}")
 for name, (plan, nbytes) in plans.items():
   for _ in range(3): plan.run(0, -1, s, False)
   ts = []
