@@ -158,3 +158,47 @@ def test_prefetch_iterator_abandoned_early_exits_cleanly(tmp_path):
   r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120,
                      env=dict(os.environ, PYTHONPATH=root))
   assert r.returncode == 0 and "done" in r.stdout, (r.returncode, r.stderr[-500:])
+
+
+def test_weights_only_checkpoint_resumes_with_fresh_optimizer(tmp_path, capsys):
+  """main.py:162-170: ``checkpoint.read()`` never asserts that optimizer slots were found, so a bundle
+  without them (weights-only export, or written before the first step) must load: Adam restarts from
+  zero with a warning; missing WEIGHTS still raise unless expect_partial."""
+  import types
+  import pytest
+  from tf2_cyclegan_b200.engine.cyclegan import CycleGAN
+  from tf2_cyclegan_b200.parallel.strategy import Strategy
+  from tf2_cyclegan_b200.utils import checkpoint as ckpt
+  args = types.SimpleNamespace(output_dir=str(tmp_path), global_batch_size=1, batch_size=1, image_size=16,
+                               num_residual_blocks=1, backend="oracle", dtype="fp32", seed=3)
+  gan = CycleGAN(args, Strategy(device="cpu"))
+  x = torch.rand(1, 16, 16, 3) * 2 - 1
+  gan.train_step(x, x.flip(1))
+  sd = gan.backend.state_dict()
+  weights = {k: v for k, v in sd.items() if "OPTIMIZER_SLOT" not in k and "_optimizer/" not in k}
+  for fmt in ("native", "tensorbundle"):
+    ckpt.save(gan.checkpoint_prefix, weights, fmt=fmt)
+    fresh = CycleGAN(args, Strategy(device="cpu"))
+    assert fresh.load_checkpoint()
+    assert "optimizer entries missing" in capsys.readouterr().out
+    k = "G/layer_with_weights-0/kernel/.ATTRIBUTES/VARIABLE_VALUE"
+    assert torch.equal(fresh.backend.state_dict()[k], sd[k])
+    assert fresh.backend.opt["G"].iterations == 0
+  del weights["F/layer_with_weights-0/kernel/.ATTRIBUTES/VARIABLE_VALUE"]
+  ckpt.save(gan.checkpoint_prefix, weights)
+  with pytest.raises(KeyError):
+    CycleGAN(args, Strategy(device="cpu")).load_checkpoint()
+  assert CycleGAN(args, Strategy(device="cpu")).load_checkpoint(expect_partial=True)
+
+
+def test_torn_tensorbundle_write_is_detected(tmp_path):
+  """New data file next to an old index (crash between the two renames): refused, not loaded."""
+  import pytest
+  from tf2_cyclegan_b200.utils import tensorbundle as tb
+  prefix = str(tmp_path / "checkpoint")
+  tb.write_bundle(prefix, {"a": torch.arange(10.0)})
+  old_index = open(prefix + ".index", "rb").read()
+  tb.write_bundle(prefix, {"a": torch.arange(12.0), "b": torch.ones(3)})
+  open(prefix + ".index", "wb").write(old_index)
+  with pytest.raises(IOError):
+    tb.read_bundle(prefix)

@@ -35,7 +35,9 @@ def _worker(rank, world, port, x, y, out):
   st.shutdown()
 
 
-@pytest.mark.parametrize("world,batch", [(2, 2), (2, 3)])
+# world 1 / 2 / 4, even shares, uneven shares (3 over 2, 6 over 4) and EMPTY shares
+# (2 and 3 samples over 4 ranks: ranks 2-3 / rank 3 get nothing but still join every collective)
+@pytest.mark.parametrize("world,batch", [(2, 2), (2, 3), (4, 4), (4, 6), (4, 2), (4, 3)])
 def test_dp_equivalence(world, batch):
   torch.manual_seed(0)
   x, y = torch.randn(batch, 16, 16, 3), torch.randn(batch, 16, 16, 3)

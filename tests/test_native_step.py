@@ -46,9 +46,26 @@ def test_forward_losses_and_cycle_match_oracle(size, b, nres):
     assert a.shape == o.shape and (a - o).abs().max().item() < 3e-2
 
 
-@pytest.mark.parametrize("size,b,nres", [(128, 2, 1)])
-def test_gradients_match_oracle(size, b, nres):
+# Per-tensor bound on the relative L2 error of a parameter gradient. The native step keeps every
+# activation and every back-propagated gradient in bf16 (relative rounding 2^-9 per stored tensor) and
+# the oracle is fp32 end to end, so the error grows with depth: a generator gradient crosses up to
+# ~2 x 17 stored tensors (+ the discriminator for the adversarial term), and the L1 terms' sign(t - p)
+# gradients flip wherever |t - p| is below the bf16 step. KERNEL_TOL / VECTOR_TOL are ~2x the worst
+# error measured on B200 (printed by the test; see profiles/r2_gradient_errors.txt); a dropped or
+# mis-scaled loss term moves these numbers by 30-100 %, and the single-term cases below catch the
+# small adversarial term that the 10x cycle term would otherwise mask.
+KERNEL_TOL, VECTOR_TOL, COS_TOL = 0.06, 0.12, 0.995
+
+
+@pytest.mark.parametrize("term", ["all", "adv", "cycle", "identity"])
+def test_gradients_match_oracle(term):
+  """Hand-scheduled backward vs autograd of the fp32 oracle, per trainable tensor. ``term``: keep only
+  one of the generators' three loss terms (adversarial / cycle / identity)."""
+  size, b, nres = 128, 2, 1
   nb, ob, x, y = _pair(size, b, nres)
+  w = {"all": (1.0, 10.0, 5.0), "adv": (1.0, 0.0, 0.0), "cycle": (0.0, 10.0, 0.0), "identity": (0.0, 0.0, 5.0)}[term]
+  nb.lambda_adv, nb.lambda_cycle, nb.lambda_identity = w
+  ob.losses.lambda_adv, ob.losses.lambda_cycle, ob.losses.lambda_identity = w
   sp = nb.plan_for(b)
   nb._load_inputs(sp, x, y)
   from tf2_cyclegan_b200.engine.native_backend import NETS
@@ -72,12 +89,18 @@ def test_gradients_match_oracle(size, b, nres):
       got = grads[n][name]
       err = ((got - ref).norm() / ref.norm().clamp_min(1e-12)).item()   # relative L2 error
       cos = torch.nn.functional.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
-      report.append((n, name, tuple(p.shape), err, cos))
-      vec = p.dim() == 1   # beta / bias: sums of many bf16-rounded values with heavy cancellation
-      if err > (0.4 if vec else 0.2) or cos < (0.92 if vec else 0.98):
+      report.append((n, name, tuple(p.shape), round(err, 4), round(cos, 5)))
+      vec = p.dim() == 1   # gamma / beta / bias: sums of many bf16-rounded values with heavy cancellation
+      if ref.norm().item() < 1e-9:
+        if got.norm().item() > 1e-6:
+          bad.append(report[-1])
+      elif err > (VECTOR_TOL if vec else KERNEL_TOL) or cos < COS_TOL - (0.01 if vec else 0.0):
         bad.append(report[-1])
+  worst_k = max((r for r in report if len(r[2]) > 1), key=lambda r: r[3])
+  worst_v = max((r for r in report if len(r[2]) == 1), key=lambda r: r[3])
+  print(f"gradient errors [{term}]: worst kernel {worst_k}, worst vector {worst_v}")
   for r in report:
-    print("grad", *r)
+    print("grad", term, *r)
   assert not bad, bad
 
 
@@ -122,6 +145,66 @@ def test_cuda_graph_replay_matches_eager_plan():
   for k in ra:
     assert abs(ra[k].item() - rg[k].item()) < 2e-3 * max(1.0, abs(ra[k].item())), k
   assert g.kernel_launches() > 0
+
+
+def test_replay_reproducibility():
+  """Two backends with the same seed fed the same batches: the only run-to-run freedom is the order of
+  fp32 atomic / split-K accumulation (InstanceNorm statistics, loss slots, wgrad bulk reduce-adds), so
+  after 5 steps losses agree to ~1e-5 relative and the weights to well below one bf16 step — and a
+  CUDA-graph replay of one backend is as reproducible as a fresh eager run."""
+  from tf2_cyclegan_b200.engine.cyclegan import build_specs
+  from tf2_cyclegan_b200.engine.native_backend import NETS, NativeBackend
+  from tf2_cyclegan_b200.parallel.strategy import Strategy
+  st = Strategy(device="cuda")
+  specs = build_specs(A(1))
+  runs = []
+  for use_graph in (True, True, False):
+    be = NativeBackend(specs, 2, st, seed=5, image_size=128, local_batch=2, use_graph=use_graph)
+    torch.manual_seed(0)
+    hist = []
+    for i in range(5):
+      x = torch.rand(2, 128, 128, 3, device="cuda") * 2 - 1
+      y = torch.rand(2, 128, 128, 3, device="cuda") * 2 - 1
+      hist.append({k: v.item() for k, v in be.train_step(x, y).items()})
+    runs.append((hist, {n: be.state[n].w.clone() for n in NETS}))
+  for other in runs[1:]:
+    for h0, h1 in zip(runs[0][0], other[0]):
+      for k in h0:
+        assert abs(h0[k] - h1[k]) <= 2e-4 * max(abs(h0[k]), 1e-2), (k, h0[k], h1[k])
+    for n in NETS:
+      d = (runs[0][1][n] - other[1][n]).abs().max().item()
+      assert d < 1e-4, (n, d)      # 5 Adam steps of lr 2e-4: a sign flip of one update would be 4e-4
+
+
+def test_multi_epoch_loss_curves_track_oracle(tmp_path):
+  """Quality evidence beyond a fixed batch: 3 epochs of the full runner (shuffled synthetic data,
+  partial last batch, test pass every epoch) with the native backend and with the fp32 autograd
+  oracle from the same seed; the per-epoch training curves and the test MAEs must stay together."""
+  from tf2_cyclegan_b200.cli import parse_args
+  from tf2_cyclegan_b200.runner import main
+  ea_mod = pytest.importorskip("tensorboard.backend.event_processing.event_accumulator")
+  curves, finals = {}, {}
+  for backend in ("native", "oracle"):
+    out = tmp_path / backend
+    argv = ["--output_dir", str(out), "--epochs", "3", "--image_size", "128", "--num_residual_blocks", "2",
+            "--synthetic_size", "9", "--batch_size", "2", "--backend", backend, "--verbose", "0",
+            "--dtype", "bf16" if backend == "native" else "fp32"]
+    finals[backend] = main(parse_args(argv))
+    ea = ea_mod.EventAccumulator(str(out), size_guidance={"tensors": 0}); ea.Reload()
+    import numpy as np
+    from tensorboard.util import tensor_util
+    curves[backend] = {t: [float(tensor_util.make_ndarray(e.tensor_proto)) for e in ea.Tensors(t)]
+                       for t in ("loss_G/total", "loss_F/total", "loss_G/cycle", "loss_X/loss", "loss_Y/loss")}
+  for t, nat in curves["native"].items():
+    orc = curves["oracle"][t]
+    assert len(nat) == len(orc) == 3
+    for e, (a, b) in enumerate(zip(nat, orc)):
+      assert abs(a - b) < 0.05 * max(abs(b), 0.05), (t, e, nat, orc)
+  for k, b in finals["oracle"].items():
+    a = finals["native"][k]
+    assert abs(a - b) < 0.08 * max(abs(b), 0.05), (k, a, b)
+  # and training made progress: the cycle term of the last epoch is below the first
+  assert curves["native"]["loss_G/cycle"][-1] < curves["native"]["loss_G/cycle"][0]
 
 
 def test_cli_end_to_end_native(tmp_path, capsys):

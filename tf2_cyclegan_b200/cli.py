@@ -23,7 +23,8 @@ def build_parser() -> argparse.ArgumentParser:
   parser.add_argument("--backend", default="auto", choices=["auto", "native", "oracle"])
   parser.add_argument("--device", default=None, choices=["cpu", "cuda"])
   parser.add_argument("--data_dir", default=None,
-                      help="folder with trainA/ trainB/ testA/ testB/ (default: synthetic)")
+                      help="TFDS data dir holding cycle_gan/horse2zebra/<version>/ (tfrecord shards), or a "
+                           "folder with trainA/ trainB/ testA/ testB/ images (default: synthetic)")
   parser.add_argument("--synthetic", action="store_true",
                       help="force the synthetic horse2zebra stand-in")
   parser.add_argument("--synthetic_size", default=None, type=int,

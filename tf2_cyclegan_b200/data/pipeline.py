@@ -11,9 +11,10 @@ once and frozen for the run; each domain is shuffled independently with a
 256-element buffer (unpaired); the last batch is partial and the replicas get
 uneven shares of it.
 
-Sources: TFDS is unavailable offline, so images come either from a CycleGAN
-style folder (``trainA/ trainB/ testA/ testB/``) or from a deterministic
-synthetic horse2zebra stand-in with the same split sizes (1067/1334/120/140).
+Sources: a TFDS-prepared ``cycle_gan/horse2zebra`` directory (the reference's
+source; read without TensorFlow by data/tfds.py), a CycleGAN style folder
+(``trainA/ trainB/ testA/ testB/``), or a deterministic synthetic horse2zebra
+stand-in with the same split sizes (1067/1334/120/140).
 The prefetcher stages batches in pinned host memory and copies them to the
 device on a side stream (the B200 counterpart of MultiDeviceIterator).
 """
@@ -83,6 +84,18 @@ class FolderSource:
   def get(self, split: str, index: int) -> np.ndarray:
     from PIL import Image
     return np.asarray(Image.open(self.files[split][index]).convert("RGB"))
+
+
+def open_source(data_dir: str):
+  """``--data_dir`` auto-detection: a CycleGAN image folder (trainA/ ...) or a TFDS-prepared
+  ``cycle_gan/horse2zebra`` directory (the reference's source, main.py:22-26)."""
+  if all(os.path.isdir(os.path.join(data_dir, s)) for s in H2Z_SPLITS):
+    return FolderSource(data_dir)
+  from .tfds import TFDSSource, find_tfds_dir
+  if find_tfds_dir(data_dir) is not None:
+    return TFDSSource(data_dir)
+  raise FileNotFoundError(f"{data_dir}: neither trainA/ trainB/ testA/ testB/ folders nor a TFDS-prepared "
+                          f"cycle_gan/horse2zebra directory")
 
 
 # ------------------------------------------------------------ preprocessing
@@ -337,7 +350,7 @@ def get_datasets(args, strategy: Strategy, buffer_size: int = 256, source=None):
   if source is None:
     data_dir = getattr(args, "data_dir", None)
     if data_dir:
-      source = FolderSource(data_dir)
+      source = open_source(data_dir)
     else:
       sizes = None
       lim = getattr(args, "synthetic_size", None)

@@ -71,6 +71,9 @@ class CycleGAN:
   def save_checkpoint(self, extra: Dict[str, object] | None = None):
     """save checkpoint to checkpoint_dir, overwrite if exists (chief only)."""
     sd = self.backend.state_dict()  # collective for sharded optimizer state
+    more = getattr(self.backend, "extra_state", lambda: {})()
+    if more:
+      extra = dict(extra or {}, backend=more)
     if self.strategy.is_chief:
       ckpt.save(self.checkpoint_prefix, sd, extra=extra,
                 fmt=self.checkpoint_format)
@@ -82,6 +85,8 @@ class CycleGAN:
     if ckpt.exists(self.checkpoint_prefix):
       sd, extra = ckpt.load(self.checkpoint_prefix)
       self.backend.load_state_dict(sd, expect_partial=expect_partial)
+      if hasattr(self.backend, "load_extra_state"):
+        self.backend.load_extra_state((extra or {}).get("backend", {}))
       self.extra_state = extra
       if self.strategy.is_chief:
         print(f"\nloaded checkpoint from {self.checkpoint_prefix}\n")

@@ -122,9 +122,10 @@ class StepPlan:
     # ---- P6: losses (+ their gradients)
     npx = S * S * 3
     nd = hd * wd
-    plan.add_mse_loss("loss.G_adv", Y.inp[-1].view(0), 1.0, 1.0 / (nd * gbs), 2.0 / (nd * gbs),
+    la = be.lambda_adv
+    plan.add_mse_loss("loss.G_adv", Y.inp[-1].view(0), 1.0, la / (nd * gbs), 2.0 * la / (nd * gbs),
                       sl("G_loss"), self.gd_adv["Y"].view(0), b, hd, wd)
-    plan.add_mse_loss("loss.F_adv", X.inp[-1].view(0), 1.0, 1.0 / (nd * gbs), 2.0 / (nd * gbs),
+    plan.add_mse_loss("loss.F_adv", X.inp[-1].view(0), 1.0, la / (nd * gbs), 2.0 * la / (nd * gbs),
                       sl("F_loss"), self.gd_adv["X"].view(0), b, hd, wd)
     lc, li = be.lambda_cycle, be.lambda_identity
     plan.add_l1_loss("loss.G_cycle", G.inp[-1].view(2 * b), yi, lc / (npx * gbs), lc / (npx * gbs),
@@ -235,6 +236,7 @@ class NativeBackend:
     self.image_size = image_size
     self.lambda_cycle = 10.0
     self.lambda_identity = 5.0
+    self.lambda_adv = 1.0     # weight of the generators' LSGAN term: 1 in the reference; a knob for tests
     self.use_graph = (os.environ.get("B2_NO_GRAPH", "0") != "1") if use_graph is None else use_graph
     self.world = strategy.world_size
     self.fused = (fused_allreduce in ("auto", "on")) and self.world > 1
@@ -515,20 +517,26 @@ class NativeBackend:
     return sd
 
   def load_state_dict(self, sd: Dict[str, torch.Tensor], expect_partial: bool = False) -> None:
-    missing: List[str] = []
+    """Restore weights + optimizer state. Like the reference's ``checkpoint.read()`` (main.py:162-170)
+    missing OPTIMIZER state is not an error: absent Adam slots / counters are (re)initialised to zero
+    with a warning (e.g. a bundle written before the first step, or weights-only exports). Missing
+    WEIGHTS raise unless ``expect_partial``."""
+    missing_w: List[str] = []
+    missing_opt: List[str] = []
     for n in NETS:
       st = self.state[n]
       cur_w = st.layout.unpack(self._full(n, st.w))
-      cur_m = st.layout.unpack(self._full(n, st.m))
-      cur_v = st.layout.unpack(self._full(n, st.v))
+      cur_m = {k: torch.zeros_like(v) for k, v in cur_w.items()}
+      cur_v = {k: torch.zeros_like(v) for k, v in cur_w.items()}
       for name in cur_w:
-        for store, key in ((cur_w, f"{n}/{name}/.ATTRIBUTES/VARIABLE_VALUE"),
-                           (cur_m, f"{n}/{name}/.OPTIMIZER_SLOT/{n}_optimizer/m/.ATTRIBUTES/VARIABLE_VALUE"),
-                           (cur_v, f"{n}/{name}/.OPTIMIZER_SLOT/{n}_optimizer/v/.ATTRIBUTES/VARIABLE_VALUE")):
+        for store, key, miss in (
+            (cur_w, f"{n}/{name}/.ATTRIBUTES/VARIABLE_VALUE", missing_w),
+            (cur_m, f"{n}/{name}/.OPTIMIZER_SLOT/{n}_optimizer/m/.ATTRIBUTES/VARIABLE_VALUE", missing_opt),
+            (cur_v, f"{n}/{name}/.OPTIMIZER_SLOT/{n}_optimizer/v/.ATTRIBUTES/VARIABLE_VALUE", missing_opt)):
           if key in sd:
             store[name] = sd[key].float()
           else:
-            missing.append(key)
+            miss.append(key)
       st.w.copy_(st.layout.pack(cur_w).to(self.device))
       st.m.copy_(st.layout.pack(cur_m).to(self.device))
       st.v.copy_(st.layout.pack(cur_v).to(self.device))
@@ -538,9 +546,36 @@ class NativeBackend:
       if key in sd:
         st.step.fill_(int(sd[key]))
       else:
-        missing.append(key)
+        st.step.zero_()
+        missing_opt.append(key)
     torch.cuda.synchronize(self.device)
     self.strategy.barrier()
-    if missing and not expect_partial:
-      raise KeyError(f"checkpoint is missing {len(missing)} keys, e.g. {missing[:3]} "
+    if missing_opt and self.strategy.is_chief:
+      print(f"[checkpoint] {len(missing_opt)} optimizer entries missing (e.g. {missing_opt[0]}): "
+            "Adam state for them starts from zero")
+    if missing_w and not expect_partial:
+      raise KeyError(f"checkpoint is missing {len(missing_w)} weight tensors, e.g. {missing_w[:3]} "
                      f"(pass expect_partial=True to ignore)")
+
+  # FP8 delayed-scaling state rides in the checkpoint's ``extra`` side-car, so the first step after a
+  # resume quantises with the scales it would have used without the interruption
+  def extra_state(self) -> Dict[str, object]:
+    out: Dict[str, object] = {}
+    if self.fp8:
+      out["fp8"] = {n: {"act_amax": self.state[n].act_amax.tolist(), "act_scale": self.state[n].act_scale.tolist(),
+                        "w_scale": self.state[n].w_scale.tolist(), "out_scale": self.state[n].out_scale.tolist()}
+                    for n in ("G", "F") if self.state[n].w8 is not None}
+    return out
+
+  def load_extra_state(self, extra: Dict[str, object]) -> None:
+    fp8 = (extra or {}).get("fp8")
+    if not (self.fp8 and fp8):
+      return
+    for n, d in fp8.items():
+      st = self.state[n]
+      if st.w8 is None:
+        continue
+      for k, v in d.items():
+        t = getattr(st, k)
+        if len(v) == t.numel():
+          t.copy_(torch.tensor(v, dtype=t.dtype))

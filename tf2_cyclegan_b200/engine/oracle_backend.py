@@ -155,7 +155,9 @@ class OracleBackend:
     return sd
 
   def load_state_dict(self, sd: Dict[str, torch.Tensor], expect_partial: bool = False) -> None:
-    missing = []
+    """Like ``checkpoint.read()`` (main.py:162-170): missing optimizer state is tolerated (warned
+    about, starts from zero); missing weights raise unless ``expect_partial``."""
+    missing, missing_opt = [], []
     for n in NETS:
       for name, p in self.params[n].items():
         key = f"{n}/{name}/.ATTRIBUTES/VARIABLE_VALUE"
@@ -170,7 +172,7 @@ class OracleBackend:
         if key in sd:
           hyper[hk] = float(sd[key])
         else:
-          missing.append(key)
+          missing_opt.append(key)
       opt.load_hyper_state(hyper)
       for name, p in self.params[n].items():
         for slot, store in (("m", opt.m), ("v", opt.v)):
@@ -178,7 +180,10 @@ class OracleBackend:
           if key in sd:
             store[name] = sd[key].to(p.device, p.dtype).clone()
           else:
-            missing.append(key)
+            missing_opt.append(key)
+    if missing_opt and self.strategy.rank == 0:
+      print(f"[checkpoint] {len(missing_opt)} optimizer entries missing (e.g. {missing_opt[0]}): "
+            "Adam state for them starts from zero")
     if missing and not expect_partial:
-      raise KeyError(f"checkpoint is missing {len(missing)} keys, e.g. {missing[:3]} "
+      raise KeyError(f"checkpoint is missing {len(missing)} weight tensors, e.g. {missing[:3]} "
                      f"(pass expect_partial=True to ignore)")

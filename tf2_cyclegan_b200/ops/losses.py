@@ -17,16 +17,17 @@ class LossHeads:
 
   def __init__(self, global_batch_size: int,
                lambda_cycle: float = LAMBDA_CYCLE,
-               lambda_identity: float = LAMBDA_IDENTITY):
+               lambda_identity: float = LAMBDA_IDENTITY, lambda_adv: float = 1.0):
     self.global_batch_size = global_batch_size
     self.lambda_cycle = lambda_cycle
     self.lambda_identity = lambda_identity
+    self.lambda_adv = lambda_adv       # 1 in the reference (main.py:176-179); a knob for per-term gradient tests
 
   def reduce_mean(self, per_sample: torch.Tensor) -> torch.Tensor:
     return per_sample.sum() / self.global_batch_size
 
   def generator_loss(self, discriminate_fake: torch.Tensor) -> torch.Tensor:
-    return self.reduce_mean(O.mse(torch.ones_like(discriminate_fake), discriminate_fake))
+    return self.lambda_adv * self.reduce_mean(O.mse(torch.ones_like(discriminate_fake), discriminate_fake))
 
   def cycle_loss(self, real: torch.Tensor, cycled: torch.Tensor) -> torch.Tensor:
     return self.lambda_cycle * self.reduce_mean(O.mae(real, cycled))

@@ -434,7 +434,12 @@ def _as_numpy(t) -> Tuple[np.ndarray, int]:
 def write_bundle(prefix: str, tensors: Dict[str, Any], extra: Optional[Dict[str, Any]] = None,
                  object_graph: bool = True) -> None:
   """Write ``tensors`` (key -> torch / numpy array, or ``bytes`` for a DT_STRING scalar) as a
-  one-shard TensorBundle. Atomic: both files are written under temporary names and renamed."""
+  one-shard TensorBundle. Both files are written under temporary names, fsynced and renamed (data
+  first, index last). The TF format has no field that could tie the two files together, so a crash
+  between the two renames leaves a NEW data file next to an OLD index: :func:`read_bundle` detects
+  that pair (data-file length vs the index's extents, then the per-tensor crc32c) and refuses it
+  instead of loading garbage. The native container (utils/checkpoint.py) carries a nonce and is
+  atomic in the strict sense."""
   os.makedirs(os.path.dirname(prefix) or ".", exist_ok=True)
   payload: Dict[str, Any] = dict(tensors)
   if object_graph and OBJECT_GRAPH_KEY not in payload:
@@ -495,6 +500,16 @@ def read_bundle(prefix: str, verify: bool = True) -> Tuple[Dict[str, torch.Tenso
 
   tensors: Dict[str, torch.Tensor] = {}
   info: Dict[str, Any] = {"extra": {}, "object_graph": None, "strings": {}}
+  if verify:   # a writer lays tensors out back to back: the index's extents must cover the shard exactly
+    extent: Dict[int, int] = {}
+    for k, v in entries[1:]:
+      e = decode_entry(v)
+      extent[e["shard_id"]] = max(extent.get(e["shard_id"], 0), e["offset"] + e["size"])
+    for i, end in extent.items():
+      have = os.path.getsize(f"{prefix}.data-{i:05d}-of-{num_shards:05d}")
+      if have != end:
+        raise IOError(f"{prefix}: data shard {i} is {have} bytes but the index describes {end}: index and data "
+                      "files are from different writes (interrupted save?)")
   for k, v in entries[1:]:
     key = k.decode()
     e = decode_entry(v)

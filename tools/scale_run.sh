@@ -1,33 +1,19 @@
 #!/bin/bash
-# 1/2/4/8-GPU scaling + fused all-reduce validation + sweep, in one multi-GPU gpurun call.
-cd "$(dirname "$0")/.."
-mkdir -p gpurun_out
-NG=$(python -c "import torch; print(torch.cuda.device_count())")
-echo "gpus=$NG"
-timeout 600 python -m pytest tests/test_fused_allreduce.py tests/test_native_dp.py -m gpu -x -q -s > gpurun_out/pytest_ar_w$NG.log 2>&1; tail -4 gpurun_out/pytest_ar_w$NG.log
-for n in ${SCALE_NS:-1 2 4 8}; do
-  [ $n -le $NG ] || continue
-  if [ $n -eq 1 ]; then
-    timeout 300 python bench.py --gpus 1 --steps 15 --warmup 4 > gpurun_out/scale_n$n.json 2> gpurun_out/scale_n$n.err
-  else
-    timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600+n)) bench.py --gpus $n --steps 15 --warmup 4 > gpurun_out/scale_n$n.json 2> gpurun_out/scale_n$n.err
-  fi
-  grep '"metric"' gpurun_out/scale_n$n.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('N=%d %.1f img/s %.2f ms e2e %.1f' % (d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value']))" || tail -3 gpurun_out/scale_n$n.err
+# One multi-GPU validation pass on an N-GPU box (gpurun --gpus N -- tools/scale_run.sh N):
+# fused all-reduce tests (both forms + stress), native DP test, quick all-reduce sweep, train-step
+# bench in push and pull form, the stand-in baseline, and a 1-GPU bench on the same box.
+N=${1:-8}
+out=gpurun_out/scale_r2_n$N
+mkdir -p $out
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+timeout 400 python -m pytest tests/test_fused_allreduce.py -m gpu -x -q > $out/pytest_fused_allreduce.log 2>&1; tail -4 $out/pytest_fused_allreduce.log
+timeout 500 python -m pytest tests/test_native_dp.py -m gpu -x -q > $out/pytest_native_dp.log 2>&1; tail -4 $out/pytest_native_dp.log
+timeout 300 $TR --master-port 29511 tools/allreduce_bench.py ${2:---quick} > $out/allreduce_sweep.log 2>&1; grep -v "^{" $out/allreduce_sweep.log | tail -20
+cp gpurun_out/allreduce_sweep_w$N.json $out/ 2>/dev/null
+for mode in push pull; do
+  timeout 200 $TR --master-port 29512 bench.py --gpus $N --steps 30 --warmup 5 --ar_mode $mode > $out/bench_native_$mode.json 2> $out/bench_native_$mode.err
+  tail -1 $out/bench_native_$mode.json | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$mode', d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e']['ms_per_step'], d['collective'], d['clocks'])"
 done
-# NCCL baseline path for comparison at full width
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29650 bench.py --gpus $NG --steps 15 --warmup 4 --fused_allreduce off --no_e2e > gpurun_out/scale_n${NG}_nccl.json 2> gpurun_out/scale_nccl.err
-grep '"metric"' gpurun_out/scale_n${NG}_nccl.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('NCCL path N=%d %.1f img/s %.2f ms' % (d['n_gpus'], d['value'], d['ms_per_step']))" || tail -3 gpurun_out/scale_nccl.err
-for w in ${SWEEP_WS:-2 8}; do
-  [ $w -le $NG ] || continue
-  timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $w --master-addr 127.0.0.1 --master-port $((29700+w)) tools/allreduce_bench.py > gpurun_out/sweep_w$w.log 2>&1
-  python - <<PY
-import json
-try:
-  d=json.load(open("gpurun_out/allreduce_sweep_w$w.json"))
-  print("sweep world", d["world"], "multicast", d["multicast"])
-  for r in d["rows"]:
-    print("  %12d B fused %8.3f ms (%6.1f GB/s bus, %4.1f%% of 900)  nccl %8.3f ms (%6.1f)  nccl+adam %8.3f ms" % (r["bytes"], r["fused_ms"], r["fused_bus_GBs"], 100*r["fused_frac_of_900"], r["nccl_allreduce_ms"], r["nccl_bus_GBs"], r["nccl_plus_adam_ms"]))
-except Exception as e:
-  print("sweep failed", e); print(open("gpurun_out/sweep_w$w.log").read()[-1500:])
-PY
-done
+timeout 200 $TR --master-port 29513 bench.py --gpus $N --steps 20 --warmup 5 --impl standin > $out/bench_standin.json 2> $out/bench_standin.err
+tail -1 $out/bench_standin.json | cut -c1-300
+python bench.py --steps 30 --warmup 5 > $out/bench_native_n1_same_box.json 2>/dev/null; cut -c100-330 $out/bench_native_n1_same_box.json
