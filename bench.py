@@ -201,8 +201,9 @@ def main():
     raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}")
 
   if a.ar_mode:
+    from tf2_cyclegan_b200.config import ENGINE
     from tf2_cyclegan_b200.parallel import fused_allreduce
-    fused_allreduce.DEFAULT_MODE = a.ar_mode
+    ENGINE.ar_mode = fused_allreduce.DEFAULT_MODE = a.ar_mode
   strategy = Strategy(device="cuda")
   dev = strategy.device
   gbs = a.batch_size * world
@@ -260,7 +261,7 @@ def main():
   e2e = None
   if not a.no_e2e:
     api = None
-    if a.impl == "native" and os.environ.get("B2_E2E_PIPELINE", "1") != "0":
+    if a.impl == "native":
       # the repo's own input pipeline (what runner.train iterates): host dataset -> native batch
       # gather into rotating pinned staging slots -> async H2D on a side stream, two batches
       # ahead -> train step -> D2H read of the loss, every step

@@ -26,7 +26,7 @@ class FakePlan:
 
   def add_conv_gemm(self, name, a_maps, b_map, taps, cin_blocks, tiles_w, tiles_h, bw, bh, w_limit,
                     out, sn, sh, sw, cout, bias, act, stats, block_n, b_mn, num_images, phases, out_scale=0, fp8=False,
-                    ts_map=b"", ts=()):
+                    ts_map=b"", ts=(), h_limit=0):
     if ts:   # tap sharing: one halo tile per channel block, taps = row shifts inside it
       nbox, box_step, box_bytes, pitch, odw, odh, sbo = ts
       td = decode(ts_map)
@@ -94,6 +94,9 @@ class FakePlan:
   def add_event_wait(self, name, lane, ref):
     assert 0 <= lane < 5 and self.ops[ref][0] == "record"
     return self._add("wait", name, lane, ref)
+
+  def set_nvtx(self, on):
+    self.nvtx = bool(on)
 
   def __getattr__(self, item):
     if item.startswith("add_"):

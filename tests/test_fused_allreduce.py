@@ -143,7 +143,7 @@ def _free_port():
     return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("nvls", ["auto", "0"])
+@pytest.mark.parametrize("nvls", ["auto", "off"])
 def test_fused_allreduce_adam_matches_nccl(tmp_path, nvls):
   ngpu = torch.cuda.device_count()
   if ngpu < 2:
@@ -151,7 +151,7 @@ def test_fused_allreduce_adam_matches_nccl(tmp_path, nvls):
   world = 2 if ngpu < 4 else (4 if ngpu < 8 else 8)
   script = tmp_path / "worker.py"
   script.write_text(WORKER)
-  env = dict(os.environ, B2_ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), B2_NVLS=nvls)
+  env = dict(os.environ, B2_ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), B2_CONFIG=f"nvls={nvls}")
   cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
          "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), str(script)]
   r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)

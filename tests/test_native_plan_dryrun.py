@@ -10,7 +10,8 @@ class A:
     self.num_residual_blocks = nres
 
 
-@pytest.mark.parametrize("size,b,nres", [(128, 2, 1), (256, 1, 9), (512, 1, 2)])
+@pytest.mark.parametrize("size,b,nres", [(128, 2, 1), (256, 1, 9), (512, 1, 2), (96, 1, 1), ((192, 320), 1, 2),
+                                         ((40, 72), 2, 1)])
 def test_step_plan_builds_and_is_well_formed(monkeypatch, size, b, nres):
   fake_native.install(monkeypatch)
   monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
@@ -34,10 +35,11 @@ def test_step_plan_builds_and_is_well_formed(monkeypatch, size, b, nres):
     assert f"opt.{n}.adam" in names and f"opt.{n}.step" in names
   # tap sharing: every residual 3x3 conv (forward: 8x16 boxed halo; dgrad: flat halo) qualifies
   kinds = {o[1]: o[0] for o in sp.plan.ops}
-  res = [n for n in names if ".res" in n and (".fwd" in n or (".dgrad" in n and size <= 256))]
-  assert res and all(kinds[n] == "conv_gemm_ts" for n in res), [n for n in res if kinds[n] != "conv_gemm_ts"][:4]
-  if size > 256:   # flat halo of a 130-wide padded row (2 x 200 rows) exceeds the A stage: per-tap kernel
-    assert all(kinds[n] == "conv_gemm" for n in names if ".res" in n and ".dgrad" in n)
+  if isinstance(size, int) and size >= 128:   # (other shapes: only that the plan builds and validates)
+    res = [n for n in names if ".res" in n and (".fwd" in n or (".dgrad" in n and size <= 256))]
+    assert res and all(kinds[n] == "conv_gemm_ts" for n in res), [n for n in res if kinds[n] != "conv_gemm_ts"][:4]
+    if size > 256:   # flat halo of a 130-wide padded row (2 x 200 rows) exceeds the A stage: per-tap kernel
+      assert all(kinds[n] == "conv_gemm" for n in names if ".res" in n and ".dgrad" in n)
   assert kinds[next(n for n in names if n.startswith("G.stem.fwd"))] == "conv_gemm"
   # every conv layer of every network gets exactly one wgrad group in the full backward
   full = names[sp.marks["test_end"]:]

@@ -10,6 +10,10 @@ class A:
     self.num_residual_blocks = nres
 
 
+def _hw(size):
+  return (size, size) if isinstance(size, int) else size
+
+
 def _pair(size, b, nres, seed=11):
   from tf2_cyclegan_b200.engine.cyclegan import build_specs
   from tf2_cyclegan_b200.engine.native_backend import NativeBackend
@@ -24,8 +28,9 @@ def _pair(size, b, nres, seed=11):
     for p in ob.params[n].values():
       p.data.copy_(p.data.to(torch.bfloat16).float())
   torch.manual_seed(3)
-  x = torch.rand(b, size, size, 3, device="cuda") * 2 - 1
-  y = torch.rand(b, size, size, 3, device="cuda") * 2 - 1
+  h, w = _hw(size)
+  x = torch.rand(b, h, w, 3, device="cuda") * 2 - 1
+  y = torch.rand(b, h, w, 3, device="cuda") * 2 - 1
   return nb, ob, x, y
 
 
@@ -33,7 +38,8 @@ def _rel(a, b):
   return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
 
 
-@pytest.mark.parametrize("size,b,nres", [(128, 2, 1), (256, 1, 2)])
+# (96, 160): neither square nor a power of two — partial tile rows, per-tap kernels, rectangular buffers
+@pytest.mark.parametrize("size,b,nres", [(128, 2, 1), (256, 1, 2), ((96, 160), 2, 1), (72, 1, 1)])
 def test_forward_losses_and_cycle_match_oracle(size, b, nres):
   nb, ob, x, y = _pair(size, b, nres)
   rn = nb.test_step(x, y)
@@ -145,6 +151,20 @@ def test_cuda_graph_replay_matches_eager_plan():
   for k in ra:
     assert abs(ra[k].item() - rg[k].item()) < 2e-3 * max(1.0, abs(ra[k].item())), k
   assert g.kernel_launches() > 0
+
+
+def test_train_steps_on_a_rectangular_image_track_oracle():
+  """cyclegan/model.py:129 leaves input_shape free: 3 full train steps at 96 x 160 (backward through
+  partial tiles, stride-2 / transposed layers at 48 x 80 and 24 x 40) vs the autograd oracle."""
+  nb, ob, x, y = _pair((96, 160), 2, 1)
+  for i in range(3):
+    rn = nb.train_step(x, y)
+    ro = ob.train_step(x, y)
+  torch.cuda.synchronize()
+  for k in ro:
+    assert abs(rn[k].item() - ro[k].item()) < 5e-2 * max(abs(ro[k].item()), 0.05), (k, rn[k].item(), ro[k].item())
+  k = "G/layer_with_weights-2/kernel/.ATTRIBUTES/VARIABLE_VALUE"
+  assert (nb.state_dict()[k] - ob.state_dict()[k]).abs().max().item() < 2e-3
 
 
 def test_replay_reproducibility():

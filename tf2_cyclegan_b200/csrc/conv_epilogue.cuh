@@ -44,7 +44,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, __nv
   for (int itr = 0; itr < kStoreIters; ++itr) {
     const int r = ew * 32 + itr * RPI + lane / CH;
     const int wl = r % p.bw, hl = r / p.bw;
-    row_off[itr] = (w0 + wl < p.w_limit)
+    row_off[itr] = (w0 + wl < p.w_limit && h0 + hl < p.h_limit)
                        ? img * p.out_sn + (h0 + hl) * p.out_sh + (w0 + wl) * p.out_sw
                        : -1;
   }
@@ -173,7 +173,7 @@ __device__ __forceinline__ void conv_epilogue_tile(const ConvGemmParams& p, __nv
     } else if (n_valid > 0) {
       const int r = e;
       const int wl = r % p.bw, hl = r / p.bw;
-      if (w0 + wl < p.w_limit) {
+      if (w0 + wl < p.w_limit && h0 + hl < p.h_limit) {
         __nv_bfloat16* dst = out_base + img * p.out_sn + (h0 + hl) * p.out_sh +
                              (w0 + wl) * p.out_sw + n0 + c0;
         for (int c = 0; c < n_valid; ++c) {

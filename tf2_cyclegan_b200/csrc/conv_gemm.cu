@@ -21,6 +21,15 @@
 
 namespace b2 {
 
+// Kernel options of this process (set once from tf2_cyclegan_b200/config.py through
+// _C.set_kernel_options; no environment reads here). dbg != 0 are timing experiments.
+struct KernelOptions {
+  int dbg = 0;          // 1 skip epilogue, 2 skip MMAs, 3 skip TMA loads, 4 skip global stores
+  bool two_cta = true;  // cta_group::2 kernels for wide layers
+  int stages = 0;       // cap on the 1-CTA kernel's smem ring depth
+  int grid = 0;         // cap on the 1-CTA kernel's persistent grid
+};
+static KernelOptions g_opt;
 int dbg_flag();
 
 template <int BLOCK_N>
@@ -234,13 +243,7 @@ static void launch_t(const ConvGemmParams& p, int num_images, cudaStream_t strea
     configured = true;
   }
   const int total = p.tiles_w * p.tiles_h * num_images * ((p.cout + BLOCK_N - 1) / BLOCK_N) * p.num_phases;
-  static int dbg_stages = -1, dbg_grid = -1;
-  if (dbg_stages < 0) {
-    const char* e = getenv("B2_STAGES");
-    dbg_stages = e ? atoi(e) : 0;
-    e = getenv("B2_GRID");
-    dbg_grid = e ? atoi(e) : 0;
-  }
+  const int dbg_stages = g_opt.stages, dbg_grid = g_opt.grid;
   int nst = Cfg::kStages;
   if (dbg_stages > 0 && dbg_stages < nst) nst = dbg_stages;
   int cap = num_sms();
@@ -254,22 +257,13 @@ bool launch_conv_gemm_2cta(const ConvGemmParams& p, int block_n, bool b_mn_major
 bool launch_conv_gemm_ts(const ConvGemmParams& p, int block_n, bool b_mn_major, int num_images,
                          cudaStream_t stream);
 
-int dbg_flag() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("B2_DBG");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
-}
-
-static bool use_2cta() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("B2_2CTA");
-    v = (e == nullptr || e[0] != '0') ? 1 : 0;
-  }
-  return v == 1;
+int dbg_flag() { return g_opt.dbg; }
+bool use_2cta() { return g_opt.two_cta; }
+void set_kernel_options(int dbg, bool two_cta, int stages, int grid) {
+  g_opt.dbg = dbg;
+  g_opt.two_cta = two_cta;
+  g_opt.stages = stages;
+  g_opt.grid = grid;
 }
 
 void launch_conv_gemm(const ConvGemmParams& p, int block_n, bool b_mn_major, int num_images,

@@ -43,6 +43,7 @@ struct ConvGemmParams {
   int tiles_w, tiles_h;         // tiles per image along w / h
   int bw, bh;                   // tile = bw x bh pixels, bw * bh == 128
   int w_limit;                  // rows with w coordinate >= w_limit are not stored (flat tails)
+  int h_limit;                  // rows with h coordinate >= h_limit are not stored (partial last tile row)
   __nv_bfloat16* out;           // NHWC-like: out[n*sn + h*sh + w*sw + c]
   long long out_sn, out_sh, out_sw;
   int cout;                     // valid output channels

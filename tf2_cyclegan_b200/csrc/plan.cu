@@ -24,6 +24,10 @@
 namespace py = pybind11;
 using namespace b2;
 
+namespace b2 {
+void set_kernel_options(int dbg, bool two_cta, int stages, int grid);   // conv_gemm.cu
+}
+
 namespace {
 
 void check(cudaError_t e, const char* what) {
@@ -272,7 +276,7 @@ class Plan {
                     int bh, int w_limit, uint64_t out, long long sn, long long sh, long long sw,
                     int cout, uint64_t bias, int act, uint64_t stats, int block_n, bool b_mn,
                     int num_images, std::vector<std::tuple<int, int, long long>> phases,
-                    uint64_t out_scale, bool fp8, py::bytes ts_map, std::vector<int> ts) {
+                    uint64_t out_scale, bool fp8, py::bytes ts_map, std::vector<int> ts, int h_limit) {
     auto p = std::make_shared<ConvGemmParams>();
     memset(p.get(), 0, sizeof(ConvGemmParams));
     if (a_maps.empty() || a_maps.size() > kMaxAMaps) throw std::runtime_error("bad a_maps");
@@ -282,6 +286,7 @@ class Plan {
     if (bw * bh != 128) throw std::runtime_error("conv_gemm tile must be 128 pixels");
     p->cin_blocks = cin_blocks; p->tiles_w = tiles_w; p->tiles_h = tiles_h;
     p->bw = bw; p->bh = bh; p->w_limit = w_limit;
+    p->h_limit = h_limit > 0 ? h_limit : tiles_h * bh;
     p->out = P<__nv_bfloat16>(out); p->out_sn = sn; p->out_sh = sh; p->out_sw = sw;
     p->cout = cout; p->bias = P<const float>(bias); p->act = act; p->stats = P<float>(stats);
     p->out_scale = P<const float>(out_scale); p->fp8 = fp8 ? 1 : 0;
@@ -489,7 +494,7 @@ class Plan {
   std::vector<Op> ops_;
   int lane_ = 0;
   // NVTX range per op (name = the op label) for timeline tools; on by B2_NVTX=1 or set_nvtx()
-  bool nvtx_ = [] { const char* e = getenv("B2_NVTX"); return e && e[0] == '1'; }();
+  bool nvtx_ = false;
   cudaStream_t side_[kLanes] = {};
   cudaEvent_t lane_ev_[kLanes] = {};
 };
@@ -500,6 +505,8 @@ PYBIND11_MODULE(_C, m) {
   m.doc() = "b200-cyclegan native runtime (sm_100a kernels + plan executor)";
   m.def("encode_tmap", &encode_tmap, py::arg("ptr"), py::arg("dtype"), py::arg("dims"),
         py::arg("strides_bytes"), py::arg("box"), py::arg("swizzle") = 3);
+  m.def("set_kernel_options", &b2::set_kernel_options, py::arg("kernel_debug"), py::arg("two_cta"),
+        py::arg("stages"), py::arg("grid"), "process-wide kernel options (tf2_cyclegan_b200/config.py)");
   m.def("set_ew_stream", &b2::set_ew_stream, "InstanceNorm kernels: true = bulk-copy ring (default), false = direct");
   m.def("ew_stream", &b2::ew_stream);
   m.def("device_sync", []() { check(cudaDeviceSynchronize(), "cudaDeviceSynchronize"); });
@@ -523,7 +530,8 @@ PYBIND11_MODULE(_C, m) {
            py::arg("bh"), py::arg("w_limit"), py::arg("out"), py::arg("sn"), py::arg("sh"), py::arg("sw"),
            py::arg("cout"), py::arg("bias"), py::arg("act"), py::arg("stats"), py::arg("block_n"),
            py::arg("b_mn"), py::arg("num_images"), py::arg("phases"), py::arg("out_scale") = 0,
-           py::arg("fp8") = false, py::arg("ts_map") = py::bytes(), py::arg("ts") = std::vector<int>())
+           py::arg("fp8") = false, py::arg("ts_map") = py::bytes(), py::arg("ts") = std::vector<int>(),
+           py::arg("h_limit") = 0)
       .def("add_wgrad", &Plan::add_wgrad)
       .def("add_in_apply", &Plan::add_in_apply, py::arg("name"), py::arg("x"), py::arg("stats"),
            py::arg("gamma"), py::arg("beta"), py::arg("inv_count"), py::arg("eps"), py::arg("act"),

@@ -348,14 +348,8 @@ static void launch2_t(const WgradParams& p, int ksplit, cudaStream_t stream) {
   cudaLaunchKernelEx(&cfg, wgrad_gemm2_kernel<BLOCK_N>, p, dbg_flag());
 }
 
-static bool wgrad_use_2cta() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("B2_2CTA");
-    v = (e == nullptr || e[0] != '0') ? 1 : 0;
-  }
-  return v == 1;
-}
+bool use_2cta();   // conv_gemm.cu: process-wide kernel options
+static bool wgrad_use_2cta() { return use_2cta(); }
 
 bool launch_wgrad_multi(const WgradParams& p, int ksplit, cudaStream_t stream);
 

@@ -48,7 +48,7 @@ class CycleGAN:
     seed = int(getattr(args, "seed", 1234))
     size = int(getattr(args, "image_size", 256))
     if backend == "auto":
-      native_ok = strategy.device.type == "cuda" and size >= 128 and size & (size - 1) == 0
+      native_ok = strategy.device.type == "cuda" and size >= 32 and size % 8 == 0
       backend = "native" if native_ok else "oracle"
     if backend == "oracle" and dtype == "fp8":
       dtype = "bf16"

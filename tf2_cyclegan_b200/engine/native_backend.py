@@ -16,12 +16,12 @@ Schedule (exploits the reference's gradient routing):
 """
 from __future__ import annotations
 
-import os
 from collections import OrderedDict
 from typing import Dict, List, Optional
 
 import torch
 
+from ..config import ENGINE
 from ..models import oracle_net
 from ..models.spec import NetSpec
 from ..ops import native as nv
@@ -46,9 +46,10 @@ class StepPlan:
     C = nv.load()
     self.b = b
     dev = be.device
-    S = be.image_size
-    self.x_in = torch.zeros(b, S, S, 3, device=dev)
-    self.y_in = torch.zeros(b, S, S, 3, device=dev)
+    S = be.image_hw
+    IH, IW = S
+    self.x_in = torch.zeros(b, IH, IW, 3, device=dev)
+    self.y_in = torch.zeros(b, IH, IW, 3, device=dev)
     self.slots = be.slots          # loss / metric accumulators (peer-readable on the fused path)
     self.ex: Dict[str, NetExec] = {
         "G": NetExec(be.specs["G"], be.state["G"], 3 * b, S, dev, "G", fp8=be.fp8),
@@ -63,6 +64,7 @@ class StepPlan:
     self.gd_adv = {"X": Buf(b, hd, wd, 8, device=dev), "Y": Buf(b, hd, wd, 8, device=dev)}
     gbs = be.global_batch_size
     plan = C.Plan()
+    plan.set_nvtx(ENGINE.nvtx)
     self.plan = plan
     self.marks: Dict[str, int] = {}
     sl = lambda k: self.slots[SLOT[k]:].data_ptr()
@@ -78,10 +80,10 @@ class StepPlan:
         be.state[n].emit_fp8_refresh(plan, n)
     # ---- P1: inputs -> 8-channel padded bf16 layouts
     xi, yi = self.x_in.data_ptr(), self.y_in.data_ptr()
-    plan.add_img_prep("prep.x->G0,X1", xi, NULL_VIEW, G.inp[0].view(0), 3, X.inp[0].view(b), b, S, S)
-    plan.add_img_prep("prep.x->F1", xi, NULL_VIEW, F.inp[0].view(b), 3, NULL_VIEW, b, S, S)
-    plan.add_img_prep("prep.y->F0,Y1", yi, NULL_VIEW, F.inp[0].view(0), 3, Y.inp[0].view(b), b, S, S)
-    plan.add_img_prep("prep.y->G1", yi, NULL_VIEW, G.inp[0].view(b), 3, NULL_VIEW, b, S, S)
+    plan.add_img_prep("prep.x->G0,X1", xi, NULL_VIEW, G.inp[0].view(0), 3, X.inp[0].view(b), b, IH, IW)
+    plan.add_img_prep("prep.x->F1", xi, NULL_VIEW, F.inp[0].view(b), 3, NULL_VIEW, b, IH, IW)
+    plan.add_img_prep("prep.y->F0,Y1", yi, NULL_VIEW, F.inp[0].view(0), 3, Y.inp[0].view(b), b, IH, IW)
+    plan.add_img_prep("prep.y->G1", yi, NULL_VIEW, G.inp[0].view(b), 3, NULL_VIEW, b, IH, IW)
     # Two lanes: lane 0 = {G, Y}, lane 1 = {F, X}. Inside a fork/join region the lanes run
     # on two streams, so one network's tail wave overlaps the other's kernels.
     two = be.two_lanes
@@ -105,9 +107,9 @@ class StepPlan:
     join("fwd")
     # ---- P3: fakes -> inputs of the cycle pass and of the discriminators
     plan.add_img_prep("prep.fake_y->F2,Y0", 0, G.inp[-1].view(0), F.inp[0].view(2 * b), 3,
-                      Y.inp[0].view(0), b, S, S)
+                      Y.inp[0].view(0), b, IH, IW)
     plan.add_img_prep("prep.fake_x->G2,X0", 0, F.inp[-1].view(0), G.inp[0].view(2 * b), 3,
-                      X.inp[0].view(0), b, S, S)
+                      X.inp[0].view(0), b, IH, IW)
     # ---- P4: cycle pass
     fork("cycle")
     lane(0); G.forward(plan, 2 * b, b)
@@ -120,7 +122,7 @@ class StepPlan:
     lane(1); X.forward(plan, 0, 2 * b)
     join("dis")
     # ---- P6: losses (+ their gradients)
-    npx = S * S * 3
+    npx = IH * IW * 3
     nd = hd * wd
     la = be.lambda_adv
     plan.add_mse_loss("loss.G_adv", Y.inp[-1].view(0), 1.0, la / (nd * gbs), 2.0 * la / (nd * gbs),
@@ -129,13 +131,13 @@ class StepPlan:
                       sl("F_loss"), self.gd_adv["X"].view(0), b, hd, wd)
     lc, li = be.lambda_cycle, be.lambda_identity
     plan.add_l1_loss("loss.G_cycle", G.inp[-1].view(2 * b), yi, lc / (npx * gbs), lc / (npx * gbs),
-                     sl("G_cycle"), sl("err_y_cycle"), 1.0 / (npx * gbs), G.gout_final.view(2 * b), b, S, S)
+                     sl("G_cycle"), sl("err_y_cycle"), 1.0 / (npx * gbs), G.gout_final.view(2 * b), b, IH, IW)
     plan.add_l1_loss("loss.G_identity", G.inp[-1].view(b), yi, li / (npx * gbs), li / (npx * gbs),
-                     sl("G_identity"), sl("err_y_same"), 1.0 / (npx * gbs), G.gout_final.view(b), b, S, S)
+                     sl("G_identity"), sl("err_y_same"), 1.0 / (npx * gbs), G.gout_final.view(b), b, IH, IW)
     plan.add_l1_loss("loss.F_cycle", F.inp[-1].view(2 * b), xi, lc / (npx * gbs), lc / (npx * gbs),
-                     sl("F_cycle"), sl("err_x_cycle"), 1.0 / (npx * gbs), F.gout_final.view(2 * b), b, S, S)
+                     sl("F_cycle"), sl("err_x_cycle"), 1.0 / (npx * gbs), F.gout_final.view(2 * b), b, IH, IW)
     plan.add_l1_loss("loss.F_identity", F.inp[-1].view(b), xi, li / (npx * gbs), li / (npx * gbs),
-                     sl("F_identity"), sl("err_x_same"), 1.0 / (npx * gbs), F.gout_final.view(b), b, S, S)
+                     sl("F_identity"), sl("err_x_same"), 1.0 / (npx * gbs), F.gout_final.view(b), b, IH, IW)
     for n in ("X", "Y"):
       D = self.ex[n]
       plan.add_mse_loss(f"loss.{n}_real", D.inp[-1].view(b), 1.0, 0.5 / (nd * gbs), 1.0 / (nd * gbs),
@@ -225,23 +227,28 @@ class NativeBackend:
     if dtype not in ("bf16", "fp8"):
       raise NotImplementedError(f"native backend: dtype {dtype!r} is not available (bf16 | fp8)")
     self.fp8 = dtype == "fp8"   # residual-block forward convs in E4M3 (per-tensor delayed scaling)
-    if image_size < 128 or image_size & (image_size - 1):
-      raise ValueError("native backend: image_size must be a power of two >= 128 "
-                       "(every layer must tile into 128-pixel boxes); use --backend oracle")
+    hw = (image_size, image_size) if isinstance(image_size, int) else tuple(int(v) for v in image_size)
+    if len(hw) != 2 or min(hw) < 32 or hw[0] % 8 or hw[1] % 8:
+      # three stride-2 stages in the discriminator (and two in the generators) must see even inputs;
+      # anything else the model admits (cyclegan/model.py:129: input_shape is free) runs natively:
+      # tiles are 128 pixels wide x high with a masked partial last tile row
+      raise ValueError("native backend: image height and width must be multiples of 8 and >= 32; "
+                       "use --backend oracle for other shapes")
     nv.load()
     self.specs = specs
     self.strategy = strategy
     self.device = strategy.device
     self.global_batch_size = global_batch_size
     self.image_size = image_size
+    self.image_hw = hw
     self.lambda_cycle = 10.0
     self.lambda_identity = 5.0
     self.lambda_adv = 1.0     # weight of the generators' LSGAN term: 1 in the reference; a knob for tests
-    self.use_graph = (os.environ.get("B2_NO_GRAPH", "0") != "1") if use_graph is None else use_graph
+    self.use_graph = ENGINE.use_graph if use_graph is None else use_graph
     self.world = strategy.world_size
     self.fused = (fused_allreduce in ("auto", "on")) and self.world > 1
-    self.two_lanes = os.environ.get("B2_ONE_STREAM", "0") != "1"
-    self.wgrad_lanes = os.environ.get("B2_WGRAD_LANES", "1") != "0"
+    self.two_lanes = ENGINE.lanes >= 2
+    self.wgrad_lanes = ENGINE.lanes >= 4
     gen = torch.Generator().manual_seed(seed)
     self.state: Dict[str, NetState] = OrderedDict()
     self.symm = None

@@ -133,9 +133,9 @@ def _out_hw(l: ConvLayer, h: int, w: int) -> Tuple[int, int]:
 
 
 class NetExec:
-  """Buffers + op emission for ``nb`` images of one network at resolution ``size``."""
+  """Buffers + op emission for ``nb`` images of one network at resolution ``size`` (int or (h, w))."""
 
-  def __init__(self, spec: NetSpec, state: NetState, nb: int, size: int, device, tag: str,
+  def __init__(self, spec: NetSpec, state: NetState, nb: int, size, device, tag: str,
                fp8: bool = False):
     self.spec, self.st, self.nb, self.size, self.tag = spec, state, nb, size, tag
     self.fp8 = fp8 and any(fp8_ok(l) for l in spec.layers)
@@ -146,7 +146,7 @@ class NetExec:
     dev = device
     # resolution of every layer input / output
     self.in_hw: List[Tuple[int, int]] = []
-    h = w = size
+    h, w = (size, size) if isinstance(size, int) else size
     for l in self.layers:
       self.in_hw.append((h, w))
       h, w = _out_hw(l, h, w)
@@ -475,7 +475,7 @@ class NetExec:
         for b in (0, 1):
           dy_maps.append(dY.tmap_parity(a, b, kbw, kbh, n0, nimg))
           taps += [(t[0], len(dy_maps) - 1, t[2], t[3], t[4]) for t in no.taps_convT_phase(a, b, l.cin)]
-      no.add_wgrad(plan, name, dy_maps, [amap], taps, wi // kbw, hi // kbh, kbw, kbh, nimg, l.cin,
+      no.add_wgrad(plan, name, dy_maps, [amap], taps, wi // kbw, -(-hi // kbh), kbw, kbh, nimg, l.cin,
                    l.cout, dw, ldw)
       return
     if j in self.w_dgrad and not is_small_cin(l):
@@ -507,7 +507,7 @@ class NetExec:
     else:
       maps = [src.tmap_interior(kbw, kbh, n0, nimg)]
       taps, cin = no.taps_conv(l.k, l.cin, origin=-self._pad_before(j)), l.cin
-    no.add_wgrad(plan, name, dy_map, maps, taps, wo // kbw, ho // kbh, kbw, kbh, nimg, cin, l.cout,
+    no.add_wgrad(plan, name, dy_map, maps, taps, wo // kbw, -(-ho // kbh), kbw, kbh, nimg, cin, l.cout,
                  dw, ldw)
 
   def _dgrad(self, plan, j: int, n0: int, nimg: int, name: str, input_target):

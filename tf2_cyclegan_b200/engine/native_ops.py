@@ -105,19 +105,19 @@ def add_conv(plan, name: str, a_maps: Sequence[bytes], taps: Sequence[Tap], k_ch
       ts = [1, 0, box_w * box_h * 128, box_w, min(dws), min(dhs), box_w * 128 if bw == 8 else 1024]
       if bw != 8 and bh != 1:
         ts_map, ts = b"", []   # 8-row groups must be equally spaced: bw == 8 (pitch) or a single row
+  # partial last tile row (bh does not divide out_h): loads are zero-filled, stores masked by h_limit
   return plan.add_conv_gemm(name, list(a_maps), nv.wmat_tmap(w2_bf16, block_n, b_mn),
-                            list(taps), k_channels // kblock, out_w // bw, out_h // bh, bw, bh,
+                            list(taps), k_channels // kblock, out_w // bw, -(-out_h // bh), bw, bh,
                             out_w if w_limit is None else w_limit, ptr, sn, sh, sw, n_channels,
-                            bias, act, stats, block_n, b_mn, nimg, ph, out_scale, fp8, ts_map, ts)
+                            bias, act, stats, block_n, b_mn, nimg, ph, out_scale, fp8, ts_map, ts, out_h)
 
 
 TS_STAGE_BYTES = 34 * 1024   # csrc/conv_gemm_ts.cu: TsCfg::kAStageBytes
 
 
 def tap_share_ok(block_n: int, fp8: bool, phases, a_maps) -> bool:
-  import os
-  return (block_n == 256 and not fp8 and phases is None and len(a_maps) == 1
-          and os.environ.get("B2_TAPSHARE", "1") != "0")
+  from ..config import ENGINE
+  return block_n == 256 and not fp8 and phases is None and len(a_maps) == 1 and ENGINE.tap_share
 
 
 def add_conv_flat(plan, name: str, a_map: bytes, taps: Sequence[Tap], k_channels: int,
@@ -142,7 +142,7 @@ def add_conv_flat(plan, name: str, a_map: bytes, taps: Sequence[Tap], k_channels
   return plan.add_conv_gemm(name, [a_map], nv.wmat_tmap(w2_bf16, block_n, b_mn), list(taps),
                             k_channels // 64, tiles, 1, 128, 1, rows, out_ptr, 0, 0,
                             out_row_stride, n_channels, 0, 0, 0, block_n, b_mn, 1, [], 0, False,
-                            ts_map, ts)
+                            ts_map, ts, 1)
 
 
 def pick_ksplit(base_ctas: int, total_kt: int, slots: int = 148, epilogue_kt: int = 12) -> int:
@@ -164,8 +164,8 @@ def pick_ksplit(base_ctas: int, total_kt: int, slots: int = 148, epilogue_kt: in
 def add_wgrad(plan, name: str, dy_map, a_maps: Sequence[bytes], taps: Sequence[Tap],
               kt_w: int, kt_h: int, kbw: int, kbh: int, nimg: int, cin: int, cout: int,
               dw_ptr: int, ldw: int, block_n: Optional[int] = None, target_ctas: Optional[int] = None):
-  import os
-  target_ctas = target_ctas or int(os.environ.get("B2_WGRAD_CTAS", "0"))   # 0: wave-aware choice
+  from ..config import ENGINE
+  target_ctas = target_ctas or ENGINE.wgrad_ctas   # 0: wave-aware choice
   block_n = block_n or max(64, nv.pick_block_n(cin))
   m_tiles = (cout + 127) // 128
   n_tiles = (cin + block_n - 1) // block_n
@@ -179,7 +179,7 @@ def add_wgrad(plan, name: str, dy_map, a_maps: Sequence[bytes], taps: Sequence[T
 
   ksplit = split(base)
   multi = (cin == 64 and 2 <= len(taps) <= 7 and not isinstance(dy_map, (list, tuple))
-           and os.environ.get("B2_WGRAD_MULTI", "1") != "0")
+           and ENGINE.wgrad_multi)
   if multi:   # narrow layers: one CTA accumulates all taps (dY tile loaded once per K tile)
     ksplit = -split(m_tiles)
   # dy_map: one view, or a list of views selected per tap through tap[1] (phase-merged wgrad)

@@ -50,6 +50,8 @@ def load():
   spec = importlib.util.spec_from_file_location("tf2_cyclegan_b200.csrc._C", path)
   mod = importlib.util.module_from_spec(spec)
   spec.loader.exec_module(mod)
+  from ..config import ENGINE
+  ENGINE.apply_to_extension(mod)
   _mod = mod
   return mod
 
@@ -151,12 +153,14 @@ class Buf8(Buf):
 
 
 def tile_shape(h: int, w: int, pixels: int = 128) -> Tuple[int, int]:
-  """(bw, bh) with bw*bh == pixels, bw | w, bh | h."""
-  bw = min(w, pixels)
-  while bw > 1 and (w % bw or pixels % bw):
-    bw -= 1
+  """(bw, bh) with bw * bh == pixels and bw | w: bw is the largest power of two that divides w (capped
+  at ``pixels``). bh need NOT divide h: the last tile row of an image is partial — TMA zero-fills the
+  rows past the image on load and the epilogue masks them on store (``h_limit``)."""
+  bw = 1
+  while bw * 2 <= pixels and w % (bw * 2) == 0:
+    bw *= 2
   bh = pixels // bw
-  if h % bh or w % bw or bw * bh != pixels or bw > 256 or bh > 256:
+  if w % bw or bw * bh != pixels or bw > 256 or bh > 256:
     raise ValueError(f"cannot tile {h}x{w} into {pixels}-pixel boxes")
   return bw, bh
 

@@ -13,7 +13,6 @@ launches issued per step by the reference's ``optimizer.minimize`` calls
 """
 from __future__ import annotations
 
-import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -23,10 +22,13 @@ from .strategy import Strategy
 
 MAX_BLOCKS = 148        # signal-pad sizing: one flag set per block and phase
 NUM_SCALARS = 16        # loss / metric slots reduced through the side channel
+from ..config import ENGINE
+
 # Form of the two-shot part: "push" (posted peer stores into the owner's staging slots, then local
 # reduction: bandwidth bound with a few CTAs) or "pull" (owner loads the peers' shards / NVLS
-# multimem.ld_reduce: needs megabytes of loads in flight). See csrc/allreduce_adam.cuh.
-DEFAULT_MODE = "push"
+# multimem.ld_reduce: needs megabytes of loads in flight). See csrc/allreduce_adam.cuh; chosen by
+# config.ENGINE.ar_mode.
+DEFAULT_MODE = ENGINE.ar_mode
 
 
 def default_blocks(nbytes: int, exposed: bool, world: int = 2, mode: Optional[str] = None) -> int:
@@ -60,7 +62,7 @@ class SymmetricBuffers:
     self.handles: Dict[str, Tuple[object, object]] = {}
     self.buckets: Dict[str, List[Tuple[int, int]]] = {}
     self.vec_lo: Dict[str, int] = {}
-    self.use_multicast = os.environ.get("B2_NVLS", "auto")
+    self.use_multicast = ENGINE.nvls
     # loss-scalar side channel: every rank's slots are peer-readable; the sums land in `scalars_sum`
     self.scalars = symm_mem.empty(NUM_SCALARS, dtype=torch.float32, device=strategy.device)
     self.scalars.zero_()

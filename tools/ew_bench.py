@@ -39,6 +39,7 @@ p = C.Plan(); p.add_in_bwd_reduce("r", g1.view(), 1, nv.NULL_VIEW, x.view(), sta
 p = C.Plan(); p.add_in_bwd_reduce("r2", g1.view(), 1, g2.view(), x.view(), stats.data_ptr(), gam.data_ptr(), bet.data_ptr(), inv, 1e-3, 0, dy.view(), bst.data_ptr(), n, h, h, c); plans["in_bwd_reduce(+g2)"] = (p, 4 * E)
 p = C.Plan(); p.add_in_bwd_apply("ap", dy.view(), x.view(), stats.data_ptr(), bst.data_ptr(), gam.data_ptr(), inv, 1e-3, dx.view(), dg.data_ptr(), db.data_ptr(), n, h, h, c); plans["in_bwd_apply"] = (p, 3 * E)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+flush2 = torch.zeros(512 << 20, dtype=torch.uint8, device="cuda")   # read after the write: leaves CLEAN lines in L2
 s = torch.cuda.current_stream().cuda_stream
 print(f"l2_flush={not a.no_flush} kernels={'direct' if a.direct else 'stream'}")
 for name, (plan, nbytes) in plans.items():
@@ -46,7 +47,7 @@ for name, (plan, nbytes) in plans.items():
   ts = []
   for _ in range(a.iters):
     if not a.no_flush:
-      flush.zero_()
+      flush.zero_(); flush2.sum()   # dirty then clean: the timed kernel does not pay the write-back
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); plan.run(0, -1, s, False); e1.record(); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))

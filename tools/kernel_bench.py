@@ -42,6 +42,7 @@ dy.interior().copy_(torch.randn(n, h, h, c, device="cuda").to(torch.bfloat16))
 dxp = nv.Buf(n, h, h, c, halo=1)
 dw = torch.zeros(c, 9 * c, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+flush2 = torch.zeros(512 << 20, dtype=torch.uint8, device="cuda")   # read after the write: leaves CLEAN lines in L2
 
 plans = {}
 ts = os.environ.get("B2_TAPSHARE", "1") != "0"   # tap-shared halo tiles (csrc/conv_gemm_ts.cu)
@@ -76,7 +77,7 @@ for name, (plan, flops) in plans.items():
   ts = []
   for _ in range(a.iters):
     if not a.no_flush:
-      flush.zero_()
+      flush.zero_(); flush2.sum()   # dirty then clean: the timed kernel does not pay the write-back
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     plan.run(0, -1, s, False)

@@ -8,7 +8,7 @@ set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 TOOLS=${*:-memcheck synccheck racecheck}
-export B2_NO_GRAPH=1
+export B2_CONFIG=use_graph=0
 for tool in $TOOLS; do
   log=gpurun_out/sanitizer_${tool}.log
   if [ "$tool" = memcheck ]; then
