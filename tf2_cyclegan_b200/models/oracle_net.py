@@ -46,7 +46,24 @@ def init_params(spec: NetSpec,
   return params
 
 
-def _layer(l: ConvLayer, params: Params, x: torch.Tensor) -> torch.Tensor:
+class _Bf16Storage(torch.autograd.Function):
+  """A tensor that is STORED in bf16 by the native engine: its value is rounded on the way forward
+  and its gradient (also a stored bf16 tensor there) on the way back."""
+
+  @staticmethod
+  def forward(ctx, x):
+    return x.to(torch.bfloat16).to(x.dtype)
+
+  @staticmethod
+  def backward(ctx, g):
+    return g.to(torch.bfloat16).to(g.dtype)
+
+
+def bf16_storage(x: torch.Tensor) -> torch.Tensor:
+  return _Bf16Storage.apply(x)
+
+
+def _layer(l: ConvLayer, params: Params, x: torch.Tensor, rnd=None) -> torch.Tensor:
   p = f"layer_with_weights-{l.lw_index}"
   kernel = params[f"{p}/kernel"]
   bias = params.get(f"{p}/bias") if l.bias else None
@@ -58,6 +75,8 @@ def _layer(l: ConvLayer, params: Params, x: torch.Tensor) -> torch.Tensor:
   else:
     y = O.conv2d_transpose(x, kernel, l.stride, bias)
   if l.norm:
+    if rnd is not None:
+      y = rnd(y)     # the raw conv output is a stored tensor; the statistics are those of the stored values
     q = f"layer_with_weights-{l.lw_index + 1}"
     y = O.instance_norm(y, params[f"{q}/gamma"], params[f"{q}/beta"])
   if l.act == "relu":
@@ -66,16 +85,25 @@ def _layer(l: ConvLayer, params: Params, x: torch.Tensor) -> torch.Tensor:
     y = O.leaky_relu(y, 0.2)
   elif l.act == "tanh":
     y = torch.tanh(y)
+  if rnd is not None and l.res != "b":
+    y = rnd(y)
   return y
 
 
-def forward(spec: NetSpec, params: Params, x: torch.Tensor) -> torch.Tensor:
-  """NHWC in → NHWC out. ``training`` is irrelevant (no BN / dropout)."""
+def forward(spec: NetSpec, params: Params, x: torch.Tensor, rnd=None) -> torch.Tensor:
+  """NHWC in → NHWC out. ``training`` is irrelevant (no BN / dropout).
+
+  ``rnd``: optional rounding applied wherever the native engine STORES a tensor (raw conv outputs
+  of normalised layers, layer outputs, residual sums) — ``bf16_storage`` makes this fp32 oracle see
+  the same activations as the bf16 engine, so activation masks agree and what is left of a
+  gradient comparison is the backward pass itself."""
   skip = None
   for l in spec.layers:
     if l.res == "a":
       skip = x
-    x = _layer(l, params, x)
+    x = _layer(l, params, x, rnd)
     if l.res == "b":
       x = skip + x  # layers.add([inputs, outputs]); no activation after (model.py:73)
+      if rnd is not None:
+        x = rnd(x)
   return x
