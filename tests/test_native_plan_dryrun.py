@@ -190,3 +190,25 @@ def test_bucketed_allreduce_plan_order(monkeypatch):
           assert q < next(r for r in recs if rec_lane[r] == lanes[q]), (n, k, names[q])
     tail = pos[f"opt.{n}.step"]
     assert tail > pos[f"opt.{n}.AR.b{nb - 1}"] and lanes[tail] == COMM_LANE
+
+
+def test_plans_of_smaller_batches_share_the_arenas(monkeypatch):
+  """The partial last batch of an epoch (or the b = 1 plot pass) must not double the activation
+  memory: its plan uses the first images of the arenas allocated for the full batch."""
+  fake_native.install(monkeypatch)
+  monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+  from tf2_cyclegan_b200.engine.cyclegan import build_specs
+  from tf2_cyclegan_b200.engine.native_backend import NativeBackend
+  from tf2_cyclegan_b200.parallel.strategy import Strategy
+  be = NativeBackend(build_specs(A(1)), 4, Strategy(device="cpu"), seed=1, image_size=64, local_batch=4)
+  big, small = be.plan_for(4), be.plan_for(1)
+  n_pool = len(be.buffer_pool)
+  for n in "GFXY":
+    eb, es = big.ex[n], small.ex[n]
+    for bb, bs in list(zip(eb.inp, es.inp)) + [(a, b) for a, b in zip(eb.raw, es.raw) if a is not None] + \
+                  [(a, b) for a, b in zip(eb.dY, es.dY) if a is not None] + [(eb.gout_final, es.gout_final)]:
+      assert bs.storage.data_ptr() == bb.storage.data_ptr() and bs.n < bb.n and bs.sn == bb.sn
+  be.plan_for(2)
+  assert len(be.buffer_pool) == n_pool          # nothing new was allocated for b = 2
+  bigger = be.plan_for(6)                        # a LARGER batch gets fresh arenas; older plans keep theirs
+  assert bigger.ex["G"].inp[3].storage.data_ptr() != big.ex["G"].inp[3].storage.data_ptr()

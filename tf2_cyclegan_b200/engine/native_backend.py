@@ -52,10 +52,10 @@ class StepPlan:
     self.y_in = torch.zeros(b, IH, IW, 3, device=dev)
     self.slots = be.slots          # loss / metric accumulators (peer-readable on the fused path)
     self.ex: Dict[str, NetExec] = {
-        "G": NetExec(be.specs["G"], be.state["G"], 3 * b, S, dev, "G", fp8=be.fp8),
-        "F": NetExec(be.specs["F"], be.state["F"], 3 * b, S, dev, "F", fp8=be.fp8),
-        "X": NetExec(be.specs["X"], be.state["X"], 2 * b, S, dev, "X"),
-        "Y": NetExec(be.specs["Y"], be.state["Y"], 2 * b, S, dev, "Y"),
+        "G": NetExec(be.specs["G"], be.state["G"], 3 * b, S, dev, "G", fp8=be.fp8, pool=be.buffer_pool),
+        "F": NetExec(be.specs["F"], be.state["F"], 3 * b, S, dev, "F", fp8=be.fp8, pool=be.buffer_pool),
+        "X": NetExec(be.specs["X"], be.state["X"], 2 * b, S, dev, "X", pool=be.buffer_pool),
+        "Y": NetExec(be.specs["Y"], be.state["Y"], 2 * b, S, dev, "Y", pool=be.buffer_pool),
     }
     for e in self.ex.values():
       e.enable_backward()
@@ -287,6 +287,7 @@ class NativeBackend:
     # loss / metric slots: on the fused path they live in peer-readable memory and the last fused
     # launch of a step leaves their sums over ranks in symm.scalars_sum (no NCCL call, no host sync)
     self.slots = self.symm.scalars if self.fused else torch.zeros(NUM_SLOTS, device=self.device)
+    self.buffer_pool: dict = {}     # activation / gradient arenas shared by the plans of all batch sizes
     self._opt_only_plan = None
     self._scalar_plan = None
     self._plans: Dict[int, StepPlan] = {}

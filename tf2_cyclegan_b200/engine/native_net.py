@@ -136,7 +136,7 @@ class NetExec:
   """Buffers + op emission for ``nb`` images of one network at resolution ``size`` (int or (h, w))."""
 
   def __init__(self, spec: NetSpec, state: NetState, nb: int, size, device, tag: str,
-               fp8: bool = False):
+               fp8: bool = False, pool: Optional[dict] = None):
     self.spec, self.st, self.nb, self.size, self.tag = spec, state, nb, size, tag
     self.fp8 = fp8 and any(fp8_ok(l) for l in spec.layers)
     if self.fp8:
@@ -144,6 +144,11 @@ class NetExec:
     self.layers = list(spec.layers)
     L = len(self.layers)
     dev = device
+    # activation / gradient arenas are shared between the plans of different batch sizes: the
+    # partial last batch of an epoch (or a b = 1 plot pass) reuses the first images of the arenas
+    # of the full batch instead of doubling the memory (pool: role -> largest buffer so far)
+    self.pool = pool
+    self.device = dev
     # resolution of every layer input / output
     self.in_hw: List[Tuple[int, int]] = []
     h, w = (size, size) if isinstance(size, int) else size
@@ -161,16 +166,16 @@ class NetExec:
       hh, ww = self.in_hw[j]
       halo = l.k // 2 if l.pad == "reflect" else (1 if is_small_cin(l) and l.pad == "same" else 0)
       slack = 1 if is_small_cin(l) else 0
-      self.inp.append(Buf(nb, hh, ww, cpad(l.cin), halo=halo, device=dev, slack_rows=slack))
+      self.inp.append(self._buf(f"inp{j}", nb, hh, ww, cpad(l.cin), halo=halo, slack_rows=slack))
     ho, wo = self.out_hw[-1]
-    self.inp.append(Buf(nb, ho, wo, cpad(self.layers[-1].cout), device=dev))
+    self.inp.append(self._buf("out", nb, ho, wo, cpad(self.layers[-1].cout)))
     # E4M3 twins of the inputs of the FP8 layers (written by the producing IN-apply kernel)
     self.inp8: Dict[int, Buf8] = {}
     if self.fp8:
       for j, l in enumerate(self.layers):
         if fp8_ok(l):
           hh, ww = self.in_hw[j]
-          self.inp8[j] = Buf8(nb, hh, ww, l.cin, halo=l.k // 2, device=dev)
+          self.inp8[j] = self._buf(f"inp8_{j}", nb, hh, ww, l.cin, halo=l.k // 2, cls=Buf8)
     self.raw: List[Optional[Buf]] = []
     self.stats: List[Optional[torch.Tensor]] = []
     self.bstats: List[Optional[torch.Tensor]] = []
@@ -181,7 +186,7 @@ class NetExec:
     for j, l in enumerate(self.layers):
       ho, wo = self.out_hw[j]
       if l.norm:
-        self.raw.append(Buf(nb, ho, wo, l.cout, device=dev))
+        self.raw.append(self._buf(f"raw{j}", nb, ho, wo, l.cout))
         self.stats.append(self.stat_arena[off:off + stat_sizes[j]].view(nb, l.cout, 2))
         self.bstats.append(self.bstat_arena[off:off + stat_sizes[j]].view(nb, l.cout, 2))
         off += stat_sizes[j]
@@ -197,6 +202,17 @@ class NetExec:
     self.gout_final: Optional[Buf] = None          # grad wrt the network output (images / logits)
     self._bwd = False
     self._special_weights()
+
+  def _buf(self, role: str, n: int, h: int, w: int, c: int, halo: int = 0, slack_rows: int = 0, cls=Buf):
+    if self.pool is None:
+      return cls(n, h, w, c, halo=halo, device=self.device, slack_rows=slack_rows)
+    key = (self.tag, role, h, w, c, halo, slack_rows, cls.__name__)
+    big = self.pool.get(key)
+    if big is not None and big.n >= n:
+      return cls(n, h, w, c, halo=halo, device=self.device, slack_rows=slack_rows, storage=big.storage)
+    b = cls(n, h, w, c, halo=halo, device=self.device, slack_rows=slack_rows)
+    self.pool[key] = b
+    return b
 
   # --------------------------------------------------------------- weights
   def _special_weights(self):
@@ -239,14 +255,14 @@ class NetExec:
       c_out = 8 if l.cout < 8 else l.cout
       flat_dgrad = l.kind == "conv" and l.pad == "reflect" and not is_small_cin(l)
       halo = l.k // 2 if flat_dgrad else 0
-      self.dY[j] = Buf(nb, ho, wo, c_out, halo=halo, device=dev, slack_rows=1 if c_out == 8 else 0)
+      self.dY[j] = self._buf(f"dY{j}", nb, ho, wo, c_out, halo=halo, slack_rows=1 if c_out == 8 else 0)
       if l.norm:
-        self.dyt[j] = Buf(nb, ho, wo, l.cout, device=dev)
+        self.dyt[j] = self._buf(f"dyt{j}", nb, ho, wo, l.cout)
       if j > 0 or True:
         c_in = 8 if l.cin < 8 else l.cin
-        self.gin[j] = Buf(nb, hi, wi, c_in, halo=halo, device=dev) if not is_small_cin(l) else None
+        self.gin[j] = self._buf(f"gin{j}", nb, hi, wi, c_in, halo=halo) if not is_small_cin(l) else None
     ho, wo = self.out_hw[-1]
-    self.gout_final = Buf(nb, ho, wo, self.inp[-1].c, device=dev)
+    self.gout_final = self._buf("gout", nb, ho, wo, self.inp[-1].c)
     # scratch for the swapped wgrad of small-Cout reflect convs (generator final layer)
     self.wgrad_scratch: Dict[int, torch.Tensor] = {}
     for j, l in enumerate(self.layers):
@@ -306,8 +322,14 @@ class NetExec:
         # small-Cout reflect conv (generator output layer): one GEMM tap per kernel ROW over the flat
         # padded domain (A traffic / k), then a k-tap horizontal gather fused with bias + tanh
         if j not in self.q_buf:
-          self.q_buf[j] = torch.zeros((self.nb * src.hp * src.wp + 256) * 32, dtype=torch.bfloat16,
-                                      device=src.t.device)
+          need = (self.nb * src.hp * src.wp + 256) * 32
+          qkey = (self.tag, f"q{j}", src.hp, src.wp)
+          shared = self.pool.get(qkey) if self.pool is not None else None
+          if shared is None or shared.numel() < need:
+            shared = torch.zeros(need, dtype=torch.bfloat16, device=src.t.device)
+            if self.pool is not None:
+              self.pool[qkey] = shared
+          self.q_buf[j] = shared
         qb = self.q_buf[j]
         rows = nimg * src.hp * src.wp
         qptr = qb.data_ptr() + 2 * 32 * n0 * src.hp * src.wp

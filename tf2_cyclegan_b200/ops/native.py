@@ -77,11 +77,15 @@ class Buf:
   so zero rings needed by dgrad stay zero for the lifetime of the plan."""
 
   def __init__(self, n: int, h: int, w: int, c: int, halo: int = 0, device="cuda",
-               slack_rows: int = 0):
+               slack_rows: int = 0, storage: Optional[torch.Tensor] = None):
     self.n, self.h, self.w, self.c, self.halo = n, h, w, c, halo
     self.hp, self.wp = h + 2 * halo, w + 2 * halo
     numel = n * self.hp * self.wp * c + slack_rows * self.wp * c
-    self.storage = torch.zeros(numel, dtype=torch.bfloat16, device=device)
+    # ``storage``: the first images of a larger buffer of the same per-image geometry (plans for a
+    # smaller batch share the arena of the largest one; halos / zero rings are per image, and the
+    # slack row then overlaps the next image's — finite — data, which is all it needs to be)
+    assert storage is None or storage.numel() >= numel
+    self.storage = torch.zeros(numel, dtype=torch.bfloat16, device=device) if storage is None else storage
     self.t = self.storage[:n * self.hp * self.wp * c].view(n, self.hp, self.wp, c)
 
   # strides in elements
@@ -136,11 +140,13 @@ class Buf:
 class Buf8(Buf):
   """E4M3 (1 byte / element) twin of :class:`Buf`: same logical layout, TMA boxes of 128 channels."""
 
-  def __init__(self, n: int, h: int, w: int, c: int, halo: int = 0, device="cuda"):
+  def __init__(self, n: int, h: int, w: int, c: int, halo: int = 0, device="cuda", slack_rows: int = 0,
+               storage: Optional[torch.Tensor] = None):
     self.n, self.h, self.w, self.c, self.halo = n, h, w, c, halo
     self.hp, self.wp = h + 2 * halo, w + 2 * halo
-    self.storage = torch.zeros(n * self.hp * self.wp * c, dtype=torch.uint8, device=device)
-    self.t = self.storage.view(n, self.hp, self.wp, c)
+    numel = n * self.hp * self.wp * c
+    self.storage = torch.zeros(numel, dtype=torch.uint8, device=device) if storage is None else storage
+    self.t = self.storage[:numel].view(n, self.hp, self.wp, c)
 
   def ptr(self, n: int = 0, h: int = 0, w: int = 0, c: int = 0, padded: bool = False) -> int:
     off = 0 if padded else self.halo

@@ -10,6 +10,10 @@ out=gpurun_out/evidence_$tag
 mkdir -p $out
 python bench.py --steps 30 --warmup 5 2>/dev/null | tail -1 > $out/bench_native_n1.json; cut -c100-330 $out/bench_native_n1.json
 python bench.py --impl standin --steps 20 --warmup 5 2>/dev/null | tail -1 > $out/bench_standin_n1.json; cut -c100-330 $out/bench_standin_n1.json
+# BASELINE configs 3 / 4 on one GPU (batch 8 bf16 vs fp8; 512 x 512 batch 1)
+python bench.py --steps 20 --warmup 5 --batch_size 8 --no_e2e 2>/dev/null | tail -1 > $out/bench_b8_bf16.json; cut -c100-330 $out/bench_b8_bf16.json
+python bench.py --steps 20 --warmup 5 --batch_size 8 --dtype fp8 --no_e2e 2>/dev/null | tail -1 > $out/bench_b8_fp8.json; cut -c100-330 $out/bench_b8_fp8.json
+python bench.py --steps 20 --warmup 5 --batch_size 1 --image_size 512 --no_e2e 2>/dev/null | tail -1 > $out/bench_512_b1.json; cut -c100-330 $out/bench_512_b1.json
 python tools/kernel_bench.py --iters 20 > $out/kernel_bench.log 2>&1; tail -3 $out/kernel_bench.log
 python tools/ew_bench.py > $out/ew_bench_flush.log 2>&1; tail -5 $out/ew_bench_flush.log
 python tools/ew_bench.py --no_flush > $out/ew_bench_warm.log 2>&1; tail -5 $out/ew_bench_warm.log
@@ -30,4 +34,7 @@ timeout 150 ncu --set full --clock-control none --import-source on -k regex:wgra
 for k in in_apply_stream_kernel in_bwd_reduce_stream_kernel in_bwd_apply_stream_kernel; do
   timeout 150 ncu --set full --clock-control none --import-source on -k regex:$k -s 4 -c 1 -f -o $out/ncu_$k python tools/ew_bench.py --iters 2 > /dev/null 2>&1
 done
+# sanitizers: memcheck over the whole (eager) smoke step, racecheck + synccheck over the kernel tests
+SANITIZE_TIMEOUT=${SANITIZE_TIMEOUT:-300} bash tools/sanitize.sh memcheck racecheck synccheck 2>&1 | tail -4
+cp gpurun_out/sanitizer_*.log $out/ 2>/dev/null
 ls -la $out
