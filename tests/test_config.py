@@ -9,9 +9,9 @@ from tf2_cyclegan_b200.config import EngineConfig
 
 def test_defaults_and_string_updates():
   c = EngineConfig()
-  assert c.use_graph and c.lanes == 4 and c.ar_mode == "push" and c.kernel_debug == 0 and c.nvls == "auto"
-  c.update_from_string("use_graph=0, lanes=2,ar_mode=pull,wgrad_ctas=96,nvtx=true")
-  assert (c.use_graph, c.lanes, c.ar_mode, c.wgrad_ctas, c.nvtx) == (False, 2, "pull", 96, True)
+  assert c.use_graph and c.lanes == 4 and c.ar_mode == "pull" and c.kernel_debug == 0 and c.nvls == "auto"
+  c.update_from_string("use_graph=0, lanes=2,ar_mode=push,wgrad_ctas=96,nvtx=true")
+  assert (c.use_graph, c.lanes, c.ar_mode, c.wgrad_ctas, c.nvtx) == (False, 2, "push", 96, True)
   for bad in ("lanes=3", "ar_mode=ring", "nope=1", "use_graph=maybe", "lanes", "kernel_debug=9"):
     with pytest.raises(ValueError):
       EngineConfig().update_from_string(bad)

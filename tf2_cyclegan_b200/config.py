@@ -32,7 +32,8 @@ class EngineConfig:
   wgrad_ctas: int = 0          # split-K target of the wgrad launches (0: whole-wave heuristic)
   # ---- data parallelism
   nvls: str = "auto"           # "auto": use the NVSwitch multicast alias when the fabric offers it | "off"
-  ar_mode: str = "push"        # two-shot part of the fused gradient reduce: "push" | "pull" (csrc/allreduce_adam.cuh)
+  ar_mode: str = "pull"        # two-shot part of the fused gradient reduce: "pull" | "push" (csrc/allreduce_adam.cuh);
+                               # pull measured faster at 4 and 8 GPUs, in the step and stand-alone (profiles/README.md)
   # ---- debugging (timing experiments; results are INVALID for kernel_debug != 0)
   kernel_debug: int = 0        # conv kernels: 1 skip epilogue, 2 skip MMAs, 3 skip TMA loads, 4 skip global stores
   stages: int = 0              # 1-CTA conv kernel: cap on the smem ring depth (0: default)

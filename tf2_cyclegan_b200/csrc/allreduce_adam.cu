@@ -108,11 +108,11 @@ __device__ __forceinline__ uint4 adam8(const AllreduceAdamParams& p, long long i
   return pk;
 }
 
-// pull form: 256 threads x up to 128 registers (many peer loads in flight per thread).
-// push form: a CTA of the collective owns its SM anyway (the conv GEMMs use the whole register file, so
-// nothing co-resides with it), therefore it uses ALL of it: 1024 threads x 64 registers — four times
-// the loads in flight per occupied SM, so a launch needs a quarter of the SMs for the same rate.
-constexpr int kPullThreads = 256;
+// A CTA of the collective owns its SM anyway (the conv GEMMs use the whole register file, so nothing
+// co-resides with it), therefore it uses ALL of it — pull form: 512 threads x up to 128 registers (many
+// peer loads in flight per thread); push form: 1024 threads x 64 registers — and both forms are launched
+// as cluster pairs (one TPC per pair), so that g CTAs displace g / 2 of the GEMMs' CTA pairs, not g.
+constexpr int kPullThreads = 512;
 constexpr int kPushThreads = 1024;
 constexpr int kPushUnroll = 4;  // push phase: chunks per thread per iteration (local loads in flight)
 
@@ -121,11 +121,15 @@ __device__ __forceinline__ void st_peer_f4(float* p, const float4 v) {
                "f"(v.w) : "memory");
 }
 
-template <bool PUSH>
+// MC: the two-shot reduction goes through the NVSwitch multicast alias (pull form only). An in-switch
+// reduction over 8 sources has a long round trip (~20 us measured), so that path keeps 4 chunk pairs
+// = 8 multimem.ld_reduce.v4 per thread in flight; the P2P code (two peers x two chunks of loads) is
+// compiled out of it, which is what makes the registers available.
+template <bool PUSH, bool MC>
 __global__ void __launch_bounds__(PUSH ? kPushThreads : kPullThreads, 1)
 allreduce_adam_kernel(const AllreduceAdamParams p) {
   constexpr int kArThreads = PUSH ? kPushThreads : kPullThreads;
-  constexpr int kArUnroll = PUSH ? 1 : 2;   // 8-element chunks per thread per iteration in the reduce / Adam loop
+  constexpr int kArUnroll = PUSH ? 1 : (MC ? 4 : 2);   // 8-element chunks per thread per iteration
   const int t = *p.step + 1;
   const float lr_t = p.lr * sqrtf(1.f - powf(p.beta2, static_cast<float>(t))) /
                      (1.f - powf(p.beta1, static_cast<float>(t)));
@@ -218,7 +222,7 @@ allreduce_adam_kernel(const AllreduceAdamParams p) {
             acc4(g1[j], *reinterpret_cast<const float4*>(sq + idx[j] + 4));
           }
       }
-    } else if (p.mc_grad != nullptr) {
+    } else if constexpr (MC) {
 #pragma unroll
       for (int j = 0; j < kArUnroll; ++j)
         if (idx[j] >= 0) {
@@ -342,24 +346,21 @@ void launch_scatter_add(float* dst, const float* src, const int* idx, long long 
 }
 
 void launch_allreduce_adam(const AllreduceAdamParams& p, int num_blocks, cudaStream_t s) {
-  if (p.stage[0] == nullptr) {
-    allreduce_adam_kernel<false><<<num_blocks, kPullThreads, 0, s>>>(p);
-    return;
-  }
-  // push form: CTA pairs (cluster of 2) share a TPC, so g CTAs displace g / 2 of the GEMMs' CTA pairs
-  // instead of up to g
+  const bool push = p.stage[0] != nullptr;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(num_blocks);
-  cfg.blockDim = dim3(kPushThreads);
+  cfg.blockDim = dim3(push ? kPushThreads : kPullThreads);
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (num_blocks % 2 == 0) ? 2 : 1;
+  attr[0].val.clusterDim.x = (num_blocks % 2 == 0) ? 2 : 1;   // CTA pairs share a TPC
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, allreduce_adam_kernel<true>, p);
+  if (push) cudaLaunchKernelEx(&cfg, allreduce_adam_kernel<true, false>, p);
+  else if (p.mc_grad != nullptr) cudaLaunchKernelEx(&cfg, allreduce_adam_kernel<false, true>, p);
+  else cudaLaunchKernelEx(&cfg, allreduce_adam_kernel<false, false>, p);
 }
 
 void launch_gather_bf16(__nv_bfloat16* dst, const float* src, const int* idx, long long n,

@@ -32,19 +32,24 @@ DEFAULT_MODE = ENGINE.ar_mode
 
 
 def default_blocks(nbytes: int, exposed: bool, world: int = 2, mode: Optional[str] = None) -> int:
-  """CTAs of one fused reduce + Adam launch. Push form: 1024-thread CTAs in pairs (one TPC per pair),
-  ~128 KB of loads in flight each; launches that run under the backward pass use few (they displace
-  GEMM CTA pairs one for one), the last, exposed launch of a network more. Pull form: 256-thread
-  CTAs, one 8-element chunk pair per thread and iteration."""
+  """CTAs of one fused reduce + Adam launch (always an even number: they are launched as cluster pairs,
+  one TPC per pair). Launches that run under the backward pass use few — they displace GEMM CTA pairs one
+  for one; the last, exposed launch of a network has the machine to itself.
+  Pull form (512 threads, 64 KB of peer loads in flight per CTA): one CTA per 128 KB of the rank's shard,
+  2..12, exposed: per 32 KB up to 148 — an in-switch reduction over 8 sources has a ~20 us round trip.
+  Push form (1024 threads, 128 KB of local loads in flight): one CTA per 2 MB, 2..8, exposed per 512 KB
+  up to 32."""
   mode = mode or DEFAULT_MODE
   if mode == "push":
     want = max(2, min(8, -(-nbytes // (2 << 20))))
     if exposed:
       want = max(want, min(32, -(-nbytes // (512 << 10))))
-    return want + (want & 1)
-  shard = max(1, nbytes // max(1, world))
-  want = max(2, min(24, -(-shard // (64 * 1024))))
-  return min(MAX_BLOCKS, max(want, min(64, -(-shard // (32 * 1024))))) if exposed else want
+  else:
+    shard = max(1, nbytes // max(1, world))
+    want = max(2, min(12, -(-shard // (128 * 1024))))
+    if exposed:
+      want = min(MAX_BLOCKS, max(want, -(-shard // (32 * 1024))))
+  return want + (want & 1)
 
 
 class SymmetricBuffers:
