@@ -2,7 +2,6 @@
 import os
 
 import pytest
-import torch
 
 from tf2_cyclegan_b200.cli import parse_args
 from tf2_cyclegan_b200.runner import main

@@ -232,7 +232,6 @@ def test_multi_epoch_loss_curves_track_oracle(tmp_path):
             "--dtype", "bf16" if backend == "native" else "fp32"]
     finals[backend] = main(parse_args(argv))
     ea = ea_mod.EventAccumulator(str(out), size_guidance={"tensors": 0}); ea.Reload()
-    import numpy as np
     from tensorboard.util import tensor_util
     curves[backend] = {t: [float(tensor_util.make_ndarray(e.tensor_proto)) for e in ea.Tensors(t)]
                        for t in ("loss_G/total", "loss_F/total", "loss_G/cycle", "loss_X/loss", "loss_Y/loss")}

@@ -1,7 +1,6 @@
 """Op semantics vs closed forms / tiny golden values (SURVEY.md §4 'unit (CPU)')."""
 import math
 
-import pytest
 import torch
 
 from tf2_cyclegan_b200.ops import oracle as O

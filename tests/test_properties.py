@@ -1,7 +1,6 @@
 """Property-based (hypothesis) tests of the pure-logic pieces: container encodings, checksums,
 TF-SAME geometry, the shuffle-buffer order and the wave-aware split-K chooser."""
 import numpy as np
-import torch
 from hypothesis import given, settings, strategies as st
 
 from tf2_cyclegan_b200.data.pipeline import tf_shuffle_order

@@ -4,7 +4,6 @@ trips, corruption detection, and the CycleGAN facade saving / resuming in the re
 import os
 import struct
 
-import numpy as np
 import pytest
 import torch
 

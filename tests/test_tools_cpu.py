@@ -7,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_critical_path_tool_runs_on_a_profile():
-  prof = os.path.join(ROOT, "profiles", "r1_step_profile_v8.txt")
+  prof = os.path.join(ROOT, "profiles", "r2", "step_profile.txt")
   r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "critical_path.py"), prof],
                      capture_output=True, text=True, timeout=600, cwd=ROOT)
   assert r.returncode == 0, r.stderr[-800:]

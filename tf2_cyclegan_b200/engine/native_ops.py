@@ -13,7 +13,6 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from ..ops import native as nv
-from ..ops.native import ACT, NULL_VIEW, Buf
 
 Tap = Tuple[int, int, int, int, int]   # (a-map index, dn, dw, dh, B column)
 

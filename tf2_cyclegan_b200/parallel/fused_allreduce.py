@@ -172,9 +172,9 @@ class SymmetricBuffers:
     if self._dummy is None:
       self._dummy = self.alloc("__scalars__", 128)
     hg, hw = self.handles["__scalars__"]
-    z = self.scalars_sum
+    # no parameter region at all (n = v_n = 0): master / moment pointers are never dereferenced
     plan.add_allreduce_adam(name, [int(p) for p in hg.buffer_ptrs], [int(p) for p in hw.buffer_ptrs],
-                            [int(p) for p in hg.signal_pad_ptrs], z.data_ptr(), z.data_ptr(), z.data_ptr(),
+                            [int(p) for p in hg.signal_pad_ptrs], 0, 0, 0,
                             self._zero_step().data_ptr(), 0.0, 0.5, 0.9, 1e-7, 0, 0, 0, 0,
                             [int(p) for p in self.h_scalars.buffer_ptrs], self.scalars_sum.data_ptr(),
                             NUM_SCALARS, self.rank, self.world, 1, 0, 0)
