@@ -22,6 +22,8 @@ ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--only", default="")
 ap.add_argument("--no_flush", action="store_true")
 ap.add_argument("--no_stats", action="store_true")
+ap.add_argument("--layer", default="res", choices=["res", "stem"],
+                help="res: 3x3 256->256 @64x64 (default); stem: 7x7 3->64 @256x256 forward (narrow N = 64 kernel)")
 a = ap.parse_args()
 C = nv.load()
 n, h, c = a.images, 64, 256
@@ -45,7 +47,23 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 flush2 = torch.zeros(512 << 20, dtype=torch.uint8, device="cuda")   # read after the write: leaves CLEAN lines in L2
 
 plans = {}
-ts = os.environ.get("B2_TAPSHARE", "1") != "0"   # tap-shared halo tiles (csrc/conv_gemm_ts.cu)
+if a.layer == "stem":
+  # the generator stem: 8-channel pixels, one GEMM tap per kernel row over an overlapping 8-pixel window
+  hs = 256
+  xin = nv.Buf(n, hs, hs, 8, halo=3, slack_rows=1)
+  xin.t.copy_(torch.randn_like(xin.t.float()).to(torch.bfloat16))
+  w2s = (torch.randn(64, 448, device="cuda") * 0.05).to(torch.bfloat16)
+  bw, bh = nv.tile_shape(hs, hs)
+  amap = nv.tmap(xin.ptr(padded=True), [64, hs, xin.hp, n], [8, xin.sh, xin.sn], [64, bw, bh, 1])
+  outs = nv.Buf(n, hs, hs, 64)
+  stats_s = torch.zeros(n, 64, 2, device="cuda")
+  p = C.Plan()
+  no.add_conv(p, "stem", [amap], [(0, 0, 0, r, r * 64) for r in range(7)], 64, w2s, outs.view(), hs, hs, n, 64,
+              stats=0 if a.no_stats else stats_s.data_ptr())
+  plans["stem_fwd"] = (p, 2.0 * n * hs * hs * 49 * 3 * 64)
+  a.only = a.only or "stem_fwd"
+from tf2_cyclegan_b200.config import ENGINE
+ts = ENGINE.tap_share   # tap-shared halo tiles (csrc/conv_gemm_ts.cu)
 bw, bh = (8, 16) if ts else nv.tile_shape(h, h)
 p = C.Plan()
 no.add_conv(p, "fwd", [x.tmap_padded(bw, bh)], no.taps_conv(3, c), c, w2, out.view(), h, h, n, c,
