@@ -171,7 +171,7 @@ def main():
   ap.add_argument("--batch_size", type=int, default=4, help="per GPU (BASELINE config 2: 4)")
   ap.add_argument("--image_size", type=int, default=256)
   ap.add_argument("--num_residual_blocks", type=int, default=9)
-  ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32", "fp8"])
+  ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32", "fp8", "mxfp8"])
   ap.add_argument("--fused_allreduce", default="on", choices=["auto", "on", "off"],
                   help="gradient path on > 1 GPU: 'on' (default) = the fused peer-memory reduce + Adam kernel or "
                        "fail loudly; 'off' = packed NCCL all-reduce + Adam kernel (baseline path)")

@@ -63,6 +63,20 @@ class FakePlan:
     assert out % 16 == 0 or cout < 8
     return self._add("conv_gemm_ts" if ts else "conv_gemm", name, len(taps), cout, block_n, b_mn, num_images)
 
+  def add_conv_gemm_mx(self, name, a_map, sfa_map, b_map, sfb, taps, cin_blocks, tiles_w, tiles_h, bw, bh, w_limit,
+                       h_limit, out, sn, sh, sw, cout, bias, act, stats, num_images):
+    assert bw * bh == 128 and 1 <= len(taps) <= 52 and 1 <= cin_blocks <= 4 and cout % 128 == 0
+    assert decode(a_map)["box"] == [128, bw, bh, 1], (name, decode(a_map)["box"])
+    sd = decode(sfa_map)
+    assert sd["box"] == [16, bw, bh, 1] and sd["dims"][0] == 16, (name, sd)
+    assert sd["dims"][1:] == decode(a_map)["dims"][1:], "scale records must cover the same pixels"
+    bd = decode(b_map)
+    assert bd["box"] == [128, 128] and bd["dims"][1] >= cout
+    for t in taps:
+      assert t[0] == 0 and t[4] % (cin_blocks * 128) == 0 and t[4] + cin_blocks * 128 <= bd["dims"][0], (name, t)
+    assert sfb % 16 == 0 and out % 16 == 0 and tiles_w >= 1 and tiles_h >= 1 and num_images >= 1
+    return self._add("conv_gemm_mx", name, len(taps), cout, num_images)
+
   def add_wgrad(self, name, dy_maps, a_maps, taps, ktw, kth, kbw, kbh, nimg, cin, cout, dw, ldw, block_n, ksplit):
     assert kbw * kbh == 64 and ksplit != 0 and block_n in (64, 128, 256)
     if ksplit < 0:   # multi-tap kernel

@@ -403,6 +403,58 @@ def test_fp8_conv_and_in_apply_quantisation():
   assert rel_err(out.t, full) < 8e-2          # quantisation error of E4M3 operands
 
 
+def test_mxfp8_conv_and_quantisers():
+  """MXFP8 (E4M3 + E8M0 scale per 32 channels): the IN-apply twin writer and the weight quantiser must
+  match the PyTorch reference bit for bit, and the block-scaled conv (kind::mxf8f6f4.block_scale,
+  scales staged into TMEM) must equal an fp32 conv of the de-quantised operands."""
+  nv, no, O = _mods()
+  from tf2_cyclegan_b200.ops import mxfp8
+  C = nv.load()
+  torch.manual_seed(12)
+  n, h, c, cout = 2, 64, 256, 256
+  # block-dependent magnitudes so that neighbouring scales differ by many powers of two
+  mag = torch.exp2(torch.randint(-6, 7, (n, h, h, c // 32), device="cuda").float()).repeat_interleave(32, dim=-1)
+  x = bf(torch.randn(n, h, h, c, device="cuda") * mag)
+  kmag = torch.exp2(torch.randint(-4, 5, (3, 3, c // 32, cout), device="cuda").float()).repeat_interleave(32, dim=2)
+  kern = bf(torch.randn(3, 3, c, cout, device="cuda") * 0.05 * kmag)
+  xb = nv.Buf(n, h, h, c); xb.t.copy_(x.to(torch.bfloat16))
+  dst = nv.Buf(n, h, h, c, halo=1)
+  dst8 = nv.Buf8(n, h, h, c, halo=1)
+  sf8 = nv.Buf8(n, h, h, 16, halo=1)
+  w2 = no.pack_conv_weight(kern).to(torch.bfloat16).contiguous()       # [cout, 9 * c]
+  w8 = torch.zeros(cout, 9 * c, dtype=torch.uint8, device="cuda")
+  wsf = torch.zeros(cout * 9 * c // 32, dtype=torch.uint8, device="cuda")
+  out = nv.Buf(n, h, h, cout)
+  stats = torch.zeros(n, cout, 2, device="cuda")
+  plan = C.Plan()
+  plan.add_in_apply("q", xb.view(), 0, 0, 0, 1.0, 1e-3, 0, nv.NULL_VIEW, dst.view(), 1, n, h, h, c,
+                    dst8.view(), 0, 0, sf8.view())
+  plan.add_mx_weight_quant("wq", w2.data_ptr(), w8.data_ptr(), wsf.data_ptr(), cout, 9, c)
+  bw, bh = nv.tile_shape(h, h)
+  no.add_conv_mx(plan, "conv.mx", dst8.tmap_padded(bw, bh), sf8.tmap_padded(bw, bh, cbox=16, swizzle=0),
+                 no.taps_conv(3, c), c, w8, wsf, out.view(), h, h, n, cout, stats=stats.data_ptr())
+  run(plan)
+  # activations: bytes + scale records (reflect halo included), bit-exact
+  xp = O.reflect_pad(x, 1)
+  q_ref, sb_ref = mxfp8.quantize(xp)
+  assert torch.equal(dst8.t, q_ref)
+  assert torch.equal(sf8.t[..., :c // 32], sb_ref) and (sf8.t[..., c // 32:] == 0).all()
+  assert (dst.t.float() - xp).abs().max().item() == 0
+  # weights
+  wq_ref, wsb_ref = mxfp8.quantize(w2.float())
+  assert torch.equal(w8, wq_ref)
+  assert torch.equal(wsf, mxfp8.weight_scale_order(wsb_ref, 9, c))
+  # conv vs the fp32 conv of the de-quantised operands
+  xq = mxfp8.dequantize(q_ref, sb_ref)
+  wq = no.unpack_conv_weight(mxfp8.dequantize(wq_ref, wsb_ref), 3, c, cout)
+  ref = O.conv2d(xq, wq, 1, "valid")
+  assert rel_err(out.t, ref) < 1e-2 and rel_l2(out.t, ref) < 5e-3
+  s_ref = torch.stack([out.t.float().sum((1, 2)), (out.t.float() ** 2).sum((1, 2))], -1)
+  assert rel_err(stats, s_ref) < 2e-3
+  full = O.conv2d(xp, kern, 1, "valid")
+  assert rel_l2(out.t, full) < 6e-2            # quantisation error of E4M3 operands with block scales
+
+
 @pytest.mark.parametrize("n,h,c,cout", [(2, 64, 256, 256), (3, 32, 64, 256), (1, 16, 128, 512)])
 def test_conv3x3_tap_shared_boxed(n, h, c, cout):
   """conv_gemm_ts.cu: 8 x 16 pixel tiles, ONE 10 x 18 halo tile per channel block, the nine

@@ -86,6 +86,28 @@ def test_fp8_plan_builds(monkeypatch):
   assert any(n.startswith("G.res0a.wgrad") for n in sp.names)
 
 
+def test_mxfp8_plan_builds(monkeypatch):
+  """--dtype mxfp8: block-scaled convs + scale-record buffers + per-layer weight quantisation ops."""
+  fake_native.install(monkeypatch)
+  monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+  from tf2_cyclegan_b200.engine.cyclegan import build_specs
+  from tf2_cyclegan_b200.engine.native_backend import NativeBackend
+  from tf2_cyclegan_b200.parallel.strategy import Strategy
+  be = NativeBackend(build_specs(A(2)), 2, Strategy(device="cpu"), seed=1, image_size=128, local_batch=2,
+                     dtype="mxfp8")
+  sp = be.plan_for(2)
+  mx = [n for n in sp.names if n.endswith(".mxfp8")]
+  assert len(mx) == 16 and all(".res" in n for n in mx)
+  assert sum(n.endswith(".mx_w_quant") for n in sp.names) == 8      # 2 generators x 4 residual convs
+  assert not any(n.endswith(".scales") or n.endswith(".w_amax") for n in sp.names)   # no scaling state
+  ex = sp.ex["G"]
+  assert set(ex.sf8) == set(ex.inp8) and all(b.c == 16 and b.halo == 1 for b in ex.sf8.values())
+  st = be.state["G"]
+  assert [t.numel() for t in st.w_sf] == [256 * 9 * 256 // 32] * 4
+  assert be.extra_state() == {}
+  assert any(n.startswith("G.res0a.wgrad") for n in sp.names)
+
+
 def test_allreduce_buckets_and_ownership(monkeypatch):
   """Bucket plan of the fused all-reduce (CPU logic only): buckets tile the kernel part of the flat
   buffer in backward order, the vector tail is one-shot (replicated), and the per-bucket rank shards

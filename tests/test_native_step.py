@@ -294,6 +294,29 @@ def test_fp8_forward_tracks_bf16():
   assert s.act_scale.min().item() > 0 and (s.w8 != 0).any()
 
 
+def test_mxfp8_forward_tracks_bf16():
+  """--dtype mxfp8: residual-block forward convs in MXFP8 (block-scaled E4M3); losses stay close to bf16."""
+  from tf2_cyclegan_b200.engine.cyclegan import build_specs
+  from tf2_cyclegan_b200.engine.native_backend import NativeBackend
+  from tf2_cyclegan_b200.parallel.strategy import Strategy
+  st = Strategy(device="cuda")
+  specs = build_specs(A(2))
+  a = NativeBackend(specs, 2, st, seed=5, image_size=128, local_batch=2, dtype="bf16")
+  f = NativeBackend(specs, 2, st, seed=5, image_size=128, local_batch=2, dtype="mxfp8")
+  torch.manual_seed(0)
+  x = torch.rand(2, 128, 128, 3, device="cuda") * 2 - 1
+  y = torch.rand(2, 128, 128, 3, device="cuda") * 2 - 1
+  for _ in range(4):
+    ra = a.train_step(x, y)
+    rf = f.train_step(x, y)
+  for k in ra:
+    va, vf = ra[k].item(), rf[k].item()
+    assert vf == vf and abs(va - vf) < 8e-2 * max(abs(va), 0.05), (k, va, vf)
+  s = f.state["G"]
+  assert s.fp8_mode == "mx" and (s.w8 != 0).any() and all((t != 0).any() for t in s.w_sf)
+  assert any(n.endswith(".mxfp8") for n in f.plan_for(2).names)
+
+
 def test_training_reduces_cycle_loss_on_fixed_batch():
   """40 native steps on one fixed batch: cycle / identity L1 terms must go down, stay finite."""
   from tf2_cyclegan_b200.engine.cyclegan import build_specs

@@ -18,8 +18,9 @@ def build_parser() -> argparse.ArgumentParser:
   # --- extras
   parser.add_argument("--image_size", default=256, type=int)
   parser.add_argument("--num_residual_blocks", default=9, type=int)
-  parser.add_argument("--dtype", default="bf16", choices=["fp32", "bf16", "fp8"],
-                      help="compute dtype of the native backend (oracle: fp32/bf16)")
+  parser.add_argument("--dtype", default="bf16", choices=["fp32", "bf16", "fp8", "mxfp8"],
+                      help="compute dtype of the native backend (oracle: fp32/bf16); fp8 / mxfp8: residual-block "
+                           "forward convs in E4M3 with per-tensor / per-32-channel (MX) scales")
   parser.add_argument("--backend", default="auto", choices=["auto", "native", "oracle"])
   parser.add_argument("--device", default=None, choices=["cpu", "cuda"])
   parser.add_argument("--data_dir", default=None,
@@ -45,8 +46,8 @@ def parse_args(argv=None):
   if args.synthetic:
     args.data_dir = None
   if args.device == "cpu" or args.backend == "oracle":
-    if args.dtype == "fp8":
-      raise SystemExit("--dtype fp8 needs the native backend")
+    if args.dtype in ("fp8", "mxfp8"):
+      raise SystemExit(f"--dtype {args.dtype} needs the native backend")
   return args
 
 

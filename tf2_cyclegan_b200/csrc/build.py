@@ -9,7 +9,7 @@ import sysconfig
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["conv_gemm.cu", "conv_gemm2.cu", "conv_gemm_ts.cu", "wgrad_gemm.cu", "wgrad_multi.cu", "elementwise.cu", "allreduce_adam.cu", "plan.cu"]
+SOURCES = ["conv_gemm.cu", "conv_gemm2.cu", "conv_gemm_ts.cu", "conv_gemm_mx.cu", "wgrad_gemm.cu", "wgrad_multi.cu", "elementwise.cu", "allreduce_adam.cu", "plan.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

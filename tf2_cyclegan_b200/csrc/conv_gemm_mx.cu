@@ -1,0 +1,333 @@
+// MXFP8 implicit-GEMM convolution for sm_100a: tcgen05.mma.kind::mxf8f6f4.block_scale with E4M3
+// activations and weights and one E8M0 scale per 32 K elements of either operand (the OCP MX
+// format; BASELINE config 3). Same tap-walking TMA scheme as conv_gemm.cu, M = 128 pixels x
+// N = 128 channels per tile, K block = 128 channels (128 bytes), four K = 32 MMAs per block.
+//
+// Scale factors live in TMEM next to the accumulators, in the layout the instruction reads
+// (taken from the CUTLASS headers vendored in this image, cute/atom/mma_traits_sm100.hpp
+// `tmem_sf_frg`): for operand row r = r0 + 32 r1 the four scales of a 128-byte K block are the
+// four bytes of TMEM column r1, lane r0, replicated in each of the four 32-lane sub-partitions;
+// the MMA for K slice k selects byte k through the scale-factor id fields of the instruction
+// descriptor. Activation scales come from a pixel-major record buffer (16 bytes per pixel, written
+// by the InstanceNorm-apply kernel) that the producer loads with the same shifted TMA box as the
+// activations; a scale warpgroup transposes them into TMEM with tcgen05.st (TMA cannot deliver
+// the interleaved order from a pixel-major tensor). Weight scales are pre-arranged per
+// (tile, tap, K block) and fetched with one 512-byte bulk copy.
+//
+// Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+// warps 4-7 epilogue, warps 8-11 scale factors. TMEM: columns [0, 256) two accumulators,
+// [256, 256 + 8 * stages) scale factors (4 columns SFA + 4 columns SFB per stage).
+#include <cuda_fp8.h>
+#include <stdlib.h>
+
+#include "conv_epilogue.cuh"
+#include "mx.cuh"
+
+namespace b2 {
+
+int dbg_flag();
+
+namespace {
+
+constexpr int kN = 128;
+struct MxCfg {
+  static constexpr int kABytes = 128 * 128;
+  static constexpr int kBBytes = kN * 128;
+  static constexpr int kSfaBytes = 128 * kMxSfRecord;
+  static constexpr int kSfbBytes = kN * 4;
+  static constexpr int kTxBytes = kABytes + kBBytes + kSfaBytes + kSfbBytes;
+  static constexpr int kStageBytes = (kTxBytes + 1023) / 1024 * 1024;   // A / B tiles need 1024-byte alignment
+  static constexpr int kStages = 5;
+  static constexpr int kAccCols = kN;
+  static constexpr int kSfCol0 = 2 * kAccCols;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kStagingBytes = EpiCfg<kN>::kStagingBytes;
+  static constexpr int kRedBytes = EpiCfg<kN>::kRedBytes;
+  static constexpr int kBarrierBytes = (3 * kStages + 4) * 8 + 16;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kRedBytes + kBarrierBytes + 1024;
+  static_assert(kSfCol0 + 8 * kStages <= kTmemCols, "TMEM budget");
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
+};
+
+// kind::mxf8f6f4 instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptorBlockScaled):
+// [4,6) B scale id, [7,10) A format (0 = E4M3), [10,13) B format, 15 / 16 A / B major (0 = K),
+// [17,23) N / 8, 23 scale format (1 = E8M0), [24,29) M / 16, [29,31) A scale id.
+__host__ __device__ constexpr uint32_t make_idesc_mxf8(int M, int N) {
+  return (uint32_t(N >> 3) << 17) | (1u << 23) | (uint32_t(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_mxf8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t tmem_sfa, uint32_t tmem_sfb, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+      : "memory");
+}
+
+// thread = TMEM lane; writes 4 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st_32x4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b),
+               "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__global__ void __launch_bounds__(384, 1)
+conv_gemm_mx_kernel(const __grid_constant__ ConvGemmMxParams q, int num_images, int dbg) {
+  using Cfg = MxCfg;
+  const ConvGemmParams& p = q.g;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* stage_buf = smem + Cfg::kStages * Cfg::kStageBytes;
+  float* red = reinterpret_cast<float*>(stage_buf + Cfg::kStagingBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_buf + Cfg::kStagingBytes + Cfg::kRedBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* sf_bar = empty_bar + Cfg::kStages;           // scale factors of the stage are in TMEM
+  uint64_t* tmem_full_bar = sf_bar + Cfg::kStages;       // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;          // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const int m_tiles = tiles_per_img * num_images;
+  const int n_tiles = (p.cout + kN - 1) / kN;
+  const int total_tiles = m_tiles * n_tiles;
+  const int kb_per_tile = p.num_taps * p.cin_blocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmA[0]);
+    tma_prefetch_desc(&q.tmSFA);
+  } else if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+      mbar_init(&sf_bar[s], 128);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 128);
+    }
+    fence_barrier_init();
+  } else if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, Cfg::kTmemCols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ============================ TMA producer ============================
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int mt = tile / n_tiles;
+      const int nt = tile - mt * n_tiles;
+      const int img = mt / tiles_per_img;
+      const int t_in = mt - img * tiles_per_img;
+      const int th = t_in / p.tiles_w;
+      const int w0 = (t_in - th * p.tiles_w) * p.bw;
+      const int h0 = th * p.bh;
+      const uint8_t* sfb_tile = q.sfb + static_cast<long long>(nt) * kb_per_tile * Cfg::kSfbBytes;
+      for (int t = 0; t < p.num_taps; ++t) {
+        const Tap tap = p.taps[t];
+        for (int cb = 0; cb < p.cin_blocks; ++cb, ++it) {
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* sa = smem + s * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          uint8_t* sfa = sb + Cfg::kBBytes;
+          uint8_t* sfb = sfa + Cfg::kSfaBytes;
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_bar[s], Cfg::kTxBytes);
+            tma_load_4d(sa, &p.tmA[0], &full_bar[s], cb * 128, w0 + tap.dw, h0 + tap.dh, img + tap.dn);
+            tma_load_2d(sb, &p.tmB, &full_bar[s], tap.bk + cb * 128, nt * kN);
+            tma_load_4d(sfa, &q.tmSFA, &full_bar[s], 0, w0 + tap.dw, h0 + tap.dh, img + tap.dn);
+            const int tk = tap.bk / (p.cin_blocks * 128);   // position of the tap in the weight matrix
+            bulk_load(sfb, sfb_tile + static_cast<long long>(tk * p.cin_blocks + cb) * Cfg::kSfbBytes,
+                      Cfg::kSfbBytes, &full_bar[s]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================= MMA issuer =============================
+    constexpr uint32_t idesc = make_idesc_mxf8(128, kN);
+    const uint32_t smem_base = smem_u32(smem);
+    uint32_t it = 0, tile_i = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
+      const uint32_t acc = tile_i & 1;
+      const uint32_t acc_ph = (tile_i >> 1) & 1;
+      mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * Cfg::kAccCols;
+      for (int kb = 0; kb < kb_per_tile; ++kb, ++it) {
+        const int s = it % Cfg::kStages;
+        const uint32_t ph = (it / Cfg::kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        mbar_wait(&sf_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * Cfg::kStageBytes;
+        const uint64_t da = make_desc_kmajor(sa);
+        const uint64_t db = make_desc_kmajor(sa + Cfg::kABytes);
+        const uint32_t tsfa = tmem_base + Cfg::kSfCol0 + 8 * s;
+        const uint32_t tsfb = tsfa + 4;
+        if (elect_one()) {
+          if (dbg != 2) {
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k) {
+              // K slice k: +32 bytes inside the swizzle row; scale byte k of the stage's columns
+              // (id fields of the descriptor and the two top bits of the scale address)
+              umma_mxf8(tmem_d, da + k * 2, db + k * 2, idesc | (k << 29) | (k << 4), tsfa | (k << 30),
+                        tsfb | (k << 30), (kb | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&tmem_full_bar[acc]);
+      __syncwarp();
+    }
+  } else if (warp >= 8) {
+    // =========================== scale factors ============================
+    // thread (sub-partition sp, lane) writes TMEM lane 32 sp + lane: SFA column j = the 4 scale
+    // bytes of tile pixel lane + 32 j, SFB column j = those of output channel lane + 32 j
+    const int sp = warp - 8;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(sp * 32) << 16) + Cfg::kSfCol0;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int t = 0; t < p.num_taps; ++t) {
+        for (int cb = 0; cb < p.cin_blocks; ++cb, ++it) {
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          const uint8_t* sfa = smem + s * Cfg::kStageBytes + Cfg::kABytes + Cfg::kBBytes;
+          const uint8_t* sfb = sfa + Cfg::kSfaBytes;
+          uint32_t a[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            a[j] = *reinterpret_cast<const uint32_t*>(sfa + (lane + 32 * j) * kMxSfRecord + (cb & 3) * 4);
+          const uint4 b = *reinterpret_cast<const uint4*>(sfb + lane * 16);
+          tmem_st_32x4(lane_base + 8 * s, a[0], a[1], a[2], a[3]);
+          tmem_st_32x4(lane_base + 8 * s + 4, b.x, b.y, b.z, b.w);
+          tmem_st_wait();
+          tc_fence_before();
+          mbar_arrive(&sf_bar[s]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================== epilogue ==============================
+    const int e = threadIdx.x - 128;
+    const int ew = warp - 4;
+    uint32_t tile_i = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
+      const int mt = tile / n_tiles;
+      const int n0 = (tile - mt * n_tiles) * kN;
+      const int img = mt / tiles_per_img;
+      const int t_in = mt - img * tiles_per_img;
+      const int th = t_in / p.tiles_w;
+      const int w0 = (t_in - th * p.tiles_w) * p.bw;
+      const int h0 = th * p.bh;
+      const uint32_t acc = tile_i & 1;
+      const uint32_t acc_ph = (tile_i >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * Cfg::kAccCols + (static_cast<uint32_t>(ew * 32) << 16);
+      if (dbg == 1) { tc_fence_before(); mbar_arrive(&tmem_empty_bar[acc]); continue; }
+      conv_epilogue_tile<kN>(p, p.out, stage_buf, red, taddr, img, h0, w0, n0, e, ew, lane, true,
+                             [&]() { mbar_arrive(&tmem_empty_bar[acc]); });
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// one thread per (output channel, 32-element K block)
+__global__ void __launch_bounds__(256) mx_weight_quant_kernel(const MxWeightQuantParams p) {
+  const int kblocks = p.taps * p.cin / kMxBlock;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.cout * kblocks) return;
+  const int n = idx / kblocks, kb = idx - n * kblocks;
+  const long long off = static_cast<long long>(n) * kblocks * kMxBlock + static_cast<long long>(kb) * kMxBlock;
+  const uint4* src = reinterpret_cast<const uint4*>(p.w + off);
+  float v[32];
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 u = __ldg(src + i);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(w[j]);
+      v[i * 8 + 2 * j] = f.x;
+      v[i * 8 + 2 * j + 1] = f.y;
+      amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
+    }
+  }
+  const uint32_t sb = mx_scale_byte(amax);
+  const float inv = mx_inv_scale(sb);
+  uint32_t o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(v[4 * j] * inv, v[4 * j + 1] * inv), __NV_SATFINITE, __NV_E4M3);
+    const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(v[4 * j + 2] * inv, v[4 * j + 3] * inv), __NV_SATFINITE, __NV_E4M3);
+    o[j] = lo | (hi << 16);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(p.w8 + off);
+  dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+  dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  // scale position: [n / 128][tap][cin block of 128][n % 32][(n % 128) / 32][K slice]
+  const int per_tap = p.cin / kMxBlock;
+  const int tap = kb / per_tap, r = kb - tap * per_tap;
+  const int cin_blocks = p.cin / 128;
+  const long long chunk = (static_cast<long long>(n / 128) * p.taps + tap) * cin_blocks + (r >> 2);
+  p.sfb[chunk * 512 + (n & 31) * 16 + ((n & 127) >> 5) * 4 + (r & 3)] = static_cast<uint8_t>(sb);
+}
+
+}  // namespace
+
+void launch_conv_gemm_mx(const ConvGemmMxParams& p, int num_images, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(conv_gemm_mx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MxCfg::kSmemBytes);
+    configured = true;
+  }
+  if (p.g.num_phases != 1 || p.g.cout % kN != 0 || p.g.cin_blocks < 1 || p.g.cin_blocks > 4) {
+    fprintf(stderr, "launch_conv_gemm_mx: needs one phase, cout %% 128 == 0, cin in {128, ..., 512}\n");
+    abort();
+  }
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int total = p.g.tiles_w * p.g.tiles_h * num_images * (p.g.cout / kN);
+  const int grid = total < sms ? total : sms;
+  conv_gemm_mx_kernel<<<grid, 384, MxCfg::kSmemBytes, stream>>>(p, num_images, dbg_flag());
+}
+
+void launch_mx_weight_quant(const MxWeightQuantParams& p, cudaStream_t stream) {
+  if (p.cin % 128 != 0 || p.cout % 128 != 0) {
+    fprintf(stderr, "launch_mx_weight_quant: cin and cout must be multiples of 128\n");
+    abort();
+  }
+  const int total = p.cout * (p.taps * p.cin / kMxBlock);
+  mx_weight_quant_kernel<<<(total + 255) / 256, 256, 0, stream>>>(p);
+}
+
+}  // namespace b2

@@ -4,6 +4,7 @@
 #include <cuda_fp8.h>
 
 #include "elementwise.cuh"
+#include "mx.cuh"
 
 namespace b2 {
 
@@ -150,8 +151,10 @@ __device__ __forceinline__ float actk(float v, float slope) {
 
 // ------------------------------------------------------------------ in_apply
 // dst = act(a * x + b) (+ skip), written into the (reflect-haloed) input buffer of the next conv
-template <int ACT, bool SKIP, bool HALO, bool HAS8>
-__global__ void __launch_bounds__(kThreads, (SKIP || HAS8) ? 3 : 4) in_apply_kernel(const InApplyParams p, int pix_per_block,
+// F8: 0 = no 8-bit twin, 1 = E4M3 with one delayed scale per tensor, 2 = MXFP8 (E4M3 + one E8M0 scale per
+// 32 channels, C == 256: one warp per pixel)
+template <int ACT, bool SKIP, bool HALO, int F8>
+__global__ void __launch_bounds__(kThreads, (SKIP || F8 != 0) ? 3 : 4) in_apply_kernel(const InApplyParams p, int pix_per_block,
                                                               uint32_t rcp_w) {
   constexpr int U = 4;
   const int c8 = p.C >> 3;
@@ -178,14 +181,21 @@ __global__ void __launch_bounds__(kThreads, (SKIP || HAS8) ? 3 : 4) in_apply_ker
     for (int j = 0; j < 8; ++j) { ka[j] = 1.f; kb[j] = 0.f; }
   }
   const V32 X = v32(p.x, n, c), S = v32(p.skip, n, c), D = v32(p.dst, n, c);
+  constexpr bool HAS8 = F8 != 0;
   uint8_t* d8 = nullptr;
-  int d8sh = 0, d8sw = 0;
+  uint8_t* sf = nullptr;
+  int d8sh = 0, d8sw = 0, sfsh = 0, sfsw = 0;
   float s8 = 1.f, amax = 0.f;
   if constexpr (HAS8) {
     d8 = reinterpret_cast<uint8_t*>(p.dst8.p) + static_cast<long long>(n) * p.dst8.sn + c;
     d8sh = static_cast<int>(p.dst8.sh);
     d8sw = static_cast<int>(p.dst8.sw);
-    s8 = __ldg(p.scale8);
+    if constexpr (F8 == 1) s8 = __ldg(p.scale8);
+    if constexpr (F8 == 2) {
+      sf = reinterpret_cast<uint8_t*>(p.sf8.p) + static_cast<long long>(n) * p.sf8.sn;
+      sfsh = static_cast<int>(p.sf8.sh);
+      sfsw = static_cast<int>(p.sf8.sw);
+    }
   }
   const float slope = act_slope(p.act);
   const int H = p.H, W = p.W, halo = p.halo;
@@ -219,16 +229,35 @@ __global__ void __launch_bounds__(kThreads, (SKIP || HAS8) ? 3 : 4) in_apply_ker
       const int h = hh[u], w = ww[u];
       stv(D, h, w, pk);
       uint2 pk8 = make_uint2(0u, 0u);
+      uint2 sfrec = make_uint2(0u, 0u);   // MX: the pixel's 8 scale bytes (lane 0)
       if constexpr (HAS8) {
         uint16_t o8[4];
+        if constexpr (F8 == 2) {
+          // the 32-channel block = 4 adjacent lanes; the whole warp works on this pixel
+          float bmax = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bmax = fmaxf(bmax, fabsf(v[j]));
+          bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, 1));
+          bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, 2));
+          const uint32_t sb = mx_scale_byte(bmax);
+          s8 = mx_inv_scale(sb);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            sfrec.x |= __shfl_sync(0xffffffffu, sb, 4 * j) << (8 * j);
+            sfrec.y |= __shfl_sync(0xffffffffu, sb, 16 + 4 * j) << (8 * j);
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          amax = fmaxf(amax, fmaxf(fabsf(v[2 * j]), fabsf(v[2 * j + 1])));
+          if constexpr (F8 == 1) amax = fmaxf(amax, fmaxf(fabsf(v[2 * j]), fabsf(v[2 * j + 1])));
           o8[j] = __nv_cvt_float2_to_fp8x2(make_float2(v[2 * j] * s8, v[2 * j + 1] * s8), __NV_SATFINITE, __NV_E4M3);
         }
         pk8 = make_uint2(static_cast<uint32_t>(o8[0]) | (static_cast<uint32_t>(o8[1]) << 16),
                          static_cast<uint32_t>(o8[2]) | (static_cast<uint32_t>(o8[3]) << 16));
         *reinterpret_cast<uint2*>(d8 + (h * d8sh + w * d8sw)) = pk8;
+        if constexpr (F8 == 2) {
+          if ((threadIdx.x & 31) == 0) *reinterpret_cast<uint2*>(sf + (h * sfsh + w * sfsw)) = sfrec;
+        }
       }
       if constexpr (HALO) {
         // mirror images of a border pixel: row hm and / or column wm (reflect: -i for 1 <= i <= halo,
@@ -238,19 +267,22 @@ __global__ void __launch_bounds__(kThreads, (SKIP || HAS8) ? 3 : 4) in_apply_ker
         if (hm != h) {
           stv(D, hm, w, pk);
           if constexpr (HAS8) *reinterpret_cast<uint2*>(d8 + (hm * d8sh + w * d8sw)) = pk8;
+          if constexpr (F8 == 2) { if ((threadIdx.x & 31) == 0) *reinterpret_cast<uint2*>(sf + (hm * sfsh + w * sfsw)) = sfrec; }
         }
         if (wm != w) {
           stv(D, h, wm, pk);
           if constexpr (HAS8) *reinterpret_cast<uint2*>(d8 + (h * d8sh + wm * d8sw)) = pk8;
+          if constexpr (F8 == 2) { if ((threadIdx.x & 31) == 0) *reinterpret_cast<uint2*>(sf + (h * sfsh + wm * sfsw)) = sfrec; }
           if (hm != h) {
             stv(D, hm, wm, pk);
             if constexpr (HAS8) *reinterpret_cast<uint2*>(d8 + (hm * d8sh + wm * d8sw)) = pk8;
+            if constexpr (F8 == 2) { if ((threadIdx.x & 31) == 0) *reinterpret_cast<uint2*>(sf + (hm * sfsh + wm * sfsw)) = sfrec; }
           }
         }
       }
     }
   }
-  if constexpr (HAS8) {   // delayed-scaling statistics: one atomic per warp (values are >= 0, so int order == float order)
+  if constexpr (F8 == 1) {   // delayed-scaling statistics: one atomic per warp (values are >= 0, so int order == float order)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(p.amax8), __float_as_int(amax));
@@ -1189,8 +1221,9 @@ static void launch_in_apply_stream_a(const InApplyParams& p, dim3 grid, int ppb,
 
 template <int ACT, bool SKIP, bool HALO>
 static void launch_in_apply_t(const InApplyParams& p, dim3 grid, int ppb, uint32_t rcp, cudaStream_t s) {
-  if (p.dst8.p != nullptr) in_apply_kernel<ACT, SKIP, HALO, true><<<grid, kThreads, 0, s>>>(p, ppb, rcp);
-  else in_apply_kernel<ACT, SKIP, HALO, false><<<grid, kThreads, 0, s>>>(p, ppb, rcp);
+  if (p.dst8.p != nullptr && p.sf8.p != nullptr) in_apply_kernel<ACT, SKIP, HALO, 2><<<grid, kThreads, 0, s>>>(p, ppb, rcp);
+  else if (p.dst8.p != nullptr) in_apply_kernel<ACT, SKIP, HALO, 1><<<grid, kThreads, 0, s>>>(p, ppb, rcp);
+  else in_apply_kernel<ACT, SKIP, HALO, 0><<<grid, kThreads, 0, s>>>(p, ppb, rcp);
 }
 template <int ACT>
 static void launch_in_apply_a(const InApplyParams& p, dim3 grid, int ppb, uint32_t rcp, cudaStream_t s) {
@@ -1199,6 +1232,10 @@ static void launch_in_apply_a(const InApplyParams& p, dim3 grid, int ppb, uint32
   else { if (halo) launch_in_apply_t<ACT, false, true>(p, grid, ppb, rcp, s); else launch_in_apply_t<ACT, false, false>(p, grid, ppb, rcp, s); }
 }
 void launch_in_apply(const InApplyParams& p, cudaStream_t s) {
+  if (p.sf8.p != nullptr && (p.dst8.p == nullptr || p.C != 256)) {
+    fprintf(stderr, "launch_in_apply: the MXFP8 twin needs dst8 and C == 256\n");
+    abort();
+  }
   const uint32_t rcp = rcp_for(p.H, p.W, p.C, "launch_in_apply");
   const int HW = p.H * p.W;
   if (g_ew_stream && p.dst8.p == nullptr && streamable(p.x, p.C) && streamable(p.skip, p.C)) {

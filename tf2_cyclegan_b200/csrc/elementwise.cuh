@@ -30,6 +30,9 @@ struct InApplyParams {
   View dst8;            // uint8 view (strides in bytes), p == nullptr if unused
   const float* scale8;
   float* amax8;
+  // MXFP8 twin instead (sf8.p != nullptr, C == 256): dst8 gets E4M3 bytes scaled per 32-channel block and
+  // sf8 (uint8 view, 16-byte records per pixel, same halo) the E8M0 block scales; scale8 / amax8 unused.
+  View sf8;
 };
 void launch_in_apply(const InApplyParams& p, cudaStream_t s);
 // The InstanceNorm kernels stream their inputs through a shared-memory ring filled by the bulk-copy

@@ -17,6 +17,7 @@
 #include "allreduce_adam.cuh"
 #include "conv_gemm.cuh"
 #include "elementwise.cuh"
+#include "mx.cuh"
 #include "wgrad_gemm.cuh"
 
 #include <nvtx3/nvToolsExt.h>
@@ -314,6 +315,33 @@ class Plan {
     });
   }
 
+  // MXFP8 conv (conv_gemm_mx.cu): E4M3 activations / weights with E8M0 scales per 32 K elements
+  int add_conv_gemm_mx(std::string name, py::bytes a_map, py::bytes sfa_map, py::bytes b_map, uint64_t sfb,
+                       std::vector<TapT> taps, int cin_blocks, int tiles_w, int tiles_h, int bw, int bh,
+                       int w_limit, int h_limit, uint64_t out, long long sn, long long sh, long long sw,
+                       int cout, uint64_t bias, int act, uint64_t stats, int num_images) {
+    auto p = std::make_shared<ConvGemmMxParams>();
+    memset(p.get(), 0, sizeof(ConvGemmMxParams));
+    ConvGemmParams& g = p->g;
+    g.tmA[0] = tmap_from(a_map);
+    g.tmB = tmap_from(b_map);
+    p->tmSFA = tmap_from(sfa_map);
+    p->sfb = P<const uint8_t>(sfb);
+    fill_taps(taps, g.taps, &g.num_taps);
+    if (bw * bh != 128) throw std::runtime_error("conv_gemm_mx tile must be 128 pixels");
+    g.cin_blocks = cin_blocks; g.tiles_w = tiles_w; g.tiles_h = tiles_h;
+    g.bw = bw; g.bh = bh; g.w_limit = w_limit;
+    g.h_limit = h_limit > 0 ? h_limit : tiles_h * bh;
+    g.out = P<__nv_bfloat16>(out); g.out_sn = sn; g.out_sh = sh; g.out_sw = sw;
+    g.cout = cout; g.bias = P<const float>(bias); g.act = act; g.stats = P<float>(stats);
+    g.fp8 = 1; g.num_phases = 1; g.phase_tap_count[0] = g.num_taps;
+    return add(std::move(name), [p, num_images](cudaStream_t s) { launch_conv_gemm_mx(*p, num_images, s); });
+  }
+  int add_mx_weight_quant(std::string name, uint64_t w, uint64_t w8, uint64_t sfb, int cout, int taps, int cin) {
+    MxWeightQuantParams p{P<const __nv_bfloat16>(w), P<uint8_t>(w8), P<uint8_t>(sfb), cout, taps, cin};
+    return add(std::move(name), [p](cudaStream_t s) { launch_mx_weight_quant(p, s); });
+  }
+
   int add_wgrad(std::string name, std::vector<py::bytes> dy_maps, std::vector<py::bytes> a_maps,
                 std::vector<TapT> taps, int ktiles_w, int ktiles_h, int kbw, int kbh,
                 int num_images, int cin, int cout, uint64_t dw, long long ldw, int block_n,
@@ -337,10 +365,11 @@ class Plan {
   // ------------------------------------------------------ elementwise ops
   int add_in_apply(std::string name, ViewT x, uint64_t stats, uint64_t gamma, uint64_t beta,
                    float inv_count, float eps, int act, ViewT skip, ViewT dst, int halo, int N,
-                   int H, int W, int C, ViewT dst8, uint64_t scale8, uint64_t amax8) {
+                   int H, int W, int C, ViewT dst8, uint64_t scale8, uint64_t amax8, ViewT sf8) {
     InApplyParams p{view_from(x), P<const float>(stats), P<const float>(gamma),
                     P<const float>(beta), inv_count, eps, act, view_from(skip), view_from(dst),
-                    halo, N, H, W, C, view_from(dst8), P<const float>(scale8), P<float>(amax8)};
+                    halo, N, H, W, C, view_from(dst8), P<const float>(scale8), P<float>(amax8),
+                    view_from(sf8)};
     return add(std::move(name), [p](cudaStream_t s) { launch_in_apply(p, s); });
   }
   int add_in_bwd_reduce(std::string name, ViewT g1, int fold1, ViewT g2, ViewT x, uint64_t stats,
@@ -536,7 +565,14 @@ PYBIND11_MODULE(_C, m) {
       .def("add_in_apply", &Plan::add_in_apply, py::arg("name"), py::arg("x"), py::arg("stats"),
            py::arg("gamma"), py::arg("beta"), py::arg("inv_count"), py::arg("eps"), py::arg("act"),
            py::arg("skip"), py::arg("dst"), py::arg("halo"), py::arg("N"), py::arg("H"), py::arg("W"),
-           py::arg("C"), py::arg("dst8") = ViewT{0, 0, 0, 0}, py::arg("scale8") = 0, py::arg("amax8") = 0)
+           py::arg("C"), py::arg("dst8") = ViewT{0, 0, 0, 0}, py::arg("scale8") = 0, py::arg("amax8") = 0,
+           py::arg("sf8") = ViewT{0, 0, 0, 0})
+      .def("add_conv_gemm_mx", &Plan::add_conv_gemm_mx, py::arg("name"), py::arg("a_map"), py::arg("sfa_map"),
+           py::arg("b_map"), py::arg("sfb"), py::arg("taps"), py::arg("cin_blocks"), py::arg("tiles_w"),
+           py::arg("tiles_h"), py::arg("bw"), py::arg("bh"), py::arg("w_limit"), py::arg("h_limit"),
+           py::arg("out"), py::arg("sn"), py::arg("sh"), py::arg("sw"), py::arg("cout"), py::arg("bias"),
+           py::arg("act"), py::arg("stats"), py::arg("num_images"))
+      .def("add_mx_weight_quant", &Plan::add_mx_weight_quant)
       .def("add_fp8_op", &Plan::add_fp8_op)
       .def("add_in_bwd_reduce", &Plan::add_in_bwd_reduce)
       .def("add_in_bwd_apply", &Plan::add_in_bwd_apply)

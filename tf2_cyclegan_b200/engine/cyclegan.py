@@ -50,7 +50,7 @@ class CycleGAN:
     if backend == "auto":
       native_ok = strategy.device.type == "cuda" and size >= 32 and size % 8 == 0
       backend = "native" if native_ok else "oracle"
-    if backend == "oracle" and dtype == "fp8":
+    if backend == "oracle" and dtype in ("fp8", "mxfp8"):
       dtype = "bf16"
     if backend == "native":
       from .native_backend import NativeBackend

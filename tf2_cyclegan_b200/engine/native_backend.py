@@ -224,9 +224,11 @@ class NativeBackend:
                fused_allreduce: str = "auto", use_graph: Optional[bool] = None):
     if not nv.available():
       raise RuntimeError("the native backend needs an sm_100 GPU (B200)")
-    if dtype not in ("bf16", "fp8"):
-      raise NotImplementedError(f"native backend: dtype {dtype!r} is not available (bf16 | fp8)")
-    self.fp8 = dtype == "fp8"   # residual-block forward convs in E4M3 (per-tensor delayed scaling)
+    if dtype not in ("bf16", "fp8", "mxfp8"):
+      raise NotImplementedError(f"native backend: dtype {dtype!r} is not available (bf16 | fp8 | mxfp8)")
+    # residual-block forward convs in E4M3: "tensor" = one delayed scale per tensor (--dtype fp8),
+    # "mx" = OCP MXFP8, one E8M0 scale per 32 channels of either operand (--dtype mxfp8); "" = bf16
+    self.fp8 = {"fp8": "tensor", "mxfp8": "mx"}.get(dtype, "")
     hw = (image_size, image_size) if isinstance(image_size, int) else tuple(int(v) for v in image_size)
     if len(hw) != 2 or min(hw) < 32 or hw[0] % 8 or hw[1] % 8:
       # three stride-2 stages in the discriminator (and two in the generators) must see even inputs;
@@ -569,7 +571,7 @@ class NativeBackend:
   # resume quantises with the scales it would have used without the interruption
   def extra_state(self) -> Dict[str, object]:
     out: Dict[str, object] = {}
-    if self.fp8:
+    if self.fp8 == "tensor":
       out["fp8"] = {n: {"act_amax": self.state[n].act_amax.tolist(), "act_scale": self.state[n].act_scale.tolist(),
                         "w_scale": self.state[n].w_scale.tolist(), "out_scale": self.state[n].out_scale.tolist()}
                     for n in ("G", "F") if self.state[n].w8 is not None}
@@ -577,7 +579,7 @@ class NativeBackend:
 
   def load_extra_state(self, extra: Dict[str, object]) -> None:
     fp8 = (extra or {}).get("fp8")
-    if not (self.fp8 and fp8):
+    if not (self.fp8 == "tensor" and fp8):
       return
     for n, d in fp8.items():
       st = self.state[n]

@@ -50,16 +50,24 @@ class NetState:
     self.step = torch.zeros(1, dtype=torch.int32, device=device)
     self.derived: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}   # name -> (bf16 dst, int32 idx)
     self.fp8_layers: List[ConvLayer] = []
+    self.fp8_mode = ""
     self.w8: Optional[torch.Tensor] = None
 
-  # ---- FP8 (E4M3, per-tensor power-of-two delayed scaling) for the residual-block convs
-  def enable_fp8(self):
+  # ---- FP8 for the residual-block convs: "tensor" = E4M3 with per-tensor power-of-two delayed scaling,
+  # "mx" = MXFP8 (E4M3 + one E8M0 scale per 32 K elements, no scaling state)
+  def enable_fp8(self, mode: str = "tensor"):
     if self.w8 is not None:
+      if mode != self.fp8_mode:
+        raise ValueError(f"network already set up for fp8 mode {self.fp8_mode!r}")
       return
     dev = self.w.device
+    self.fp8_mode = mode
     self.fp8_layers = [l for l in self.spec.layers if fp8_ok(l)]
     L = max(1, len(self.fp8_layers))
     self.w8 = torch.zeros(self.n, dtype=torch.uint8, device=dev)
+    # MX weight scales: one byte per (output channel, 32 K elements), per layer
+    self.w_sf = [torch.zeros(self.seg(l, "kernel").numel // 32 if mode == "mx" else 0, dtype=torch.uint8, device=dev)
+                 for l in self.fp8_layers]
     self.act_amax = torch.zeros(L, device=dev)
     self.w_amax = torch.zeros(L, device=dev)
     self.act_scale = torch.ones(L, device=dev)
@@ -77,6 +85,12 @@ class NetState:
     """Start-of-step bookkeeping: weight amax -> scales (activations: previous step's amax) ->
     E4M3 weight copy. Reads the bf16 compute copy, which is complete on every rank."""
     if not self.fp8_layers:
+      return
+    if self.fp8_mode == "mx":
+      for i, l in enumerate(self.fp8_layers):
+        seg = self.seg(l, "kernel")
+        plan.add_mx_weight_quant(f"fp8.{tag}.{l.name}.mx_w_quant", self.wb.data_ptr() + 2 * seg.offset,
+                                 self.w8.data_ptr() + seg.offset, self.w_sf[i].data_ptr(), l.cout, l.k * l.k, l.cin)
       return
     offs = [self.seg(l, "kernel").offset for l in self.fp8_layers]
     nums = [self.seg(l, "kernel").numel for l in self.fp8_layers]
@@ -136,11 +150,14 @@ class NetExec:
   """Buffers + op emission for ``nb`` images of one network at resolution ``size`` (int or (h, w))."""
 
   def __init__(self, spec: NetSpec, state: NetState, nb: int, size, device, tag: str,
-               fp8: bool = False, pool: Optional[dict] = None):
+               fp8="", pool: Optional[dict] = None):
+    """``fp8``: "" / False = bf16, "tensor" (or True) = per-tensor E4M3, "mx" = MXFP8 residual forward convs."""
     self.spec, self.st, self.nb, self.size, self.tag = spec, state, nb, size, tag
-    self.fp8 = fp8 and any(fp8_ok(l) for l in spec.layers)
+    fp8 = "tensor" if fp8 is True else (fp8 or "")
+    self.fp8 = fp8 if any(fp8_ok(l) for l in spec.layers) else ""
+    self.mx = self.fp8 == "mx"
     if self.fp8:
-      state.enable_fp8()
+      state.enable_fp8(self.fp8)
     self.layers = list(spec.layers)
     L = len(self.layers)
     dev = device
@@ -171,11 +188,14 @@ class NetExec:
     self.inp.append(self._buf("out", nb, ho, wo, cpad(self.layers[-1].cout)))
     # E4M3 twins of the inputs of the FP8 layers (written by the producing IN-apply kernel)
     self.inp8: Dict[int, Buf8] = {}
+    self.sf8: Dict[int, Buf8] = {}
     if self.fp8:
       for j, l in enumerate(self.layers):
         if fp8_ok(l):
           hh, ww = self.in_hw[j]
           self.inp8[j] = self._buf(f"inp8_{j}", nb, hh, ww, l.cin, halo=l.k // 2, cls=Buf8)
+          if self.mx:   # 16-byte scale records per pixel (byte i = channels [32 i, 32 i + 32))
+            self.sf8[j] = self._buf(f"sf8_{j}", nb, hh, ww, 16, halo=l.k // 2, cls=Buf8)
     self.raw: List[Optional[Buf]] = []
     self.stats: List[Optional[torch.Tensor]] = []
     self.bstats: List[Optional[torch.Tensor]] = []
@@ -343,6 +363,14 @@ class NetExec:
         if is_small_cin(l):
           maps, taps = self._small_cin_maps(j, n0, nimg, bw, bh)
           kch = 64
+        elif j in self.sf8:
+          # MXFP8 forward: block-scaled E4M3 activations x weights (scales applied inside the MMA)
+          slot = st.fp8_slot(l)
+          no.add_conv_mx(plan, name + ".mxfp8", self.inp8[j].tmap_padded(bw, bh, n0, nimg),
+                         self.sf8[j].tmap_padded(bw, bh, n0, nimg, cbox=16, swizzle=0),
+                         no.taps_conv(l.k, l.cin), l.cin, st.kernel_fp8(l), st.w_sf[slot], dst.view(n0), ho, wo,
+                         nimg, l.cout, bias, act, stats)
+          maps = None
         elif j in self.inp8:
           # FP8 forward: E4M3 activations x E4M3 weights, fp32 accumulate, de-scaled in the epilogue
           slot = st.fp8_slot(l)
@@ -372,8 +400,10 @@ class NetExec:
       if l.norm:
         nxt = self.inp[j + 1]
         skip = self.inp[j - 1].view(n0) if l.res == "b" else NULL_VIEW
-        dst8, scale8, amax8 = NULL_VIEW, 0, 0
-        if (j + 1) in self.inp8:
+        dst8, scale8, amax8, sfv = NULL_VIEW, 0, 0, NULL_VIEW
+        if (j + 1) in self.sf8:
+          dst8, sfv = self.inp8[j + 1].view(n0), self.sf8[j + 1].view(n0)
+        elif (j + 1) in self.inp8:
           b8 = self.inp8[j + 1]
           slot = st.fp8_slot(self.layers[j + 1])
           dst8 = b8.view(n0)
@@ -382,7 +412,7 @@ class NetExec:
         plan.add_in_apply(f"{self.tag}.{l.name}.in_apply[{n0}:{n0 + nimg}]", self.raw[j].view(n0),
                           stats, st.wptr(l, "gamma"), st.wptr(l, "beta"), 1.0 / (ho * wo), IN_EPS,
                           ACT[l.act], skip, nxt.view(n0), nxt.halo, nimg, ho, wo, l.cout,
-                          dst8, scale8, amax8)
+                          dst8, scale8, amax8, sfv)
 
   # -------------------------------------------------------------- backward
   def backward(self, plan, n0: int, nimg: int, wgrad: bool, stop_layer: int = 0,

@@ -111,6 +111,25 @@ def add_conv(plan, name: str, a_maps: Sequence[bytes], taps: Sequence[Tap], k_ch
                             bias, act, stats, block_n, b_mn, nimg, ph, out_scale, fp8, ts_map, ts, out_h)
 
 
+def add_conv_mx(plan, name: str, a_map: bytes, sfa_map: bytes, taps: Sequence[Tap], k_channels: int,
+                w8: torch.Tensor, sfb: torch.Tensor, out_view, out_h: int, out_w: int, nimg: int,
+                n_channels: int, bias: int = 0, act: int = 0, stats: int = 0,
+                tile: Optional[Tuple[int, int]] = None):
+  """MXFP8 box-mode implicit GEMM (csrc/conv_gemm_mx.cu): E4M3 activations (``a_map``, 128-channel
+  boxes) and weights (``w8`` [cout, taps * cin] bytes) with E8M0 scales per 32 K elements —
+  ``sfa_map``: 16-byte scale records per pixel; ``sfb``: the weight scales as written by
+  ``Plan.add_mx_weight_quant``. 128-channel output tiles."""
+  if k_channels % 128 or not 128 <= k_channels <= 512 or n_channels % 128:
+    raise ValueError(f"{name}: MXFP8 conv needs cin in 128..512 and cout as multiples of 128")
+  if sfb.numel() != n_channels * len(taps) * k_channels // 32:
+    raise ValueError(f"{name}: weight scale buffer has {sfb.numel()} bytes")
+  bw, bh = tile or nv.tile_shape(out_h, out_w)
+  ptr, sn, sh, sw = out_view
+  return plan.add_conv_gemm_mx(name, a_map, sfa_map, nv.wmat_tmap(w8, 256, False), sfb.data_ptr(), list(taps),
+                               k_channels // 128, out_w // bw, -(-out_h // bh), bw, bh, out_w, out_h,
+                               ptr, sn, sh, sw, n_channels, bias, act, stats, nimg)
+
+
 TS_STAGE_BYTES = 34 * 1024   # csrc/conv_gemm_ts.cu: TsCfg::kAStageBytes
 
 

@@ -152,10 +152,12 @@ class Buf8(Buf):
     off = 0 if padded else self.halo
     return self.t.data_ptr() + (n * self.sn + (h + off) * self.sh + (w + off) * self.sw + c)
 
-  def tmap_padded(self, bw: int, bh: int, n0: int = 0, nimg: Optional[int] = None, cbox: int = 128):
+  def tmap_padded(self, bw: int, bh: int, n0: int = 0, nimg: Optional[int] = None, cbox: int = 128,
+                  swizzle: int = 3):
+    """``cbox`` = 128, swizzle 3: E4M3 activations; ``cbox`` = 16, swizzle 0: MX scale records."""
     nimg = self.n - n0 if nimg is None else nimg
     return tmap(self.ptr(n0, padded=True), [self.c, self.wp, self.hp, nimg],
-                [self.sw, self.sh, self.sn], [cbox, bw, bh, 1], elem_bytes=1, dtype=2)
+                [self.sw, self.sh, self.sn], [cbox, bw, bh, 1], elem_bytes=1, dtype=2, swizzle=swizzle)
 
 
 def tile_shape(h: int, w: int, pixels: int = 128) -> Tuple[int, int]:

@@ -70,6 +70,19 @@ no.add_conv(p, "fwd", [x.tmap_padded(bw, bh)], no.taps_conv(3, c), c, w2, out.vi
             stats=0 if a.no_stats else stats.data_ptr(), tile=(bw, bh),
             halo_map=(lambda w_, h_: x.tmap_padded(w_, h_)) if ts else None)
 plans["fwd"] = (p, 2.0 * n * h * h * 9 * c * c)
+# the same conv with MXFP8 operands (csrc/conv_gemm_mx.cu): random E4M3 bytes / moderate scales
+x8 = nv.Buf8(n, h, h, c, halo=1)
+x8.t.copy_(torch.randint(0, 0x70, x8.t.shape, device="cuda", dtype=torch.uint8))
+sf8 = nv.Buf8(n, h, h, 16, halo=1)
+sf8.t.copy_(torch.randint(120, 134, sf8.t.shape, device="cuda", dtype=torch.uint8))
+w8 = torch.randint(0, 0x70, (c, 9 * c), device="cuda", dtype=torch.uint8)
+wsf = torch.randint(120, 134, (c * 9 * c // 32,), device="cuda", dtype=torch.uint8)
+out_mx = nv.Buf(n, h, h, c)
+p = C.Plan()
+mbw, mbh = nv.tile_shape(h, h)
+no.add_conv_mx(p, "mxfp8", x8.tmap_padded(mbw, mbh), sf8.tmap_padded(mbw, mbh, cbox=16, swizzle=0),
+               no.taps_conv(3, c), c, w8, wsf, out_mx.view(), h, h, n, c, stats=0 if a.no_stats else stats.data_ptr())
+plans["mxfp8"] = (p, 2.0 * n * h * h * 9 * c * c)
 P = h + 2
 rows = n * P * P
 p = C.Plan()
