@@ -64,14 +64,23 @@ class FakePlan:
     return self._add("conv_gemm_ts" if ts else "conv_gemm", name, len(taps), cout, block_n, b_mn, num_images)
 
   def add_conv_gemm_mx(self, name, a_map, sfa_map, b_map, sfb, taps, cin_blocks, tiles_w, tiles_h, bw, bh, w_limit,
-                       h_limit, out, sn, sh, sw, cout, bias, act, stats, num_images):
+                       h_limit, out, sn, sh, sw, cout, bias, act, stats, num_images, ts_map=b"", sfts_map=b"", ts=()):
     assert bw * bh == 128 and 1 <= len(taps) <= 52 and 1 <= cin_blocks <= 4 and cout % 128 == 0
+    if ts:   # tap sharing: activation halo box + scale-record halo box over the same pixels
+      nbox, box_step, box_bytes, pitch, odw, odh, sbo = ts
+      td, sd_ = decode(ts_map), decode(sfts_map)
+      assert td["box"][0] == 128 and td["box"][1] * td["box"][2] * 128 == box_bytes, (name, td["box"])
+      assert sd_["box"] == [16] + td["box"][1:] and sd_["dims"][1:] == td["dims"][1:], (name, sd_, td)
+      assert nbox * box_bytes <= 34 * 1024 and (nbox == 1 or box_bytes % 1024 == 0)
+      for t in taps:
+        shift = (t[3] - odh) * pitch + (t[2] - odw)
+        assert shift >= 0 and shift * 128 + 15 * sbo + 1024 <= nbox * box_bytes, (name, t)
     assert decode(a_map)["box"] == [128, bw, bh, 1], (name, decode(a_map)["box"])
     sd = decode(sfa_map)
     assert sd["box"] == [16, bw, bh, 1] and sd["dims"][0] == 16, (name, sd)
     assert sd["dims"][1:] == decode(a_map)["dims"][1:], "scale records must cover the same pixels"
     bd = decode(b_map)
-    assert bd["box"] == [128, 128] and bd["dims"][1] >= cout
+    assert bd["box"] == [128, 64] and bd["dims"][1] >= cout
     for t in taps:
       assert t[0] == 0 and t[4] % (cin_blocks * 128) == 0 and t[4] + cin_blocks * 128 <= bd["dims"][0], (name, t)
     assert sfb % 16 == 0 and out % 16 == 0 and tiles_w >= 1 and tiles_h >= 1 and num_images >= 1

@@ -403,10 +403,12 @@ def test_fp8_conv_and_in_apply_quantisation():
   assert rel_err(out.t, full) < 8e-2          # quantisation error of E4M3 operands
 
 
-def test_mxfp8_conv_and_quantisers():
+@pytest.mark.parametrize("shared", [False, True])
+def test_mxfp8_conv_and_quantisers(shared):
   """MXFP8 (E4M3 + E8M0 scale per 32 channels): the IN-apply twin writer and the weight quantiser must
   match the PyTorch reference bit for bit, and the block-scaled conv (kind::mxf8f6f4.block_scale,
-  scales staged into TMEM) must equal an fp32 conv of the de-quantised operands."""
+  scales staged into TMEM) must equal an fp32 conv of the de-quantised operands. ``shared``: the
+  tap-shared CTA-pair kernel (8 x 16 tiles, halo tiles of activations and scale records)."""
   nv, no, O = _mods()
   from tf2_cyclegan_b200.ops import mxfp8
   C = nv.load()
@@ -430,9 +432,11 @@ def test_mxfp8_conv_and_quantisers():
   plan.add_in_apply("q", xb.view(), 0, 0, 0, 1.0, 1e-3, 0, nv.NULL_VIEW, dst.view(), 1, n, h, h, c,
                     dst8.view(), 0, 0, sf8.view())
   plan.add_mx_weight_quant("wq", w2.data_ptr(), w8.data_ptr(), wsf.data_ptr(), cout, 9, c)
-  bw, bh = nv.tile_shape(h, h)
+  bw, bh = (8, 16) if shared else nv.tile_shape(h, h)
+  halo = (lambda w_, h_: (dst8.tmap_padded(w_, h_), sf8.tmap_padded(w_, h_, cbox=16, swizzle=0))) if shared else None
   no.add_conv_mx(plan, "conv.mx", dst8.tmap_padded(bw, bh), sf8.tmap_padded(bw, bh, cbox=16, swizzle=0),
-                 no.taps_conv(3, c), c, w8, wsf, out.view(), h, h, n, cout, stats=stats.data_ptr())
+                 no.taps_conv(3, c), c, w8, wsf, out.view(), h, h, n, cout, stats=stats.data_ptr(),
+                 tile=(bw, bh), halo_maps=halo)
   run(plan)
   # activations: bytes + scale records (reflect halo included), bit-exact
   xp = O.reflect_pad(x, 1)

@@ -35,7 +35,8 @@ class EngineConfig:
   ar_mode: str = "pull"        # two-shot part of the fused gradient reduce: "pull" | "push" (csrc/allreduce_adam.cuh);
                                # pull measured faster at 4 and 8 GPUs, in the step and stand-alone (profiles/README.md)
   # ---- debugging (timing experiments; results are INVALID for kernel_debug != 0)
-  kernel_debug: int = 0        # conv kernels: 1 skip epilogue, 2 skip MMAs, 3 skip TMA loads, 4 skip global stores
+  kernel_debug: int = 0        # conv kernels: 1 skip epilogue, 2 skip MMAs, 3 skip TMA loads, 4 skip global stores,
+                               # 5 (MXFP8 kernels) skip the scale-factor stores to TMEM
   stages: int = 0              # 1-CTA conv kernel: cap on the smem ring depth (0: default)
   grid: int = 0                # 1-CTA conv kernel: cap on the persistent grid (0: all SMs)
 
@@ -67,8 +68,8 @@ class EngineConfig:
       raise ValueError("config: ar_mode must be 'push' or 'pull'")
     if self.nvls not in ("auto", "off"):
       raise ValueError("config: nvls must be 'auto' or 'off'")
-    if not 0 <= self.kernel_debug <= 4:
-      raise ValueError("config: kernel_debug must be 0..4")
+    if not 0 <= self.kernel_debug <= 5:
+      raise ValueError("config: kernel_debug must be 0..5")
 
   def apply_to_extension(self, mod) -> None:
     """Push the kernel options into the loaded C++ extension (no getenv on that side)."""

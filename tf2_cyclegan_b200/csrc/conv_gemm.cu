@@ -36,8 +36,13 @@ template <int BLOCK_N>
 struct GemmCfg {
   static constexpr int kABytes = 128 * 128;        // 128 pixels x 64 bf16
   static constexpr int kBBytes = BLOCK_N * 128;    // BLOCK_N x 64 bf16
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+  static constexpr int kKbBytes = kABytes + kBBytes;              // one K block (64 channels of one tap)
+  // K blocks per pipeline stage. The MMA warp's own instruction stream costs ~800 cycles per barrier
+  // round trip (measured: profiles/r2/stem_probe.log) against 32 x N / 64 cycles of tensor work per K
+  // block, so narrow tiles batch two K blocks per stage (one wait, one commit for eight MMAs).
+  static constexpr int kKB = (BLOCK_N <= 128) ? 2 : 1;
+  static constexpr int kStageBytes = kKB * kKbBytes;
+  static constexpr int kStages = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 3 : (BLOCK_N >= 64 ? 4 : 5));
   static constexpr int kAccCols = BLOCK_N < 32 ? 32 : BLOCK_N;
   static constexpr int kTmemCols = 2 * kAccCols;   // 64 .. 512, power of two
   static constexpr int kChunkN = BLOCK_N < 64 ? BLOCK_N : 64;   // epilogue column chunk
@@ -101,7 +106,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int n
     // ============================ TMA producer ============================
     // warp-uniform loop; one elected lane issues (operands stay in uniform registers)
     {
-      uint32_t it = 0;
+      uint32_t s = 0, ph = 0;   // ring slot / phase of the stage being filled
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int phase = tile / tiles_per_phase;
         const int tp = tile - phase * tiles_per_phase;
@@ -113,20 +118,21 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int n
         const int w0 = (t_in - th * p.tiles_w) * p.bw;
         const int h0 = th * p.bh;
         const int t_begin = p.phase_tap_begin[phase], t_end = t_begin + p.phase_tap_count[phase];
+        const int num_kb = p.phase_tap_count[phase] * p.cin_blocks;
+        int kb = 0;
         for (int t = t_begin; t < t_end; ++t) {
           const Tap tap = p.taps[t];
           const CUtensorMap* amap = &p.tmA[tap.map];
-          for (int cb = 0; cb < p.cin_blocks; ++cb, ++it) {
-            const int s = it % nstages;
-            const uint32_t ph = (it / nstages) & 1;
-            mbar_wait(&empty_bar[s], ph ^ 1);
-            uint8_t* sa = smem + s * Cfg::kStageBytes;
+          for (int cb = 0; cb < p.cin_blocks; ++cb, ++kb) {
+            const int j = kb % Cfg::kKB;                      // position inside the stage
+            if (j == 0) mbar_wait(&empty_bar[s], ph ^ 1);
+            uint8_t* sa = smem + s * Cfg::kStageBytes + j * Cfg::kKbBytes;
             uint8_t* sb = sa + Cfg::kABytes;
             if (elect_one()) {
               if (dbg == 3) {
-                mbar_arrive(&full_bar[s]);
+                if (j == 0) mbar_arrive(&full_bar[s]);
               } else {
-                mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+                if (j == 0) mbar_arrive_expect_tx(&full_bar[s], min(Cfg::kKB, num_kb - kb) * Cfg::kKbBytes);
                 tma_load_4d(sa, amap, &full_bar[s], cb * 64, w0 + tap.dw, h0 + tap.dh, img + tap.dn);
                 if constexpr (!B_MN) {
                   if constexpr (BLOCK_N >= 128) {   // the host encodes half-height boxes for wide tiles
@@ -138,12 +144,15 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int n
                   }
                 } else {
 #pragma unroll
-                  for (int j = 0; j < BLOCK_N / 64; ++j)
-                    tma_load_2d(sb + j * (64 * 128), &p.tmB, &full_bar[s], tap.bk + n0 + j * 64, cb * 64);
+                  for (int jj = 0; jj < BLOCK_N / 64; ++jj)
+                    tma_load_2d(sb + jj * (64 * 128), &p.tmB, &full_bar[s], tap.bk + n0 + jj * 64, cb * 64);
                 }
               }
             }
             __syncwarp();
+            if (j == Cfg::kKB - 1 || kb == num_kb - 1) {      // stage complete
+              if (++s == static_cast<uint32_t>(nstages)) { s = 0; ph ^= 1; }
+            }
           }
         }
       }
@@ -154,7 +163,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int n
     {
       constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, B_MN ? 1 : 0);
       const uint32_t smem_base = smem_u32(smem);
-      uint32_t it = 0, tile_i = 0;
+      uint32_t s = 0, ph = 0, tile_i = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
         const int num_kb = p.phase_tap_count[tile / tiles_per_phase] * p.cin_blocks;
         const uint32_t acc = tile_i & 1;
@@ -162,29 +171,34 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p, int num_images, int n
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * Cfg::kAccCols;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % nstages;
-          const uint32_t ph = (it / nstages) & 1;
+        for (int kb = 0; kb < num_kb; kb += Cfg::kKB) {
+          const int nk = min(Cfg::kKB, num_kb - kb);
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t sa = smem_base + s * Cfg::kStageBytes;
-          const uint32_t sb = sa + Cfg::kABytes;
-          const uint64_t da = make_desc_kmajor(sa);
-          const uint64_t db = B_MN ? make_desc_mnmajor(sb, 64) : make_desc_kmajor(sb);
+          const uint32_t st = smem_base + s * Cfg::kStageBytes;
           if (elect_one()) {
             if (dbg != 2) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                // K advance of 16 elements: +32 B inside the swizzle row (K-major),
-                // +16 rows * 128 B (MN-major); descriptor address field is in 16-byte units
-                const uint64_t da_k = da + static_cast<uint64_t>(k * 2);
-                const uint64_t db_k = db + static_cast<uint64_t>(B_MN ? k * 128 : k * 2);
-                umma_bf16(tmem_d, da_k, db_k, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int j = 0; j < Cfg::kKB; ++j) {
+                if (j < nk) {
+                  const uint32_t sa = st + j * Cfg::kKbBytes;
+                  const uint64_t da = make_desc_kmajor(sa);
+                  const uint64_t db = B_MN ? make_desc_mnmajor(sa + Cfg::kABytes, 64) : make_desc_kmajor(sa + Cfg::kABytes);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) {
+                    // K advance of 16 elements: +32 B inside the swizzle row (K-major),
+                    // +16 rows * 128 B (MN-major); descriptor address field is in 16-byte units
+                    const uint64_t da_k = da + static_cast<uint64_t>(k * 2);
+                    const uint64_t db_k = db + static_cast<uint64_t>(B_MN ? k * 128 : k * 2);
+                    umma_bf16(tmem_d, da_k, db_k, idesc, (kb | j | k) != 0 ? 1u : 0u);
+                  }
+                }
               }
             }
             umma_commit(&empty_bar[s]);        // frees the smem slot when these MMAs retire
           }
           __syncwarp();
+          if (++s == static_cast<uint32_t>(nstages)) { s = 0; ph ^= 1; }
         }
         if (elect_one()) umma_commit(&tmem_full_bar[acc]);    // accumulator complete
         __syncwarp();

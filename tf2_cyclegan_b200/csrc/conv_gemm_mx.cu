@@ -26,6 +26,7 @@
 namespace b2 {
 
 int dbg_flag();
+bool use_2cta();
 
 namespace {
 
@@ -113,7 +114,7 @@ conv_gemm_mx_kernel(const __grid_constant__ ConvGemmMxParams q, int num_images, 
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
-      mbar_init(&sf_bar[s], 128);
+      mbar_init(&sf_bar[s], 4);            // one arrival per scale warp
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
@@ -153,7 +154,8 @@ conv_gemm_mx_kernel(const __grid_constant__ ConvGemmMxParams q, int num_images, 
           if (elect_one()) {
             mbar_arrive_expect_tx(&full_bar[s], Cfg::kTxBytes);
             tma_load_4d(sa, &p.tmA[0], &full_bar[s], cb * 128, w0 + tap.dw, h0 + tap.dh, img + tap.dn);
-            tma_load_2d(sb, &p.tmB, &full_bar[s], tap.bk + cb * 128, nt * kN);
+            tma_load_2d(sb, &p.tmB, &full_bar[s], tap.bk + cb * 128, nt * kN);             // box {128, 64}:
+            tma_load_2d(sb + 64 * 128, &p.tmB, &full_bar[s], tap.bk + cb * 128, nt * kN + 64);   // two halves
             tma_load_4d(sfa, &q.tmSFA, &full_bar[s], 0, w0 + tap.dw, h0 + tap.dh, img + tap.dn);
             const int tk = tap.bk / (p.cin_blocks * 128);   // position of the tap in the weight matrix
             bulk_load(sfb, sfb_tile + static_cast<long long>(tk * p.cin_blocks + cb) * Cfg::kSfbBytes,
@@ -222,11 +224,14 @@ conv_gemm_mx_kernel(const __grid_constant__ ConvGemmMxParams q, int num_images, 
           for (int j = 0; j < 4; ++j)
             a[j] = *reinterpret_cast<const uint32_t*>(sfa + (lane + 32 * j) * kMxSfRecord + (cb & 3) * 4);
           const uint4 b = *reinterpret_cast<const uint4*>(sfb + lane * 16);
-          tmem_st_32x4(lane_base + 8 * s, a[0], a[1], a[2], a[3]);
-          tmem_st_32x4(lane_base + 8 * s + 4, b.x, b.y, b.z, b.w);
-          tmem_st_wait();
+          if (dbg != 5) {   // timing experiment 5: no TMEM stores
+            tmem_st_32x4(lane_base + 8 * s, a[0], a[1], a[2], a[3]);
+            tmem_st_32x4(lane_base + 8 * s + 4, b.x, b.y, b.z, b.w);
+            tmem_st_wait();
+          }
           tc_fence_before();
-          mbar_arrive(&sf_bar[s]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sf_bar[s]);     // one arrival per warp: 128 per stage would serialise on the barrier
         }
       }
     }
@@ -257,6 +262,343 @@ conv_gemm_mx_kernel(const __grid_constant__ ConvGemmMxParams q, int num_images, 
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------
+// Tap-shared CTA-pair variant (the fast path; structure of conv_gemm_ts.cu): M = 256 pixels across
+// the pair (cta_group::2), N = 128, each CTA loads half of the weight tile, ONE activation halo
+// tile + ONE scale-record halo tile per 128-channel block serve all taps — the MMA reads the
+// activations through a row-shifted descriptor and the scale warpgroup reads the scale records
+// of the same shifted rows. Operand traffic per 128 x 128 output tile drops from 621 KB to ~200 KB,
+// which is what the per-tap kernel above is bound by.
+//
+// Barriers: a_full / b_full / sf_bar / tmem_* live in the leader (both CTAs' operand loads complete
+// there, as in conv_gemm_ts.cu); the scale data of each CTA lands on ITS OWN sfa_full / sfb_full
+// barriers because its own scale warpgroup consumes it.
+// Optional stall attribution (tools/kernel_bench.py --mx_profile): cycles every role of CTA 0 spends in
+// each of its barrier waits, written to a 16-slot device buffer. Off (nullptr) in normal runs.
+__device__ unsigned long long* g_mx_prof = nullptr;
+struct WaitClock {   // adds the cycles of its scope to a LOCAL counter (flushed once at the end of the role)
+  long long* acc;
+  long long t0;
+  __device__ __forceinline__ WaitClock(long long* counters, int i, bool on) : acc(on ? counters + i : nullptr), t0(0) {
+    if (acc) t0 = clock64();
+  }
+  __device__ __forceinline__ ~WaitClock() {
+    if (acc) *acc += clock64() - t0;
+  }
+};
+
+struct MxTsCfg {
+  static constexpr int kAStageBytes = 34 * 1024;           // activation halo tile (<= 272 rows x 128 B)
+  static constexpr int kSfHaloBytes = 5 * 1024;            // scale records of the same rows (16 B each)
+  static constexpr int kAStride = kAStageBytes + kSfHaloBytes;
+  static constexpr int kAStages = 2;
+  static constexpr int kBBytes = 64 * 128;                 // this CTA's half of the 128-row weight tile
+  static constexpr int kSfbBytes = kN * 4;
+  // Taps per weight stage: the MMA warp's own instruction stream costs ~900 cycles per barrier round
+  // trip (stall attribution: profiles/r2/mx_probe.log) against 256 tensor cycles per tap, so one
+  // stage carries three taps (one wait / commit / scale hand-over for twelve MMAs).
+  static constexpr int kTaps = 3;
+  static constexpr int kSfbOff = kTaps * kBBytes;          // weight scales follow the weight tiles
+  static constexpr int kBStride = 26 * 1024;               // kTaps * (kBBytes + kSfbBytes), 1024-aligned
+  static constexpr int kBStages = 4;
+  static constexpr int kSfCols = 8 * kTaps;                // TMEM columns per stage (SFA + SFB per tap)
+  static constexpr int kAccCols = kN;
+  static constexpr int kSfCol0 = 2 * kAccCols;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kStagingBytes = EpiCfg<kN>::kStagingBytes;
+  static constexpr int kRedBytes = EpiCfg<kN>::kRedBytes;
+  static constexpr int kNumBars = 3 * kAStages + 4 * kBStages + 4;
+  static constexpr int kBarrierBytes = kNumBars * 8 + 16;
+  static constexpr int kSmemBytes = kAStages * kAStride + kBStages * kBStride + kStagingBytes + kRedBytes +
+                                    kBarrierBytes + 1024;
+  static_assert(kTaps * (kBBytes + kSfbBytes) <= kBStride && kAStride % 1024 == 0, "stage layout");
+  static_assert(kSfCol0 + kSfCols * kBStages <= kTmemCols, "TMEM budget");
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
+};
+
+__device__ __forceinline__ void umma_mxf8_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t tmem_sfa, uint32_t tmem_sfb, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::2.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(384, 1)
+conv_gemm_mx_ts_kernel(const __grid_constant__ ConvGemmMxParams q, int num_images, int dbg) {
+  using Cfg = MxTsCfg;
+  const ConvGemmParams& p = q.g;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = smem + Cfg::kAStages * Cfg::kAStride;
+  uint8_t* stage_buf = b_ring + Cfg::kBStages * Cfg::kBStride;
+  float* red = reinterpret_cast<float*>(stage_buf + Cfg::kStagingBytes);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(stage_buf + Cfg::kStagingBytes + Cfg::kRedBytes);
+  uint64_t* a_empty = a_full + Cfg::kAStages;
+  uint64_t* sfa_full = a_empty + Cfg::kAStages;          // local: this CTA's scale-record halo landed
+  uint64_t* b_full = sfa_full + Cfg::kAStages;
+  uint64_t* b_empty = b_full + Cfg::kBStages;
+  uint64_t* sfb_full = b_empty + Cfg::kBStages;          // local: this CTA's weight-scale chunk landed
+  uint64_t* sf_bar = sfb_full + Cfg::kBStages;           // leader: both CTAs' scales are in TMEM
+  uint64_t* tmem_full_bar = sf_bar + Cfg::kBStages;      // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;          // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const int m_tiles = tiles_per_img * num_images;
+  const int m_pairs = (m_tiles + 1) >> 1;
+  const int n_tiles = p.cout / kN;
+  const int total_pairs = m_pairs * n_tiles;
+  const int kb_per_tile = p.num_taps * p.cin_blocks;
+  const TapShare ts = p.ts;
+  // first halo row of every tap, and the position of its weights / weight scales
+  __shared__ uint32_t tap_row[kMaxTaps];
+  __shared__ int tap_bk[kMaxTaps];
+  if (threadIdx.x < p.num_taps) {
+    const Tap tap = p.taps[threadIdx.x];
+    tap_bk[threadIdx.x] = tap.bk;
+    tap_row[threadIdx.x] = static_cast<uint32_t>((tap.dh - ts.origin_dh) * ts.pitch + (tap.dw - ts.origin_dw));
+  }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmTS);
+    tma_prefetch_desc(&q.tmSFTS);
+  } else if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kAStages; ++s) {
+      mbar_init(&a_full[s], 2);
+      mbar_init(&a_empty[s], 1);
+      mbar_init(&sfa_full[s], 1);
+    }
+    for (int s = 0; s < Cfg::kBStages; ++s) {
+      mbar_init(&b_full[s], 2);
+      mbar_init(&b_empty[s], 1);
+      mbar_init(&sfb_full[s], 1);
+      mbar_init(&sf_bar[s], 8);            // 4 scale warps x 2 CTAs
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 256);  // 128 epilogue threads x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 2) tmem_alloc_2sm(tmem_ptr_smem, Cfg::kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  auto decode = [&](int pt, int& mt, int& nt, int& img, int& h0, int& w0) {
+    const int mp = pt / n_tiles;
+    nt = pt - mp * n_tiles;
+    mt = 2 * mp + static_cast<int>(rank);
+    img = mt / tiles_per_img;              // == num_images for the phantom tile: TMA zero-fills
+    const int t_in = mt - img * tiles_per_img;
+    const int th = t_in / p.tiles_w;
+    w0 = (t_in - th * p.tiles_w) * p.bw;
+    h0 = th * p.bh;
+  };
+  const uint32_t sf_box_bytes = static_cast<uint32_t>(ts.box_bytes) / 128u * kMxSfRecord;
+  unsigned long long* prof_out = g_mx_prof;
+  const bool prof_on = prof_out != nullptr && blockIdx.x == 0 && lane == 0 &&
+                       (warp == 0 || warp == 1 || warp == 8 || warp == 4);
+  long long prof[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) prof[i] = 0;
+  const long long role_t0 = prof_on ? clock64() : 0;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    uint32_t ita = 0, itb = 0;
+    for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
+      int mt, nt, img, h0, w0;
+      decode(pt, mt, nt, img, h0, w0);
+      const uint8_t* sfb_tile = q.sfb + static_cast<long long>(nt) * kb_per_tile * Cfg::kSfbBytes;
+      for (int cb = 0; cb < p.cin_blocks; ++cb, ++ita) {
+        const int sa = ita % Cfg::kAStages;
+        { WaitClock wc(prof, 1, prof_on); mbar_wait(&a_empty[sa], ((ita / Cfg::kAStages) & 1) ^ 1); }
+        uint8_t* abuf = a_ring + sa * Cfg::kAStride;
+        uint8_t* sfbuf = abuf + Cfg::kAStageBytes;
+        if (elect_one()) {
+          if (rank == 0) mbar_arrive_expect_tx(&a_full[sa], 2 * ts.nbox * ts.box_bytes);
+          mbar_arrive_expect_tx(&sfa_full[sa], ts.nbox * sf_box_bytes);
+          for (int b = 0; b < ts.nbox; ++b) {
+            tma_load_4d_2sm(abuf + b * ts.box_bytes, &p.tmTS, &a_full[sa], cb * 128,
+                            w0 + ts.origin_dw + b * ts.box_step, h0 + ts.origin_dh, img);
+            tma_load_4d(sfbuf + b * sf_box_bytes, &q.tmSFTS, &sfa_full[sa], 0,
+                        w0 + ts.origin_dw + b * ts.box_step, h0 + ts.origin_dh, img);
+          }
+          if (rank != 0) mbar_arrive_cluster(&a_full[sa], 0);
+        }
+        __syncwarp();
+        for (int t = 0; t < p.num_taps; t += Cfg::kTaps, ++itb) {
+          const int nk = min(Cfg::kTaps, p.num_taps - t);
+          const int sb = itb % Cfg::kBStages;
+          { WaitClock wc(prof, 2, prof_on); mbar_wait(&b_empty[sb], ((itb / Cfg::kBStages) & 1) ^ 1); }
+          uint8_t* bbuf = b_ring + sb * Cfg::kBStride;
+          if (elect_one()) {
+            if (rank == 0) mbar_arrive_expect_tx(&b_full[sb], 2 * nk * Cfg::kBBytes);
+            mbar_arrive_expect_tx(&sfb_full[sb], nk * Cfg::kSfbBytes);
+            for (int j = 0; j < nk; ++j) {
+              const int bk = tap_bk[t + j];
+              tma_load_2d_2sm(bbuf + j * Cfg::kBBytes, &p.tmB, &b_full[sb], bk + cb * 128, nt * kN + rank * 64);
+              const int tk = bk / (p.cin_blocks * 128);
+              bulk_load(bbuf + Cfg::kSfbOff + j * Cfg::kSfbBytes,
+                        sfb_tile + static_cast<long long>(tk * p.cin_blocks + cb) * Cfg::kSfbBytes, Cfg::kSfbBytes,
+                        &sfb_full[sb]);
+            }
+            if (rank != 0) mbar_arrive_cluster(&b_full[sb], 0);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = make_idesc_mxf8(256, kN);
+      const uint32_t a_ring_u = smem_u32(a_ring), b_ring_u = smem_u32(b_ring);
+      uint32_t ita = 0, itb = 0, tile_i = 0;
+      for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++tile_i) {
+        const uint32_t acc = tile_i & 1;
+        { WaitClock wc(prof, 4, prof_on); mbar_wait(&tmem_empty_bar[acc], ((tile_i >> 1) & 1) ^ 1); }
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * Cfg::kAccCols;
+        uint32_t accumulate = 0;
+        for (int cb = 0; cb < p.cin_blocks; ++cb, ++ita) {
+          const int sa = ita % Cfg::kAStages;
+          { WaitClock wc(prof, 5, prof_on); mbar_wait(&a_full[sa], (ita / Cfg::kAStages) & 1); }
+          tc_fence_after();
+          const uint32_t a_base = a_ring_u + sa * Cfg::kAStride;
+          for (int t = 0; t < p.num_taps; t += Cfg::kTaps, ++itb) {
+            const int nk = min(Cfg::kTaps, p.num_taps - t);
+            const int sb = itb % Cfg::kBStages;
+            const uint32_t phb = (itb / Cfg::kBStages) & 1;
+            const bool stamp = prof_on && itb < 40;     // time line of the first 40 stages (slots 16 ..)
+            if (stamp) prof_out[16 + 5 * itb + 0] = clock64() - role_t0;
+            { WaitClock wc(prof, 6, prof_on); mbar_wait(&b_full[sb], phb); }
+            if (stamp) prof_out[16 + 5 * itb + 1] = clock64() - role_t0;
+            { WaitClock wc(prof, 7, prof_on); mbar_wait(&sf_bar[sb], phb); }
+            if (stamp) prof_out[16 + 5 * itb + 2] = clock64() - role_t0;
+            tc_fence_after();
+            const uint32_t b_base = b_ring_u + sb * Cfg::kBStride;
+            const uint32_t tsf = tmem_base + Cfg::kSfCol0 + Cfg::kSfCols * sb;
+            if (elect_one()) {
+              if (dbg != 2) {
+                WaitClock wc(prof, 13, prof_on);
+#pragma unroll
+                for (int j = 0; j < Cfg::kTaps; ++j) {
+                  if (j < nk) {
+                    const uint64_t da = make_smem_desc_sw128(a_base + tap_row[t + j] * 128u, 0, static_cast<uint32_t>(ts.sbo));
+                    const uint64_t db = make_desc_kmajor(b_base + j * Cfg::kBBytes);
+                    const uint32_t tsfa = tsf + 8 * j, tsfb = tsfa + 4;
+#pragma unroll
+                    for (uint32_t k = 0; k < 4; ++k)
+                      umma_mxf8_2sm(tmem_d, da + k * 2, db + k * 2, idesc | (k << 29) | (k << 4), tsfa | (k << 30),
+                                    tsfb | (k << 30), (j == 0 && k == 0) ? accumulate : 1u);
+                  }
+                }
+              }
+              if (stamp) prof_out[16 + 5 * itb + 3] = clock64() - role_t0;
+              {
+                WaitClock wc(prof, 14, prof_on);
+                umma_commit_2sm(&b_empty[sb]);
+              }
+            }
+            __syncwarp();
+            if (stamp) prof_out[16 + 5 * itb + 4] = clock64() - role_t0;
+            accumulate = 1;
+          }
+          if (elect_one()) umma_commit_2sm(&a_empty[sa]);
+          __syncwarp();
+        }
+        if (elect_one()) umma_commit_2sm(&tmem_full_bar[acc]);
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== scale factors (both CTAs, own TMEM) =====================
+    const int sp = warp - 8;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(sp * 32) << 16) + Cfg::kSfCol0;
+    const uint32_t group_rows = static_cast<uint32_t>(ts.sbo) / 128u;   // halo rows between 8-row groups of the tile
+    uint32_t rel[4];                        // halo row of tile pixel lane + 32 j, relative to the tap's first row
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t m = lane + 32 * j;
+      rel[j] = (m >> 3) * group_rows + (m & 7);
+    }
+    uint32_t ita = 0, itb = 0;
+    for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
+      for (int cb = 0; cb < p.cin_blocks; ++cb, ++ita) {
+        const int sa = ita % Cfg::kAStages;
+        { WaitClock wc(prof, 9, prof_on); mbar_wait(&sfa_full[sa], (ita / Cfg::kAStages) & 1); }
+        const uint8_t* sfh = a_ring + sa * Cfg::kAStride + Cfg::kAStageBytes + (cb & 3) * 4;
+        for (int t = 0; t < p.num_taps; t += Cfg::kTaps, ++itb) {
+          const int nk = min(Cfg::kTaps, p.num_taps - t);
+          const int sb = itb % Cfg::kBStages;
+          { WaitClock wc(prof, 10, prof_on); mbar_wait(&sfb_full[sb], (itb / Cfg::kBStages) & 1); }
+          const uint8_t* sfb = b_ring + sb * Cfg::kBStride + Cfg::kSfbOff + lane * 16;
+#pragma unroll
+          for (int j = 0; j < Cfg::kTaps; ++j) {
+            if (j < nk) {
+              const uint32_t r0 = tap_row[t + j];
+              uint32_t a[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const uint32_t*>(sfh + (r0 + rel[i]) * kMxSfRecord);
+              const uint4 b = *reinterpret_cast<const uint4*>(sfb + j * Cfg::kSfbBytes);
+              if (dbg != 5) {   // timing experiment 5: no TMEM stores
+                tmem_st_32x4(lane_base + Cfg::kSfCols * sb + 8 * j, a[0], a[1], a[2], a[3]);
+                tmem_st_32x4(lane_base + Cfg::kSfCols * sb + 8 * j + 4, b.x, b.y, b.z, b.w);
+              }
+            }
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&sf_bar[sb], 0);   // one arrival per warp
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own TMEM lanes) =====================
+    const int e = threadIdx.x - 128;
+    const int ew = warp - 4;
+    uint32_t tile_i = 0;
+    for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++tile_i) {
+      int mt, nt, img, h0, w0;
+      decode(pt, mt, nt, img, h0, w0);
+      const uint32_t acc = tile_i & 1;
+      { WaitClock wc(prof, 12, prof_on && warp == 4); mbar_wait(&tmem_full_bar[acc], (tile_i >> 1) & 1); }
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * Cfg::kAccCols + (static_cast<uint32_t>(ew * 32) << 16);
+      if (dbg == 1) { tc_fence_before(); mbar_arrive_cluster(&tmem_empty_bar[acc], 0); continue; }
+      conv_epilogue_tile<kN>(p, p.out, stage_buf, red, taddr, img, h0, w0, nt * kN, e, ew, lane, mt < m_tiles,
+                             [&]() { mbar_arrive_cluster(&tmem_empty_bar[acc], 0); }, dbg);
+    }
+  }
+
+  if (prof_on) {   // each role flushes its own counter slots
+    const int lo = warp == 0 ? 0 : warp == 1 ? 3 : warp == 8 ? 8 : 11;
+    const int hi = warp == 0 ? 3 : warp == 1 ? 8 : warp == 8 ? 11 : 13;
+    prof[lo] = clock64() - role_t0;
+    for (int i = lo; i < hi; ++i) prof_out[i] = static_cast<unsigned long long>(prof[i]);
+    if (warp == 1) for (int i = 13; i < 16; ++i) prof_out[i] = static_cast<unsigned long long>(prof[i]);
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
 }
 
 // one thread per (output channel, 32-element K block)
@@ -303,6 +645,9 @@ __global__ void __launch_bounds__(256) mx_weight_quant_kernel(const MxWeightQuan
 
 }  // namespace
 
+// device buffer of 16 counters (or 0 to switch the stall attribution off)
+void set_mx_profile(unsigned long long* buf) { cudaMemcpyToSymbol(g_mx_prof, &buf, sizeof(buf)); }
+
 void launch_conv_gemm_mx(const ConvGemmMxParams& p, int num_images, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
@@ -316,6 +661,32 @@ void launch_conv_gemm_mx(const ConvGemmMxParams& p, int num_images, cudaStream_t
   int sms = 0, dev = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const TapShare& ts = p.g.ts;
+  if (ts.enabled && use_2cta() && p.g.tiles_w * p.g.tiles_h * num_images >= 2 && ts.nbox >= 1 &&
+      ts.nbox * ts.box_bytes <= MxTsCfg::kAStageBytes && (ts.nbox == 1 || ts.box_bytes % 1024 == 0)) {
+    static bool configured_ts = false;
+    if (!configured_ts) {
+      cudaFuncSetAttribute(conv_gemm_mx_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MxTsCfg::kSmemBytes);
+      configured_ts = true;
+    }
+    const int m_tiles = p.g.tiles_w * p.g.tiles_h * num_images;
+    const int pairs = ((m_tiles + 1) / 2) * (p.g.cout / kN);
+    const int clusters = pairs < sms / 2 ? pairs : sms / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(384);
+    cfg.dynamicSmemBytes = MxTsCfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, conv_gemm_mx_ts_kernel, p, num_images, dbg_flag());
+    return;
+  }
   const int total = p.g.tiles_w * p.g.tiles_h * num_images * (p.g.cout / kN);
   const int grid = total < sms ? total : sms;
   conv_gemm_mx_kernel<<<grid, 384, MxCfg::kSmemBytes, stream>>>(p, num_images, dbg_flag());

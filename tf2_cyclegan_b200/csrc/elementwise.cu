@@ -589,7 +589,8 @@ __device__ __forceinline__ void stream_run(uint8_t* smem, const V32 (&views)[NT]
   }
 }
 
-template <int ACT, bool SKIP, bool HALO>
+// MX: also write the MXFP8 twin (dst8 bytes + sf8 scale records; C == 256: one consumer warp per pixel)
+template <int ACT, bool SKIP, bool HALO, bool MX>
 __global__ void __launch_bounds__(kStreamThreads, 2) in_apply_stream_kernel(const InApplyParams p, int pix_per_block,
                                                                            uint32_t rcp_w) {
   extern __shared__ __align__(128) uint8_t ring[];
@@ -628,6 +629,18 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_apply_stream_kernel(cons
   const V32 D = v32(p.dst, n, c);
   const float slope = act_slope(p.act);
   const int H = p.H, W = p.W, halo = p.halo;
+  uint8_t* d8 = nullptr;
+  uint8_t* sf = nullptr;
+  int d8sh = 0, d8sw = 0, sfsh = 0, sfsw = 0;
+  if constexpr (MX) {
+    d8 = reinterpret_cast<uint8_t*>(p.dst8.p) + static_cast<long long>(n) * p.dst8.sn + c;
+    d8sh = static_cast<int>(p.dst8.sh);
+    d8sw = static_cast<int>(p.dst8.sw);
+    sf = reinterpret_cast<uint8_t*>(p.sf8.p) + static_cast<long long>(n) * p.sf8.sn;
+    sfsh = static_cast<int>(p.sf8.sh);
+    sfsw = static_cast<int>(p.sf8.sw);
+  }
+  const bool lane0 = (threadIdx.x & 31) == 0;
   stream_run<NT, STAGES>(ring, views, g, c, ln, lanes, [&](int, int h, int w, const uint4 (&v)[NT]) {
     float x[8], o[8];
     unpack8(v[0], x);
@@ -641,13 +654,42 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_apply_stream_kernel(cons
     }
     const uint4 pk = pack8(o);
     stv(D, h, w, pk);
+    uint2 pk8 = make_uint2(0u, 0u), sfrec = make_uint2(0u, 0u);
+    if constexpr (MX) {
+      // block = 4 adjacent lanes of this pixel's warp; quantises the fp32 values (as the direct kernel does)
+      const float (&q)[8] = o;
+      float bmax = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bmax = fmaxf(bmax, fabsf(q[j]));
+      bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, 1));
+      bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, 2));
+      const uint32_t sb = mx_scale_byte(bmax);
+      const float inv = mx_inv_scale(sb);
+      uint32_t o8[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        o8[j] = __nv_cvt_float2_to_fp8x2(make_float2(q[2 * j] * inv, q[2 * j + 1] * inv), __NV_SATFINITE, __NV_E4M3);
+        sfrec.x |= __shfl_sync(0xffffffffu, sb, 4 * j) << (8 * j);
+        sfrec.y |= __shfl_sync(0xffffffffu, sb, 16 + 4 * j) << (8 * j);
+      }
+      pk8 = make_uint2(o8[0] | (o8[1] << 16), o8[2] | (o8[3] << 16));
+      *reinterpret_cast<uint2*>(d8 + (h * d8sh + w * d8sw)) = pk8;
+      if (lane0) *reinterpret_cast<uint2*>(sf + (h * sfsh + w * sfsw)) = sfrec;
+    }
     if constexpr (HALO) {
       const int hm = (h >= 1 && h <= halo) ? -h : ((h >= H - 1 - halo && h <= H - 2) ? 2 * (H - 1) - h : h);
       const int wm = (w >= 1 && w <= halo) ? -w : ((w >= W - 1 - halo && w <= W - 2) ? 2 * (W - 1) - w : w);
-      if (hm != h) stv(D, hm, w, pk);
+      auto mirror = [&](int hh, int ww) {
+        stv(D, hh, ww, pk);
+        if constexpr (MX) {
+          *reinterpret_cast<uint2*>(d8 + (hh * d8sh + ww * d8sw)) = pk8;
+          if (lane0) *reinterpret_cast<uint2*>(sf + (hh * sfsh + ww * sfsw)) = sfrec;
+        }
+      };
+      if (hm != h) mirror(hm, w);
       if (wm != w) {
-        stv(D, h, wm, pk);
-        if (hm != h) stv(D, hm, wm, pk);
+        mirror(h, wm);
+        if (hm != h) mirror(hm, wm);
       }
     }
   });
@@ -1208,9 +1250,15 @@ constexpr size_t ring_bytes(int nt, int stages) { return static_cast<size_t>(sta
 template <int ACT, bool SKIP, bool HALO>
 static void launch_in_apply_stream_t(const InApplyParams& p, dim3 grid, int ppb, uint32_t rcp, cudaStream_t s) {
   constexpr size_t smem = ring_bytes(SKIP ? 2 : 1, SKIP ? 6 : 8);
-  static bool once = (stream_smem(in_apply_stream_kernel<ACT, SKIP, HALO>, smem), true);
+  if (p.sf8.p != nullptr) {
+    static bool once_mx = (stream_smem(in_apply_stream_kernel<ACT, SKIP, HALO, true>, smem), true);
+    (void)once_mx;
+    in_apply_stream_kernel<ACT, SKIP, HALO, true><<<grid, kStreamThreads, smem, s>>>(p, ppb, rcp);
+    return;
+  }
+  static bool once = (stream_smem(in_apply_stream_kernel<ACT, SKIP, HALO, false>, smem), true);
   (void)once;
-  in_apply_stream_kernel<ACT, SKIP, HALO><<<grid, kStreamThreads, smem, s>>>(p, ppb, rcp);
+  in_apply_stream_kernel<ACT, SKIP, HALO, false><<<grid, kStreamThreads, smem, s>>>(p, ppb, rcp);
 }
 template <int ACT>
 static void launch_in_apply_stream_a(const InApplyParams& p, dim3 grid, int ppb, uint32_t rcp, cudaStream_t s) {
@@ -1238,7 +1286,7 @@ void launch_in_apply(const InApplyParams& p, cudaStream_t s) {
   }
   const uint32_t rcp = rcp_for(p.H, p.W, p.C, "launch_in_apply");
   const int HW = p.H * p.W;
-  if (g_ew_stream && p.dst8.p == nullptr && streamable(p.x, p.C) && streamable(p.skip, p.C)) {
+  if (g_ew_stream && (p.dst8.p == nullptr || p.sf8.p != nullptr) && streamable(p.x, p.C) && streamable(p.skip, p.C)) {
     const int ppb = stream_ppb(HW, p.N, p.C);
     dim3 grid((HW + ppb - 1) / ppb, p.N);
     if (p.act == ACT_RELU) launch_in_apply_stream_a<ACTK_RELU>(p, grid, ppb, rcp, s);

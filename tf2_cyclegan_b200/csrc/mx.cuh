@@ -24,11 +24,14 @@ __device__ __forceinline__ float mx_inv_scale(uint32_t byte) {
 
 // Implicit-GEMM conv with MXFP8 operands (conv_gemm_mx.cu).
 struct ConvGemmMxParams {
-  ConvGemmParams g;     // tmA[0]: E4M3 activations, box {128 ch, bw, bh, 1}; tmB: E4M3 weights, box {128, 128}
+  ConvGemmParams g;     // tmA[0]: E4M3 activations, box {128 ch, bw, bh, 1}; tmB: E4M3 weights, box {128, 64};
+                        // g.ts / g.tmTS: optional halo box of the activations (tap-shared CTA-pair kernel)
   CUtensorMap tmSFA;    // activation scale records [.., 16] uint8, box {16, bw, bh, 1}, no swizzle
+  CUtensorMap tmSFTS;   // g.ts.enabled: halo box of the scale records (same pixels as g.tmTS, 16-byte inner box)
   const uint8_t* sfb;   // weight scales [n_tiles][taps][cin_blocks][32][4][4] (TMEM scale-factor order)
 };
 void launch_conv_gemm_mx(const ConvGemmMxParams& p, int num_images, cudaStream_t stream);
+void set_mx_profile(unsigned long long* buf);   // stall attribution of the tap-shared kernel (tools/kernel_bench.py)
 
 // bf16 [cout][taps * cin] weights -> E4M3 bytes (same indexing) + scales in the order above
 struct MxWeightQuantParams {

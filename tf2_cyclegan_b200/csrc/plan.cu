@@ -319,7 +319,8 @@ class Plan {
   int add_conv_gemm_mx(std::string name, py::bytes a_map, py::bytes sfa_map, py::bytes b_map, uint64_t sfb,
                        std::vector<TapT> taps, int cin_blocks, int tiles_w, int tiles_h, int bw, int bh,
                        int w_limit, int h_limit, uint64_t out, long long sn, long long sh, long long sw,
-                       int cout, uint64_t bias, int act, uint64_t stats, int num_images) {
+                       int cout, uint64_t bias, int act, uint64_t stats, int num_images, py::bytes ts_map,
+                       py::bytes sfts_map, std::vector<int> ts) {
     auto p = std::make_shared<ConvGemmMxParams>();
     memset(p.get(), 0, sizeof(ConvGemmMxParams));
     ConvGemmParams& g = p->g;
@@ -335,6 +336,18 @@ class Plan {
     g.out = P<__nv_bfloat16>(out); g.out_sn = sn; g.out_sh = sh; g.out_sw = sw;
     g.cout = cout; g.bias = P<const float>(bias); g.act = act; g.stats = P<float>(stats);
     g.fp8 = 1; g.num_phases = 1; g.phase_tap_count[0] = g.num_taps;
+    if (!ts.empty()) {   // tap sharing, as in add_conv_gemm; the scale records get a halo box of the same pixels
+      if (ts.size() != 7) throw std::runtime_error("ts needs 7 integers");
+      g.tmTS = tmap_from(ts_map);
+      p->tmSFTS = tmap_from(sfts_map);
+      g.ts = TapShare{1, ts[0], ts[1], ts[2], ts[3], ts[4], ts[5], ts[6]};
+      for (int i = 0; i < g.num_taps; ++i) {
+        const Tap& t = g.taps[i];
+        const int shift = (t.dh - ts[5]) * ts[3] + (t.dw - ts[4]);
+        if (t.map != 0 || t.dn != 0 || shift < 0 || shift * 128 + 15 * ts[6] + 1024 > ts[0] * ts[2])
+          throw std::runtime_error("tap outside the shared halo tile");
+      }
+    }
     return add(std::move(name), [p, num_images](cudaStream_t s) { launch_conv_gemm_mx(*p, num_images, s); });
   }
   int add_mx_weight_quant(std::string name, uint64_t w, uint64_t w8, uint64_t sfb, int cout, int taps, int cin) {
@@ -538,6 +551,8 @@ PYBIND11_MODULE(_C, m) {
         py::arg("stages"), py::arg("grid"), "process-wide kernel options (tf2_cyclegan_b200/config.py)");
   m.def("set_ew_stream", &b2::set_ew_stream, "InstanceNorm kernels: true = bulk-copy ring (default), false = direct");
   m.def("ew_stream", &b2::ew_stream);
+  m.def("set_mx_profile", [](uint64_t ptr) { b2::set_mx_profile(reinterpret_cast<unsigned long long*>(ptr)); },
+        "device buffer of 16 uint64 counters for the MXFP8 kernel's stall attribution (0 = off)");
   m.def("device_sync", []() { check(cudaDeviceSynchronize(), "cudaDeviceSynchronize"); });
   m.attr("MAX_TAPS") = kMaxTaps;
   py::class_<Plan>(m, "Plan")
@@ -571,7 +586,8 @@ PYBIND11_MODULE(_C, m) {
            py::arg("b_map"), py::arg("sfb"), py::arg("taps"), py::arg("cin_blocks"), py::arg("tiles_w"),
            py::arg("tiles_h"), py::arg("bw"), py::arg("bh"), py::arg("w_limit"), py::arg("h_limit"),
            py::arg("out"), py::arg("sn"), py::arg("sh"), py::arg("sw"), py::arg("cout"), py::arg("bias"),
-           py::arg("act"), py::arg("stats"), py::arg("num_images"))
+           py::arg("act"), py::arg("stats"), py::arg("num_images"), py::arg("ts_map") = py::bytes(""),
+           py::arg("sfts_map") = py::bytes(""), py::arg("ts") = std::vector<int>{})
       .def("add_mx_weight_quant", &Plan::add_mx_weight_quant)
       .def("add_fp8_op", &Plan::add_fp8_op)
       .def("add_in_bwd_reduce", &Plan::add_in_bwd_reduce)

@@ -366,10 +366,16 @@ class NetExec:
         elif j in self.sf8:
           # MXFP8 forward: block-scaled E4M3 activations x weights (scales applied inside the MMA)
           slot = st.fp8_slot(l)
-          no.add_conv_mx(plan, name + ".mxfp8", self.inp8[j].tmap_padded(bw, bh, n0, nimg),
-                         self.sf8[j].tmap_padded(bw, bh, n0, nimg, cbox=16, swizzle=0),
+          a8, s8 = self.inp8[j], self.sf8[j]
+          tile, halo = None, None
+          if ho % 16 == 0 and wo % 8 == 0:   # 8 x 16 tiles: one halo tile per channel block (CTA-pair kernel)
+            tile, (bw, bh) = (8, 16), (8, 16)
+            halo = lambda w_, h_: (a8.tmap_padded(w_, h_, n0, nimg),
+                                   s8.tmap_padded(w_, h_, n0, nimg, cbox=16, swizzle=0))
+          no.add_conv_mx(plan, name + ".mxfp8", a8.tmap_padded(bw, bh, n0, nimg),
+                         s8.tmap_padded(bw, bh, n0, nimg, cbox=16, swizzle=0),
                          no.taps_conv(l.k, l.cin), l.cin, st.kernel_fp8(l), st.w_sf[slot], dst.view(n0), ho, wo,
-                         nimg, l.cout, bias, act, stats)
+                         nimg, l.cout, bias, act, stats, tile=tile, halo_maps=halo)
           maps = None
         elif j in self.inp8:
           # FP8 forward: E4M3 activations x E4M3 weights, fp32 accumulate, de-scaled in the epilogue

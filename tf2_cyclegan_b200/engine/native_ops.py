@@ -114,20 +114,54 @@ def add_conv(plan, name: str, a_maps: Sequence[bytes], taps: Sequence[Tap], k_ch
 def add_conv_mx(plan, name: str, a_map: bytes, sfa_map: bytes, taps: Sequence[Tap], k_channels: int,
                 w8: torch.Tensor, sfb: torch.Tensor, out_view, out_h: int, out_w: int, nimg: int,
                 n_channels: int, bias: int = 0, act: int = 0, stats: int = 0,
-                tile: Optional[Tuple[int, int]] = None):
+                tile: Optional[Tuple[int, int]] = None, halo_maps=None):
   """MXFP8 box-mode implicit GEMM (csrc/conv_gemm_mx.cu): E4M3 activations (``a_map``, 128-channel
   boxes) and weights (``w8`` [cout, taps * cin] bytes) with E8M0 scales per 32 K elements —
   ``sfa_map``: 16-byte scale records per pixel; ``sfb``: the weight scales as written by
-  ``Plan.add_mx_weight_quant``. 128-channel output tiles."""
-  if k_channels % 128 or not 128 <= k_channels <= 512 or n_channels % 128:
-    raise ValueError(f"{name}: MXFP8 conv needs cin in 128..512 and cout as multiples of 128")
-  if sfb.numel() != n_channels * len(taps) * k_channels // 32:
-    raise ValueError(f"{name}: weight scale buffer has {sfb.numel()} bytes")
+  ``Plan.add_mx_weight_quant``. 128-channel output tiles. ``halo_maps(box_w, box_h)`` -> (activation,
+  scale-record) tensor maps with a halo-sized box enables the tap-shared CTA-pair kernel."""
+  _check_mx(name, k_channels, n_channels, len(taps), sfb)
   bw, bh = tile or nv.tile_shape(out_h, out_w)
   ptr, sn, sh, sw = out_view
-  return plan.add_conv_gemm_mx(name, a_map, sfa_map, nv.wmat_tmap(w8, 256, False), sfb.data_ptr(), list(taps),
+  ts_map, sfts_map, ts = b"", b"", []
+  from ..config import ENGINE
+  if halo_maps is not None and ENGINE.tap_share:
+    dws, dhs = [t[2] for t in taps], [t[3] for t in taps]
+    box_w, box_h = bw + max(dws) - min(dws), bh + max(dhs) - min(dhs)
+    if bw == 8 and box_w <= 256 and box_h <= 256 and box_w * box_h * 128 <= TS_STAGE_BYTES:
+      ts_map, sfts_map = halo_maps(box_w, box_h)
+      ts = [1, 0, box_w * box_h * 128, box_w, min(dws), min(dhs), box_w * 128]
+  return plan.add_conv_gemm_mx(name, a_map, sfa_map, nv.wmat_tmap(w8, 128, False), sfb.data_ptr(), list(taps),
                                k_channels // 128, out_w // bw, -(-out_h // bh), bw, bh, out_w, out_h,
-                               ptr, sn, sh, sw, n_channels, bias, act, stats, nimg)
+                               ptr, sn, sh, sw, n_channels, bias, act, stats, nimg, ts_map, sfts_map, ts)
+
+
+def add_conv_flat_mx(plan, name: str, a_map: bytes, sfa_map: bytes, taps: Sequence[Tap], k_channels: int,
+                     w8: torch.Tensor, sfb: torch.Tensor, out_ptr: int, out_row_stride: int, rows: int,
+                     n_channels: int, halo_maps=None):
+  """Flat-mode MXFP8 implicit GEMM over ``rows`` consecutive pixels of a zero-ringed domain (dgrad of a
+  reflection-padded conv); ``halo_maps(rows_box)`` -> (activation, scale-record) maps for tap sharing."""
+  _check_mx(name, k_channels, n_channels, len(taps), sfb)
+  tiles = (rows + 127) // 128
+  ts_map, sfts_map, ts = b"", b"", []
+  from ..config import ENGINE
+  if halo_maps is not None and ENGINE.tap_share:
+    dws = [t[2] for t in taps]
+    span = 128 + max(dws) - min(dws)
+    box_rows = -(-((span + 1) // 2) // 8) * 8
+    if all(t[3] == 0 for t in taps) and 2 * box_rows * 128 <= TS_STAGE_BYTES and box_rows <= 256:
+      ts_map, sfts_map = halo_maps(box_rows)
+      ts = [2, box_rows, box_rows * 128, 0, min(dws), 0, 1024]
+  return plan.add_conv_gemm_mx(name, a_map, sfa_map, nv.wmat_tmap(w8, 128, False), sfb.data_ptr(), list(taps),
+                               k_channels // 128, tiles, 1, 128, 1, rows, 1, out_ptr, 0, 0, out_row_stride,
+                               n_channels, 0, 0, 0, 1, ts_map, sfts_map, ts)
+
+
+def _check_mx(name: str, k_channels: int, n_channels: int, ntaps: int, sfb: torch.Tensor):
+  if k_channels % 128 or not 128 <= k_channels <= 512 or n_channels % 128:
+    raise ValueError(f"{name}: MXFP8 conv needs cin in 128..512 and cout as multiples of 128")
+  if sfb.numel() != n_channels * ntaps * k_channels // 32:
+    raise ValueError(f"{name}: weight scale buffer has {sfb.numel()} bytes")
 
 
 TS_STAGE_BYTES = 34 * 1024   # csrc/conv_gemm_ts.cu: TsCfg::kAStageBytes

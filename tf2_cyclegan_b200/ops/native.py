@@ -160,6 +160,14 @@ class Buf8(Buf):
                 [self.sw, self.sh, self.sn], [cbox, bw, bh, 1], elem_bytes=1, dtype=2, swizzle=swizzle)
 
 
+  def tmap_flat(self, n0: int = 0, nimg: Optional[int] = None, rows_box: int = 128, cbox: int = 128,
+                swizzle: int = 3):
+    nimg = self.n - n0 if nimg is None else nimg
+    rows = nimg * self.hp * self.wp
+    return tmap(self.ptr(n0, padded=True), [self.c, rows, 1, 1], [self.sw, rows * self.sw, rows * self.sw],
+                [cbox, rows_box, 1, 1], elem_bytes=1, dtype=2, swizzle=swizzle)
+
+
 def tile_shape(h: int, w: int, pixels: int = 128) -> Tuple[int, int]:
   """(bw, bh) with bw * bh == pixels and bw | w: bw is the largest power of two that divides w (capped
   at ``pixels``). bh need NOT divide h: the last tile row of an image is partial — TMA zero-fills the

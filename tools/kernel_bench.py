@@ -22,6 +22,7 @@ ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--only", default="")
 ap.add_argument("--no_flush", action="store_true")
 ap.add_argument("--no_stats", action="store_true")
+ap.add_argument("--mx_profile", action="store_true", help="stall attribution of the tap-shared MXFP8 kernel (CTA 0)")
 ap.add_argument("--layer", default="res", choices=["res", "stem"],
                 help="res: 3x3 256->256 @64x64 (default); stem: 7x7 3->64 @256x256 forward (narrow N = 64 kernel)")
 a = ap.parse_args()
@@ -83,6 +84,11 @@ mbw, mbh = nv.tile_shape(h, h)
 no.add_conv_mx(p, "mxfp8", x8.tmap_padded(mbw, mbh), sf8.tmap_padded(mbw, mbh, cbox=16, swizzle=0),
                no.taps_conv(3, c), c, w8, wsf, out_mx.view(), h, h, n, c, stats=0 if a.no_stats else stats.data_ptr())
 plans["mxfp8"] = (p, 2.0 * n * h * h * 9 * c * c)
+p = C.Plan()   # tap-shared CTA-pair variant
+no.add_conv_mx(p, "mxfp8_ts", x8.tmap_padded(8, 16), sf8.tmap_padded(8, 16, cbox=16, swizzle=0),
+               no.taps_conv(3, c), c, w8, wsf, out_mx.view(), h, h, n, c, stats=0 if a.no_stats else stats.data_ptr(),
+               tile=(8, 16), halo_maps=lambda w_, h_: (x8.tmap_padded(w_, h_), sf8.tmap_padded(w_, h_, cbox=16, swizzle=0)))
+plans["mxfp8_ts"] = (p, 2.0 * n * h * h * 9 * c * c)
 P = h + 2
 rows = n * P * P
 p = C.Plan()
@@ -121,6 +127,24 @@ for name, (plan, flops) in plans.items():
   res[name] = {"ms_median": ms, "ms_min": ts[0], "tflops": tf, "frac_of_measured_bf16_peak": tf / peak}
   print(f"{name:6s} images={n} median {ms * 1e3:8.1f} us  {tf:7.1f} TFLOP/s  "
         f"{100 * tf / peak:5.1f}% of measured cuBLAS bf16 peak ({peak:.0f})")
+if a.mx_profile and "mxfp8_ts" in plans:
+  prof = torch.zeros(16 + 5 * 40, dtype=torch.int64, device="cuda")
+  C.set_mx_profile(prof.data_ptr())
+  plans["mxfp8_ts"][0].run(0, -1, s, False)
+  torch.cuda.synchronize()
+  C.set_mx_profile(0)
+  v = prof.tolist()
+  names = ["producer total", "  wait a_empty", "  wait b_empty", "mma total", "  wait tmem_empty", "  wait a_full",
+           "  wait b_full", "  wait sf_bar", "scale warp total", "  wait sfa_full", "  wait sfb_full", "epilogue warp total",
+           "  wait tmem_full", "mma: 4 x tcgen05.mma", "mma: tcgen05.commit", "mma: elect..syncwarp block"]
+  print("stall attribution, CTA 0 (cycles):")
+  for nm, x in zip(names, v):
+    print(f"  {nm:24s} {x:10d}")
+  print("MMA warp time line (cycles since role start): stage start | b_full seen | sf_bar seen | MMAs issued | stage end")
+  for i in range(40):
+    row = v[16 + 5 * i:21 + 5 * i]
+    if any(row):
+      print("  stage %2d: " % i + " ".join(f"{x:8d}" for x in row))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump({"shape": f"3x3 conv 256->256 @64x64 x{n} images", "l2_flush": not a.no_flush, "results": res},
           open("gpurun_out/kernel_bench.json", "w"), indent=1)
