@@ -39,6 +39,6 @@ def test_weight_scale_order():
   sb = torch.arange(cout * taps * cin // 32, dtype=torch.int64).reshape(cout, taps * cin // 32)
   flat = mxfp8.weight_scale_order(sb, taps, cin)
   for n, tap, cb, k in [(0, 0, 0, 0), (37, 4, 1, 2), (200, 8, 0, 3), (255, 8, 1, 3)]:
-    chunk = ((n // 128) * taps + tap) * (cin // 128) + cb
+    chunk = ((n // 128) * (cin // 128) + cb) * taps + tap
     pos = chunk * 512 + (n % 32) * 16 + ((n % 128) // 32) * 4 + k
     assert flat[pos].item() == sb[n, tap * (cin // 32) + cb * 4 + k].item()

@@ -158,7 +158,7 @@ conv_gemm_mx_kernel(const __grid_constant__ ConvGemmMxParams q, int num_images, 
             tma_load_2d(sb + 64 * 128, &p.tmB, &full_bar[s], tap.bk + cb * 128, nt * kN + 64);   // two halves
             tma_load_4d(sfa, &q.tmSFA, &full_bar[s], 0, w0 + tap.dw, h0 + tap.dh, img + tap.dn);
             const int tk = tap.bk / (p.cin_blocks * 128);   // position of the tap in the weight matrix
-            bulk_load(sfb, sfb_tile + static_cast<long long>(tk * p.cin_blocks + cb) * Cfg::kSfbBytes,
+            bulk_load(sfb, sfb_tile + static_cast<long long>(cb * p.num_taps + tk) * Cfg::kSfbBytes,
                       Cfg::kSfbBytes, &full_bar[s]);
           }
           __syncwarp();
@@ -290,31 +290,42 @@ struct WaitClock {   // adds the cycles of its scope to a LOCAL counter (flushed
 };
 
 struct MxTsCfg {
+  static constexpr int kMaxTaps = 9;                       // 3x3 filters (forward and flat dgrad)
   static constexpr int kAStageBytes = 34 * 1024;           // activation halo tile (<= 272 rows x 128 B)
   static constexpr int kSfHaloBytes = 5 * 1024;            // scale records of the same rows (16 B each)
-  static constexpr int kAStride = kAStageBytes + kSfHaloBytes;
+  static constexpr int kSfbBytes = kN * 4;                 // weight scales of one (tap, 128-channel block)
+  static constexpr int kSfbAllBytes = 5 * 1024;            // ... of all taps of the block (<= 9 x 512 B)
+  static constexpr int kAStride = kAStageBytes;
   static constexpr int kAStages = 2;
+  // scale data (records of the halo pixels + weight scales of all taps) has its own, deeper ring fed by
+  // its own producer warp: the scale warpgroup needs ~2000 cycles per block, so it must run more than one
+  // block ahead of the MMAs (a block's MMAs take about as long)
+  static constexpr int kSfStride = kSfHaloBytes + kSfbAllBytes;
+  static constexpr int kSfStages = 3;
   static constexpr int kBBytes = 64 * 128;                 // this CTA's half of the 128-row weight tile
-  static constexpr int kSfbBytes = kN * 4;
-  // Taps per weight stage: the MMA warp's own instruction stream costs ~900 cycles per barrier round
-  // trip (stall attribution: profiles/r2/mx_probe.log) against 256 tensor cycles per tap, so one
-  // stage carries three taps (one wait / commit / scale hand-over for twelve MMAs).
+  // Taps per weight stage: the MMA warp's own instruction stream costs ~140 cycles per barrier wait and
+  // ~50 per tcgen05.mma (time line: profiles/r2/mx_timeline.txt) against 64 tensor cycles per MMA, so a
+  // stage carries three taps (one wait / one commit for twelve MMAs), and ALL scale factors of a
+  // 128-channel block (every tap) are staged into TMEM once, off the per-stage critical path.
   static constexpr int kTaps = 3;
-  static constexpr int kSfbOff = kTaps * kBBytes;          // weight scales follow the weight tiles
-  static constexpr int kBStride = 26 * 1024;               // kTaps * (kBBytes + kSfbBytes), 1024-aligned
-  static constexpr int kBStages = 4;
-  static constexpr int kSfCols = 8 * kTaps;                // TMEM columns per stage (SFA + SFB per tap)
+  static constexpr int kBStride = kTaps * kBBytes;
+  static constexpr int kBStages = 3;
+  static constexpr int kSfCols = 8 * kMaxTaps;             // TMEM columns per activation stage (SFA + SFB per tap)
   static constexpr int kAccCols = kN;
   static constexpr int kSfCol0 = 2 * kAccCols;
   static constexpr int kTmemCols = 512;
-  static constexpr int kStagingBytes = EpiCfg<kN>::kStagingBytes;
-  static constexpr int kRedBytes = EpiCfg<kN>::kRedBytes;
-  static constexpr int kNumBars = 3 * kAStages + 4 * kBStages + 4;
+  // two epilogue warpgroups, 64 columns each: with one, draining a 128 x 128 tile (~7000 cycles) takes
+  // longer than its MMAs (~5200) and the issue warp waits for a free accumulator
+  static constexpr int kHalfN = kN / 2;
+  static constexpr int kStagingBytes = 2 * EpiCfg<kHalfN>::kStagingBytes;
+  static constexpr int kRedBytes = 2 * EpiCfg<kHalfN>::kRedBytes;
+  static constexpr int kNumBars = 2 * kAStages + 3 * kSfStages + 2 * kBStages + 4;
   static constexpr int kBarrierBytes = kNumBars * 8 + 16;
-  static constexpr int kSmemBytes = kAStages * kAStride + kBStages * kBStride + kStagingBytes + kRedBytes +
-                                    kBarrierBytes + 1024;
-  static_assert(kTaps * (kBBytes + kSfbBytes) <= kBStride && kAStride % 1024 == 0, "stage layout");
-  static_assert(kSfCol0 + kSfCols * kBStages <= kTmemCols, "TMEM budget");
+  static constexpr int kSmemBytes = kAStages * kAStride + kSfStages * kSfStride + kBStages * kBStride + kStagingBytes +
+                                    kRedBytes + kBarrierBytes + 1024;
+  static_assert(kAStride % 1024 == 0 && kBStride % 1024 == 0 && kSfStride % 1024 == 0 &&
+                kMaxTaps * kSfbBytes <= kSfbAllBytes, "stage layout");
+  static_assert(kSfCol0 + kSfCols * kSfStages <= kTmemCols, "TMEM budget");
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
@@ -327,7 +338,8 @@ __device__ __forceinline__ void umma_mxf8_2sm(uint32_t tmem_d, uint64_t desc_a, 
       : "memory");
 }
 
-__global__ void __launch_bounds__(384, 1)
+template <bool PROF>
+__global__ void __launch_bounds__(512, 1)
 conv_gemm_mx_ts_kernel(const __grid_constant__ ConvGemmMxParams q, int num_images, int dbg) {
   using Cfg = MxTsCfg;
   const ConvGemmParams& p = q.g;
@@ -336,16 +348,17 @@ conv_gemm_mx_ts_kernel(const __grid_constant__ ConvGemmMxParams q, int num_image
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* a_ring = smem;
   uint8_t* b_ring = smem + Cfg::kAStages * Cfg::kAStride;
-  uint8_t* stage_buf = b_ring + Cfg::kBStages * Cfg::kBStride;
+  uint8_t* sf_ring = b_ring + Cfg::kBStages * Cfg::kBStride;
+  uint8_t* stage_buf = sf_ring + Cfg::kSfStages * Cfg::kSfStride;
   float* red = reinterpret_cast<float*>(stage_buf + Cfg::kStagingBytes);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(stage_buf + Cfg::kStagingBytes + Cfg::kRedBytes);
   uint64_t* a_empty = a_full + Cfg::kAStages;
-  uint64_t* sfa_full = a_empty + Cfg::kAStages;          // local: this CTA's scale-record halo landed
-  uint64_t* b_full = sfa_full + Cfg::kAStages;
+  uint64_t* sfd_full = a_empty + Cfg::kAStages;          // local: this CTA's scale records + weight scales landed
+  uint64_t* sf_empty = sfd_full + Cfg::kSfStages;        // multicast commit: the block's MMAs retired
+  uint64_t* sf_bar = sf_empty + Cfg::kSfStages;          // leader: both CTAs' scales of the block are in TMEM
+  uint64_t* b_full = sf_bar + Cfg::kSfStages;
   uint64_t* b_empty = b_full + Cfg::kBStages;
-  uint64_t* sfb_full = b_empty + Cfg::kBStages;          // local: this CTA's weight-scale chunk landed
-  uint64_t* sf_bar = sfb_full + Cfg::kBStages;           // leader: both CTAs' scales are in TMEM
-  uint64_t* tmem_full_bar = sf_bar + Cfg::kBStages;      // [2]
+  uint64_t* tmem_full_bar = b_empty + Cfg::kBStages;     // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;          // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
@@ -360,14 +373,16 @@ conv_gemm_mx_ts_kernel(const __grid_constant__ ConvGemmMxParams q, int num_image
   const int m_pairs = (m_tiles + 1) >> 1;
   const int n_tiles = p.cout / kN;
   const int total_pairs = m_pairs * n_tiles;
-  const int kb_per_tile = p.num_taps * p.cin_blocks;
+  const int num_taps = p.num_taps;
   const TapShare ts = p.ts;
-  // first halo row of every tap, and the position of its weights / weight scales
-  __shared__ uint32_t tap_row[kMaxTaps];
-  __shared__ int tap_bk[kMaxTaps];
-  if (threadIdx.x < p.num_taps) {
+  // first halo row of every tap, and the K offset of its weights
+  __shared__ uint32_t tap_row[Cfg::kMaxTaps];
+  __shared__ int tap_bk[Cfg::kMaxTaps];
+  __shared__ uint32_t tap_col[Cfg::kMaxTaps];   // first scale column of the tap: 8 x its position in the weight matrix
+  if (threadIdx.x < num_taps) {
     const Tap tap = p.taps[threadIdx.x];
     tap_bk[threadIdx.x] = tap.bk;
+    tap_col[threadIdx.x] = 8u * static_cast<uint32_t>(tap.bk / (p.cin_blocks * 128));
     tap_row[threadIdx.x] = static_cast<uint32_t>((tap.dh - ts.origin_dh) * ts.pitch + (tap.dw - ts.origin_dw));
   }
 
@@ -377,19 +392,21 @@ conv_gemm_mx_ts_kernel(const __grid_constant__ ConvGemmMxParams q, int num_image
     tma_prefetch_desc(&q.tmSFTS);
   } else if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kAStages; ++s) {
-      mbar_init(&a_full[s], 2);
-      mbar_init(&a_empty[s], 1);
-      mbar_init(&sfa_full[s], 1);
+      mbar_init(&a_full[s], 2);            // one arrival per CTA of the pair
+      mbar_init(&a_empty[s], 1);           // multicast commit from the leader's MMA thread
+    }
+    for (int s = 0; s < Cfg::kSfStages; ++s) {
+      mbar_init(&sfd_full[s], 1);
+      mbar_init(&sf_empty[s], 1);
+      mbar_init(&sf_bar[s], 8);            // 4 scale warps x 2 CTAs
     }
     for (int s = 0; s < Cfg::kBStages; ++s) {
       mbar_init(&b_full[s], 2);
       mbar_init(&b_empty[s], 1);
-      mbar_init(&sfb_full[s], 1);
-      mbar_init(&sf_bar[s], 8);            // 4 scale warps x 2 CTAs
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 256);  // 128 epilogue threads x 2 CTAs
+      mbar_init(&tmem_empty_bar[a], 512);  // 256 epilogue threads x 2 CTAs
     }
     fence_barrier_init();
   }
@@ -411,8 +428,9 @@ conv_gemm_mx_ts_kernel(const __grid_constant__ ConvGemmMxParams q, int num_image
     h0 = th * p.bh;
   };
   const uint32_t sf_box_bytes = static_cast<uint32_t>(ts.box_bytes) / 128u * kMxSfRecord;
+  // stall attribution (PROF only): per-role cycle counters flushed at the end + a time line of the MMA warp
   unsigned long long* prof_out = g_mx_prof;
-  const bool prof_on = prof_out != nullptr && blockIdx.x == 0 && lane == 0 &&
+  const bool prof_on = PROF && prof_out != nullptr && blockIdx.x == 0 && lane == 0 &&
                        (warp == 0 || warp == 1 || warp == 8 || warp == 4);
   long long prof[16];
 #pragma unroll
@@ -425,44 +443,55 @@ conv_gemm_mx_ts_kernel(const __grid_constant__ ConvGemmMxParams q, int num_image
     for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
       int mt, nt, img, h0, w0;
       decode(pt, mt, nt, img, h0, w0);
-      const uint8_t* sfb_tile = q.sfb + static_cast<long long>(nt) * kb_per_tile * Cfg::kSfbBytes;
       for (int cb = 0; cb < p.cin_blocks; ++cb, ++ita) {
         const int sa = ita % Cfg::kAStages;
         { WaitClock wc(prof, 1, prof_on); mbar_wait(&a_empty[sa], ((ita / Cfg::kAStages) & 1) ^ 1); }
         uint8_t* abuf = a_ring + sa * Cfg::kAStride;
-        uint8_t* sfbuf = abuf + Cfg::kAStageBytes;
         if (elect_one()) {
           if (rank == 0) mbar_arrive_expect_tx(&a_full[sa], 2 * ts.nbox * ts.box_bytes);
-          mbar_arrive_expect_tx(&sfa_full[sa], ts.nbox * sf_box_bytes);
-          for (int b = 0; b < ts.nbox; ++b) {
+          for (int b = 0; b < ts.nbox; ++b)
             tma_load_4d_2sm(abuf + b * ts.box_bytes, &p.tmTS, &a_full[sa], cb * 128,
                             w0 + ts.origin_dw + b * ts.box_step, h0 + ts.origin_dh, img);
-            tma_load_4d(sfbuf + b * sf_box_bytes, &q.tmSFTS, &sfa_full[sa], 0,
-                        w0 + ts.origin_dw + b * ts.box_step, h0 + ts.origin_dh, img);
-          }
           if (rank != 0) mbar_arrive_cluster(&a_full[sa], 0);
         }
         __syncwarp();
-        for (int t = 0; t < p.num_taps; t += Cfg::kTaps, ++itb) {
-          const int nk = min(Cfg::kTaps, p.num_taps - t);
+        for (int t = 0; t < num_taps; t += Cfg::kTaps, ++itb) {
+          const int nk = min(Cfg::kTaps, num_taps - t);
           const int sb = itb % Cfg::kBStages;
           { WaitClock wc(prof, 2, prof_on); mbar_wait(&b_empty[sb], ((itb / Cfg::kBStages) & 1) ^ 1); }
           uint8_t* bbuf = b_ring + sb * Cfg::kBStride;
           if (elect_one()) {
             if (rank == 0) mbar_arrive_expect_tx(&b_full[sb], 2 * nk * Cfg::kBBytes);
-            mbar_arrive_expect_tx(&sfb_full[sb], nk * Cfg::kSfbBytes);
-            for (int j = 0; j < nk; ++j) {
-              const int bk = tap_bk[t + j];
-              tma_load_2d_2sm(bbuf + j * Cfg::kBBytes, &p.tmB, &b_full[sb], bk + cb * 128, nt * kN + rank * 64);
-              const int tk = bk / (p.cin_blocks * 128);
-              bulk_load(bbuf + Cfg::kSfbOff + j * Cfg::kSfbBytes,
-                        sfb_tile + static_cast<long long>(tk * p.cin_blocks + cb) * Cfg::kSfbBytes, Cfg::kSfbBytes,
-                        &sfb_full[sb]);
-            }
+            for (int j = 0; j < nk; ++j)
+              tma_load_2d_2sm(bbuf + j * Cfg::kBBytes, &p.tmB, &b_full[sb], tap_bk[t + j] + cb * 128,
+                              nt * kN + rank * 64);
             if (rank != 0) mbar_arrive_cluster(&b_full[sb], 0);
           }
           __syncwarp();
         }
+      }
+    }
+  } else if (warp == 3) {
+    // ===================== scale-data producer (both CTAs, own barriers) =====================
+    uint32_t its = 0;
+    for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
+      int mt, nt, img, h0, w0;
+      decode(pt, mt, nt, img, h0, w0);
+      for (int cb = 0; cb < p.cin_blocks; ++cb, ++its) {
+        const int ss = its % Cfg::kSfStages;
+        mbar_wait(&sf_empty[ss], ((its / Cfg::kSfStages) & 1) ^ 1);
+        uint8_t* sbuf = sf_ring + ss * Cfg::kSfStride;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&sfd_full[ss], ts.nbox * sf_box_bytes + num_taps * Cfg::kSfbBytes);
+          for (int b = 0; b < ts.nbox; ++b)
+            tma_load_4d(sbuf + b * sf_box_bytes, &q.tmSFTS, &sfd_full[ss], 0, w0 + ts.origin_dw + b * ts.box_step,
+                        h0 + ts.origin_dh, img);
+          // weight scales of every tap of this (tile, channel block): contiguous, in weight-matrix tap order
+          bulk_load(sbuf + Cfg::kSfHaloBytes,
+                    q.sfb + (static_cast<long long>(nt) * p.cin_blocks + cb) * num_taps * Cfg::kSfbBytes,
+                    num_taps * Cfg::kSfbBytes, &sfd_full[ss]);
+        }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
@@ -471,6 +500,21 @@ conv_gemm_mx_ts_kernel(const __grid_constant__ ConvGemmMxParams q, int num_image
       constexpr uint32_t idesc = make_idesc_mxf8(256, kN);
       const uint32_t a_ring_u = smem_u32(a_ring), b_ring_u = smem_u32(b_ring);
       uint32_t ita = 0, itb = 0, tile_i = 0;
+      // results of non-blocking probes of the NEXT stage's / block's barriers, issued before the current
+      // stage's MMAs so that the ~140-cycle barrier latency is off the issue path
+      bool b_ready = false, a_ready = false, sf_ready = false;
+      // per-tap descriptor offset (halo row x 128 B, in the descriptor's 16-byte units) and scale columns,
+      // kept in registers: the issue loop below is fully unrolled, so there is no load -> address -> R2UR
+      // chain in front of every tap's first MMA
+      uint32_t t_enc[Cfg::kMaxTaps], t_col[Cfg::kMaxTaps];
+#pragma unroll
+      for (int i = 0; i < Cfg::kMaxTaps; ++i) {
+        t_enc[i] = i < num_taps ? tap_row[i] * 8u : 0u;
+        t_col[i] = i < num_taps ? tap_col[i] : 0u;
+      }
+      // high word of the activation descriptor (SWIZZLE_128B, version 1, stride between 8-row groups)
+      const uint32_t da_hi = ((static_cast<uint32_t>(ts.sbo) >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+      constexpr uint32_t db_hi = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
       for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++tile_i) {
         const uint32_t acc = tile_i & 1;
         { WaitClock wc(prof, 4, prof_on); mbar_wait(&tmem_empty_bar[acc], ((tile_i >> 1) & 1) ^ 1); }
@@ -479,35 +523,51 @@ conv_gemm_mx_ts_kernel(const __grid_constant__ ConvGemmMxParams q, int num_image
         uint32_t accumulate = 0;
         for (int cb = 0; cb < p.cin_blocks; ++cb, ++ita) {
           const int sa = ita % Cfg::kAStages;
-          { WaitClock wc(prof, 5, prof_on); mbar_wait(&a_full[sa], (ita / Cfg::kAStages) & 1); }
+          const uint32_t pha = (ita / Cfg::kAStages) & 1;
+          const bool stamp_a = prof_on && ita < 14;   // block-boundary time line (slots 216 ..)
+          if (stamp_a) prof_out[216 + 4 * ita + 0] = clock64() - role_t0;
+          if (!a_ready) { WaitClock wc(prof, 5, prof_on); mbar_wait(&a_full[sa], pha); }
+          if (stamp_a) prof_out[216 + 4 * ita + 1] = clock64() - role_t0;
+          const int ss = ita % Cfg::kSfStages;
+          if (!sf_ready) { WaitClock wc(prof, 7, prof_on); mbar_wait(&sf_bar[ss], (ita / Cfg::kSfStages) & 1); }
+          if (stamp_a) prof_out[216 + 4 * ita + 2] = clock64() - role_t0;
           tc_fence_after();
-          const uint32_t a_base = a_ring_u + sa * Cfg::kAStride;
-          for (int t = 0; t < p.num_taps; t += Cfg::kTaps, ++itb) {
-            const int nk = min(Cfg::kTaps, p.num_taps - t);
+          const uint32_t a_enc = ((a_ring_u + sa * Cfg::kAStride) >> 4) & 0x3FFFu;
+          const uint32_t tsf_a = tmem_base + Cfg::kSfCol0 + Cfg::kSfCols * ss;
+#pragma unroll
+          for (int st = 0; st < Cfg::kMaxTaps / Cfg::kTaps; ++st) {
+            const int t = st * Cfg::kTaps;
+            if (t >= num_taps) break;
+            const int nk = min(Cfg::kTaps, num_taps - t);
             const int sb = itb % Cfg::kBStages;
-            const uint32_t phb = (itb / Cfg::kBStages) & 1;
             const bool stamp = prof_on && itb < 40;     // time line of the first 40 stages (slots 16 ..)
             if (stamp) prof_out[16 + 5 * itb + 0] = clock64() - role_t0;
-            { WaitClock wc(prof, 6, prof_on); mbar_wait(&b_full[sb], phb); }
+            if (!b_ready) { WaitClock wc(prof, 6, prof_on); mbar_wait(&b_full[sb], (itb / Cfg::kBStages) & 1); }
             if (stamp) prof_out[16 + 5 * itb + 1] = clock64() - role_t0;
-            { WaitClock wc(prof, 7, prof_on); mbar_wait(&sf_bar[sb], phb); }
-            if (stamp) prof_out[16 + 5 * itb + 2] = clock64() - role_t0;
             tc_fence_after();
-            const uint32_t b_base = b_ring_u + sb * Cfg::kBStride;
-            const uint32_t tsf = tmem_base + Cfg::kSfCol0 + Cfg::kSfCols * sb;
+            {   // probe what the next iteration(s) will wait for
+              const uint32_t nb = itb + 1;
+              b_ready = mbar_test_wait(&b_full[nb % Cfg::kBStages], (nb / Cfg::kBStages) & 1);
+              if (t + Cfg::kTaps >= num_taps) {
+                const uint32_t na = ita + 1;
+                a_ready = mbar_test_wait(&a_full[na % Cfg::kAStages], (na / Cfg::kAStages) & 1);
+                sf_ready = mbar_test_wait(&sf_bar[na % Cfg::kSfStages], (na / Cfg::kSfStages) & 1);
+              }
+            }
+            const uint32_t b_enc = ((b_ring_u + sb * Cfg::kBStride) >> 4) & 0x3FFFu;
             if (elect_one()) {
               if (dbg != 2) {
                 WaitClock wc(prof, 13, prof_on);
 #pragma unroll
                 for (int j = 0; j < Cfg::kTaps; ++j) {
                   if (j < nk) {
-                    const uint64_t da = make_smem_desc_sw128(a_base + tap_row[t + j] * 128u, 0, static_cast<uint32_t>(ts.sbo));
-                    const uint64_t db = make_desc_kmajor(b_base + j * Cfg::kBBytes);
-                    const uint32_t tsfa = tsf + 8 * j, tsfb = tsfa + 4;
+                    const uint64_t da = (static_cast<uint64_t>(da_hi) << 32) | (a_enc + t_enc[t + j]);
+                    const uint64_t db = (static_cast<uint64_t>(db_hi) << 32) | (b_enc + j * (Cfg::kBBytes >> 4));
+                    const uint32_t tsfa = tsf_a + t_col[t + j], tsfb = tsfa + 4;
 #pragma unroll
-                    for (uint32_t k = 0; k < 4; ++k)
-                      umma_mxf8_2sm(tmem_d, da + k * 2, db + k * 2, idesc | (k << 29) | (k << 4), tsfa | (k << 30),
-                                    tsfb | (k << 30), (j == 0 && k == 0) ? accumulate : 1u);
+                    for (uint32_t k = 0; k < 4; ++k)   // K slice k: scale byte k, selected by the descriptor's id fields
+                      umma_mxf8_2sm(tmem_d, da + k * 2, db + k * 2, idesc | (k << 29) | (k << 4), tsfa, tsfb,
+                                    (j == 0 && k == 0) ? accumulate : 1u);
                   }
                 }
               }
@@ -520,61 +580,84 @@ conv_gemm_mx_ts_kernel(const __grid_constant__ ConvGemmMxParams q, int num_image
             __syncwarp();
             if (stamp) prof_out[16 + 5 * itb + 4] = clock64() - role_t0;
             accumulate = 1;
+            ++itb;
           }
-          if (elect_one()) umma_commit_2sm(&a_empty[sa]);
+          if (elect_one()) {
+            umma_commit_2sm(&a_empty[sa]);
+            umma_commit_2sm(&sf_empty[ss]);
+          }
           __syncwarp();
+          if (stamp_a) prof_out[216 + 4 * ita + 3] = clock64() - role_t0;
         }
         if (elect_one()) umma_commit_2sm(&tmem_full_bar[acc]);
         __syncwarp();
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 12) {
     // ===================== scale factors (both CTAs, own TMEM) =====================
+    // once per 128-channel block: the scales of EVERY tap go to TMEM (8 columns per tap: 4 SFA + 4 SFB),
+    // so nothing of this is on the MMA warp's per-stage path
     const int sp = warp - 8;
     const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(sp * 32) << 16) + Cfg::kSfCol0;
     const uint32_t group_rows = static_cast<uint32_t>(ts.sbo) / 128u;   // halo rows between 8-row groups of the tile
-    uint32_t rel[4];                        // halo row of tile pixel lane + 32 j, relative to the tap's first row
+    uint32_t rel[4];                        // halo row of tile pixel lane + 32 i, relative to the tap's first row
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t m = lane + 32 * j;
-      rel[j] = (m >> 3) * group_rows + (m & 7);
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t m = lane + 32 * i;
+      rel[i] = (m >> 3) * group_rows + (m & 7);
     }
-    uint32_t ita = 0, itb = 0;
+    // per-tap halo byte offset / scale column in registers (static indexing in the unrolled loops below)
+    uint32_t t_off[Cfg::kMaxTaps], t_col[Cfg::kMaxTaps];
+#pragma unroll
+    for (int i = 0; i < Cfg::kMaxTaps; ++i) {
+      t_off[i] = i < num_taps ? tap_row[i] * kMxSfRecord : 0u;
+      t_col[i] = i < num_taps ? tap_col[i] : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) rel[i] *= kMxSfRecord;
+    uint32_t ita = 0;
     for (int pt = cluster_id; pt < total_pairs; pt += num_clusters) {
       for (int cb = 0; cb < p.cin_blocks; ++cb, ++ita) {
-        const int sa = ita % Cfg::kAStages;
-        { WaitClock wc(prof, 9, prof_on); mbar_wait(&sfa_full[sa], (ita / Cfg::kAStages) & 1); }
-        const uint8_t* sfh = a_ring + sa * Cfg::kAStride + Cfg::kAStageBytes + (cb & 3) * 4;
-        for (int t = 0; t < p.num_taps; t += Cfg::kTaps, ++itb) {
-          const int nk = min(Cfg::kTaps, p.num_taps - t);
-          const int sb = itb % Cfg::kBStages;
-          { WaitClock wc(prof, 10, prof_on); mbar_wait(&sfb_full[sb], (itb / Cfg::kBStages) & 1); }
-          const uint8_t* sfb = b_ring + sb * Cfg::kBStride + Cfg::kSfbOff + lane * 16;
+        const int ss = ita % Cfg::kSfStages;
+        { WaitClock wc(prof, 9, prof_on); mbar_wait(&sfd_full[ss], (ita / Cfg::kSfStages) & 1); }
+        const uint8_t* sbuf = sf_ring + ss * Cfg::kSfStride;
+        const uint8_t* sfh = sbuf + (cb & 3) * 4;
+        const uint8_t* sfb = sbuf + Cfg::kSfHaloBytes + lane * 16;
+        const uint32_t col0 = lane_base + Cfg::kSfCols * ss;
+        // all loads first (independent, their latencies overlap), then the TMEM stores
+        uint32_t a[Cfg::kMaxTaps][4];
+        uint4 b[Cfg::kMaxTaps];
 #pragma unroll
-          for (int j = 0; j < Cfg::kTaps; ++j) {
-            if (j < nk) {
-              const uint32_t r0 = tap_row[t + j];
-              uint32_t a[4];
+        for (int t = 0; t < Cfg::kMaxTaps; ++t) {
+          if (t < num_taps) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const uint32_t*>(sfh + (r0 + rel[i]) * kMxSfRecord);
-              const uint4 b = *reinterpret_cast<const uint4*>(sfb + j * Cfg::kSfbBytes);
-              if (dbg != 5) {   // timing experiment 5: no TMEM stores
-                tmem_st_32x4(lane_base + Cfg::kSfCols * sb + 8 * j, a[0], a[1], a[2], a[3]);
-                tmem_st_32x4(lane_base + Cfg::kSfCols * sb + 8 * j + 4, b.x, b.y, b.z, b.w);
-              }
+            for (int i = 0; i < 4; ++i) a[t][i] = *reinterpret_cast<const uint32_t*>(sfh + t_off[t] + rel[i]);
+            b[t] = *reinterpret_cast<const uint4*>(sfb + t_col[t] * (Cfg::kSfbBytes / 8));
+          }
+        }
+        if (dbg != 5) {   // timing experiment 5: no TMEM stores
+#pragma unroll
+          for (int t = 0; t < Cfg::kMaxTaps; ++t) {
+            if (t < num_taps) {
+              tmem_st_32x4(col0 + t_col[t], a[t][0], a[t][1], a[t][2], a[t][3]);
+              tmem_st_32x4(col0 + t_col[t] + 4, b[t].x, b[t].y, b[t].z, b[t].w);
             }
           }
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(&sf_bar[sb], 0);   // one arrival per warp
         }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&sf_bar[ss], 0);   // one arrival per warp
       }
     }
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs, own TMEM lanes) =====================
-    const int e = threadIdx.x - 128;
-    const int ew = warp - 4;
+    // warps 4-7 and 12-15: one warpgroup per 64-column half of the tile
+    const int wg = warp >= 12 ? 1 : 0;
+    const int e = threadIdx.x & 127;
+    const int ew = warp & 3;
+    uint8_t* my_stage = stage_buf + wg * EpiCfg<Cfg::kHalfN>::kStagingBytes;
+    float* my_red = red + wg * (EpiCfg<Cfg::kHalfN>::kRedBytes / 4);
     uint32_t tile_i = 0;
     for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++tile_i) {
       int mt, nt, img, h0, w0;
@@ -582,10 +665,11 @@ conv_gemm_mx_ts_kernel(const __grid_constant__ ConvGemmMxParams q, int num_image
       const uint32_t acc = tile_i & 1;
       { WaitClock wc(prof, 12, prof_on && warp == 4); mbar_wait(&tmem_full_bar[acc], (tile_i >> 1) & 1); }
       tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * Cfg::kAccCols + (static_cast<uint32_t>(ew * 32) << 16);
+      const uint32_t taddr = tmem_base + acc * Cfg::kAccCols + wg * Cfg::kHalfN + (static_cast<uint32_t>(ew * 32) << 16);
       if (dbg == 1) { tc_fence_before(); mbar_arrive_cluster(&tmem_empty_bar[acc], 0); continue; }
-      conv_epilogue_tile<kN>(p, p.out, stage_buf, red, taddr, img, h0, w0, nt * kN, e, ew, lane, mt < m_tiles,
-                             [&]() { mbar_arrive_cluster(&tmem_empty_bar[acc], 0); }, dbg);
+      conv_epilogue_tile<Cfg::kHalfN>(p, p.out, my_stage, my_red, taddr, img, h0, w0, nt * kN + wg * Cfg::kHalfN, e, ew,
+                                      lane, mt < m_tiles, [&]() { mbar_arrive_cluster(&tmem_empty_bar[acc], 0); }, dbg,
+                                      1 + 2 * wg);
     }
   }
 
@@ -635,18 +719,22 @@ __global__ void __launch_bounds__(256) mx_weight_quant_kernel(const MxWeightQuan
   uint4* dst = reinterpret_cast<uint4*>(p.w8 + off);
   dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
   dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-  // scale position: [n / 128][tap][cin block of 128][n % 32][(n % 128) / 32][K slice]
+  // scale position: [n / 128][cin block of 128][tap][n % 32][(n % 128) / 32][K slice]
   const int per_tap = p.cin / kMxBlock;
   const int tap = kb / per_tap, r = kb - tap * per_tap;
   const int cin_blocks = p.cin / 128;
-  const long long chunk = (static_cast<long long>(n / 128) * p.taps + tap) * cin_blocks + (r >> 2);
+  const long long chunk = (static_cast<long long>(n / 128) * cin_blocks + (r >> 2)) * p.taps + tap;
   p.sfb[chunk * 512 + (n & 31) * 16 + ((n & 127) >> 5) * 4 + (r & 3)] = static_cast<uint8_t>(sb);
 }
 
 }  // namespace
 
 // device buffer of 16 counters (or 0 to switch the stall attribution off)
-void set_mx_profile(unsigned long long* buf) { cudaMemcpyToSymbol(g_mx_prof, &buf, sizeof(buf)); }
+static bool g_mx_prof_host = false;
+void set_mx_profile(unsigned long long* buf) {
+  cudaMemcpyToSymbol(g_mx_prof, &buf, sizeof(buf));
+  g_mx_prof_host = buf != nullptr;     // selects the instrumented instantiation of the kernel
+}
 
 void launch_conv_gemm_mx(const ConvGemmMxParams& p, int num_images, cudaStream_t stream) {
   static bool configured = false;
@@ -663,10 +751,12 @@ void launch_conv_gemm_mx(const ConvGemmMxParams& p, int num_images, cudaStream_t
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const TapShare& ts = p.g.ts;
   if (ts.enabled && use_2cta() && p.g.tiles_w * p.g.tiles_h * num_images >= 2 && ts.nbox >= 1 &&
+      p.g.num_taps <= MxTsCfg::kMaxTaps &&
       ts.nbox * ts.box_bytes <= MxTsCfg::kAStageBytes && (ts.nbox == 1 || ts.box_bytes % 1024 == 0)) {
     static bool configured_ts = false;
     if (!configured_ts) {
-      cudaFuncSetAttribute(conv_gemm_mx_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MxTsCfg::kSmemBytes);
+      cudaFuncSetAttribute(conv_gemm_mx_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MxTsCfg::kSmemBytes);
+      cudaFuncSetAttribute(conv_gemm_mx_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MxTsCfg::kSmemBytes);
       configured_ts = true;
     }
     const int m_tiles = p.g.tiles_w * p.g.tiles_h * num_images;
@@ -674,7 +764,7 @@ void launch_conv_gemm_mx(const ConvGemmMxParams& p, int num_images, cudaStream_t
     const int clusters = pairs < sms / 2 ? pairs : sms / 2;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * clusters);
-    cfg.blockDim = dim3(384);
+    cfg.blockDim = dim3(512);
     cfg.dynamicSmemBytes = MxTsCfg::kSmemBytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -684,7 +774,8 @@ void launch_conv_gemm_mx(const ConvGemmMxParams& p, int num_images, cudaStream_t
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaLaunchKernelEx(&cfg, conv_gemm_mx_ts_kernel, p, num_images, dbg_flag());
+    if (g_mx_prof_host) cudaLaunchKernelEx(&cfg, conv_gemm_mx_ts_kernel<true>, p, num_images, dbg_flag());
+    else cudaLaunchKernelEx(&cfg, conv_gemm_mx_ts_kernel<false>, p, num_images, dbg_flag());
     return;
   }
   const int total = p.g.tiles_w * p.g.tiles_h * num_images * (p.g.cout / kN);

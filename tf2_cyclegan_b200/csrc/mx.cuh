@@ -28,7 +28,7 @@ struct ConvGemmMxParams {
                         // g.ts / g.tmTS: optional halo box of the activations (tap-shared CTA-pair kernel)
   CUtensorMap tmSFA;    // activation scale records [.., 16] uint8, box {16, bw, bh, 1}, no swizzle
   CUtensorMap tmSFTS;   // g.ts.enabled: halo box of the scale records (same pixels as g.tmTS, 16-byte inner box)
-  const uint8_t* sfb;   // weight scales [n_tiles][taps][cin_blocks][32][4][4] (TMEM scale-factor order)
+  const uint8_t* sfb;   // weight scales [n_tiles][cin_blocks][taps][32][4][4] (TMEM scale-factor order)
 };
 void launch_conv_gemm_mx(const ConvGemmMxParams& p, int num_images, cudaStream_t stream);
 void set_mx_profile(unsigned long long* buf);   // stall attribution of the tap-shared kernel (tools/kernel_bench.py)

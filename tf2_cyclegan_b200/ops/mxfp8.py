@@ -50,8 +50,9 @@ def fake_quantize(t: torch.Tensor) -> torch.Tensor:
 
 def weight_scale_order(sb: torch.Tensor, taps: int, cin: int) -> torch.Tensor:
   """Scale bytes [cout, taps * cin / 32] of a [cout, taps * cin] weight matrix -> the flat order
-  the conv kernel fetches: [cout / 128][tap][cin / 128][cout % 32][(cout % 128) / 32][K slice of 4]."""
+  the conv kernels fetch: [cout / 128][cin / 128][tap][cout % 32][(cout % 128) / 32][K slice of 4]
+  (all taps of one 128-channel block are contiguous: one bulk copy per block)."""
   cout = sb.shape[0]
   assert cout % 128 == 0 and cin % 128 == 0 and sb.shape[1] == taps * cin // BLOCK
   v = sb.reshape(cout // 128, 4, 32, taps, cin // 128, 4)      # [nt, n1, n0, tap, cb, k]
-  return v.permute(0, 3, 4, 2, 1, 5).contiguous().reshape(-1)  # [nt, tap, cb, n0, n1, k]
+  return v.permute(0, 4, 3, 2, 1, 5).contiguous().reshape(-1)  # [nt, cb, tap, n0, n1, k]

@@ -128,7 +128,7 @@ for name, (plan, flops) in plans.items():
   print(f"{name:6s} images={n} median {ms * 1e3:8.1f} us  {tf:7.1f} TFLOP/s  "
         f"{100 * tf / peak:5.1f}% of measured cuBLAS bf16 peak ({peak:.0f})")
 if a.mx_profile and "mxfp8_ts" in plans:
-  prof = torch.zeros(16 + 5 * 40, dtype=torch.int64, device="cuda")
+  prof = torch.zeros(16 + 5 * 40 + 4 * 14, dtype=torch.int64, device="cuda")
   C.set_mx_profile(prof.data_ptr())
   plans["mxfp8_ts"][0].run(0, -1, s, False)
   torch.cuda.synchronize()
@@ -145,6 +145,11 @@ if a.mx_profile and "mxfp8_ts" in plans:
     row = v[16 + 5 * i:21 + 5 * i]
     if any(row):
       print("  stage %2d: " % i + " ".join(f"{x:8d}" for x in row))
+  print("channel-block boundaries: block start | a_full seen | sf_bar seen | block end (a_empty committed)")
+  for i in range(14):
+    row = v[216 + 4 * i:220 + 4 * i]
+    if any(row):
+      print("  block %2d: " % i + " ".join(f"{x:8d}" for x in row))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump({"shape": f"3x3 conv 256->256 @64x64 x{n} images", "l2_flush": not a.no_flush, "results": res},
           open("gpurun_out/kernel_bench.json", "w"), indent=1)
