@@ -22,7 +22,11 @@ struct TsCfg {
   static constexpr int BLOCK_N = 256;
   static constexpr int kAStageBytes = 34 * 1024;       // 272 rows x 128 B (flat: 2 boxes of 136 rows)
   static constexpr int kAStages = 2;
-  static constexpr int kBBytes = 128 * 128;            // this CTA's half of the weight tile
+  static constexpr int kBBytes = 128 * 128;            // this CTA's half of the weight tile (one tap)
+  // taps per weight stage. 2 (one wait / commit for eight MMAs, 3 stages) measured the same as 1 (6 stages):
+  // with 512 tensor cycles per tap this kernel is not bound by the issue warp, unlike its MXFP8 sibling
+  static constexpr int kTaps = 1;
+  static constexpr int kBStride = kTaps * kBBytes;
   static constexpr int kBStages = 6;
   static constexpr int kAccCols = BLOCK_N;
   static constexpr int kTmemCols = 2 * kAccCols;
@@ -31,7 +35,7 @@ struct TsCfg {
   static constexpr int kRedBytes = 2 * EpiCfg<kHalfN>::kRedBytes;
   static constexpr int kNumBars = 2 * kAStages + 2 * kBStages + 4;
   static constexpr int kBarrierBytes = kNumBars * 8 + 16;
-  static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBBytes + kStagingBytes +
+  static constexpr int kSmemBytes = kAStages * kAStageBytes + kBStages * kBStride + kStagingBytes +
                                     kRedBytes + kBarrierBytes + 1024;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
@@ -46,7 +50,7 @@ conv_gemm_ts_kernel(const __grid_constant__ ConvGemmParams p, int num_images, in
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* a_ring = smem;
   uint8_t* b_ring = smem + Cfg::kAStages * Cfg::kAStageBytes;
-  uint8_t* stage_buf = b_ring + Cfg::kBStages * Cfg::kBBytes;
+  uint8_t* stage_buf = b_ring + Cfg::kBStages * Cfg::kBStride;
   float* red = reinterpret_cast<float*>(stage_buf + Cfg::kStagingBytes);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(stage_buf + Cfg::kStagingBytes + Cfg::kRedBytes);
   uint64_t* a_empty = a_full + Cfg::kAStages;
@@ -138,23 +142,27 @@ conv_gemm_ts_kernel(const __grid_constant__ ConvGemmParams p, int num_images, in
             if (rank != 0) mbar_arrive_cluster(&a_full[sa], 0);
           }
           __syncwarp();
-          for (int t = 0; t < p.num_taps; ++t, ++itb) {
+          for (int t = 0; t < p.num_taps; t += Cfg::kTaps, ++itb) {
+            const int nk = min(Cfg::kTaps, p.num_taps - t);
             const int sb = itb % Cfg::kBStages;
             mbar_wait(&b_empty[sb], ((itb / Cfg::kBStages) & 1) ^ 1);
-            uint8_t* bbuf = b_ring + sb * Cfg::kBBytes;
-            const int bk = tap_bk[t];
+            uint8_t* bbuf = b_ring + sb * Cfg::kBStride;
             if (elect_one()) {
               if (dbg == 3) {
                 if (rank == 0) mbar_arrive(&b_full[sb]);
               } else {
-              if (rank == 0) mbar_arrive_expect_tx(&b_full[sb], 2 * Cfg::kBBytes);
-              if constexpr (!B_MN) {
-                tma_load_2d_2sm(bbuf, &p.tmB, &b_full[sb], bk + cb * 64, n0 + rank * 128);
-              } else {
+              if (rank == 0) mbar_arrive_expect_tx(&b_full[sb], 2 * nk * Cfg::kBBytes);
+              for (int j = 0; j < nk; ++j) {
+                const int bk = tap_bk[t + j];
+                uint8_t* bj = bbuf + j * Cfg::kBBytes;
+                if constexpr (!B_MN) {
+                  tma_load_2d_2sm(bj, &p.tmB, &b_full[sb], bk + cb * 64, n0 + rank * 128);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
-                  tma_load_2d_2sm(bbuf + j * (64 * 128), &p.tmB, &b_full[sb],
-                                  bk + n0 + rank * 128 + j * 64, cb * 64);
+                  for (int jj = 0; jj < 2; ++jj)
+                    tma_load_2d_2sm(bj + jj * (64 * 128), &p.tmB, &b_full[sb],
+                                    bk + n0 + rank * 128 + jj * 64, cb * 64);
+                }
               }
               }
               if (rank != 0) mbar_arrive_cluster(&b_full[sb], 0);
@@ -171,6 +179,16 @@ conv_gemm_ts_kernel(const __grid_constant__ ConvGemmParams p, int num_images, in
       constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N, 0, B_MN ? 1 : 0);
       const uint32_t a_ring_u = smem_u32(a_ring), b_ring_u = smem_u32(b_ring);
       uint32_t ita = 0, itb = 0, tile_i = 0;
+      // The issue loop is latency-bound on its own instruction stream (measured on the MXFP8 sibling of this
+      // kernel, profiles/r2/mx_timeline.txt: ~140 cycles per barrier wait even when the barrier is complete,
+      // ~60 per MMA when every tap starts with a load -> address -> R2UR chain). So: the next stage's / block's
+      // barriers are probed (non-blocking) BEFORE the current MMAs are issued, the next tap's halo offset is
+      // loaded one iteration ahead, and descriptors are built as (constant high word, 14-bit address field).
+      bool b_ready = false, a_ready = false;
+      const uint32_t da_hi = ((static_cast<uint32_t>(ts.sbo) >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+      constexpr uint32_t db_hi = ((1024u >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+      constexpr uint32_t db_lbo = B_MN ? ((64u * 128u) >> 4) << 16 : 0u;     // MN-major: stride between 64-wide atoms
+      uint32_t off_next = tap_off[0] >> 4;
       for (int pt = cluster_id; pt < total_pairs; pt += num_clusters, ++tile_i) {
         const uint32_t acc = tile_i & 1;
         mbar_wait(&tmem_empty_bar[acc], ((tile_i >> 1) & 1) ^ 1);
@@ -179,23 +197,40 @@ conv_gemm_ts_kernel(const __grid_constant__ ConvGemmParams p, int num_images, in
         uint32_t accumulate = 0;
         for (int cb = 0; cb < p.cin_blocks; ++cb, ++ita) {
           const int sa = ita % Cfg::kAStages;
-          mbar_wait(&a_full[sa], (ita / Cfg::kAStages) & 1);
+          if (!a_ready) mbar_wait(&a_full[sa], (ita / Cfg::kAStages) & 1);
           tc_fence_after();
-          const uint32_t a_base = a_ring_u + sa * Cfg::kAStageBytes;
-          for (int t = 0; t < p.num_taps; ++t, ++itb) {
+          const uint32_t a_enc = ((a_ring_u + sa * Cfg::kAStageBytes) >> 4) & 0x3FFFu;
+          for (int t = 0; t < p.num_taps; t += Cfg::kTaps, ++itb) {
+            const int nk = min(Cfg::kTaps, p.num_taps - t);
             const int sb = itb % Cfg::kBStages;
-            mbar_wait(&b_full[sb], (itb / Cfg::kBStages) & 1);
+            const uint32_t off0 = off_next;
+            const uint32_t off1 = tap_off[t + 1 < p.num_taps ? t + 1 : 0] >> 4;
+            off_next = tap_off[t + Cfg::kTaps < p.num_taps ? t + Cfg::kTaps : 0] >> 4;
+            if (!b_ready) mbar_wait(&b_full[sb], (itb / Cfg::kBStages) & 1);
             tc_fence_after();
-            const uint64_t da = make_smem_desc_sw128(a_base + tap_off[t], 0, static_cast<uint32_t>(ts.sbo));
-            const uint32_t sbp = b_ring_u + sb * Cfg::kBBytes;
-            const uint64_t db = B_MN ? make_desc_mnmajor(sbp, 64) : make_desc_kmajor(sbp);
+            {
+              const uint32_t nb = itb + 1;
+              b_ready = mbar_test_wait(&b_full[nb % Cfg::kBStages], (nb / Cfg::kBStages) & 1);
+              if (t + Cfg::kTaps >= p.num_taps) {
+                const uint32_t na = ita + 1;
+                a_ready = mbar_test_wait(&a_full[na % Cfg::kAStages], (na / Cfg::kAStages) & 1);
+              }
+            }
+            const uint32_t b_enc = ((b_ring_u + sb * Cfg::kBStride) >> 4) & 0x3FFFu;
             if (elect_one()) {
               if (dbg != 2) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16_2sm(tmem_d, da + static_cast<uint64_t>(k * 2),
-                                db + static_cast<uint64_t>(B_MN ? k * 128 : k * 2), idesc,
-                                (k == 0) ? accumulate : 1u);
+                for (int j = 0; j < Cfg::kTaps; ++j) {
+                  if (j < nk) {
+                    const uint64_t da = (static_cast<uint64_t>(da_hi) << 32) | (a_enc + (j == 0 ? off0 : off1));
+                    const uint64_t db = (static_cast<uint64_t>(db_hi) << 32) | ((b_enc + j * (Cfg::kBBytes >> 4)) | db_lbo);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      umma_bf16_2sm(tmem_d, da + static_cast<uint64_t>(k * 2),
+                                    db + static_cast<uint64_t>(B_MN ? k * 128 : k * 2), idesc,
+                                    (j == 0 && k == 0) ? accumulate : 1u);
+                  }
+                }
               }
               umma_commit_2sm(&b_empty[sb]);
             }
