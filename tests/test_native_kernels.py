@@ -431,7 +431,7 @@ def test_mxfp8_conv_and_quantisers(shared):
   plan = C.Plan()
   plan.add_in_apply("q", xb.view(), 0, 0, 0, 1.0, 1e-3, 0, nv.NULL_VIEW, dst.view(), 1, n, h, h, c,
                     dst8.view(), 0, 0, sf8.view())
-  plan.add_mx_weight_quant("wq", w2.data_ptr(), w8.data_ptr(), wsf.data_ptr(), cout, 9, c)
+  no.add_mx_weight_quant(plan, "wq", w2.data_ptr(), w8.data_ptr(), wsf.data_ptr(), cout, 9, c)
   bw, bh = (8, 16) if shared else nv.tile_shape(h, h)
   halo = (lambda w_, h_: (dst8.tmap_padded(w_, h_), sf8.tmap_padded(w_, h_, cbox=16, swizzle=0))) if shared else None
   no.add_conv_mx(plan, "conv.mx", dst8.tmap_padded(bw, bh), sf8.tmap_padded(bw, bh, cbox=16, swizzle=0),
@@ -457,6 +457,90 @@ def test_mxfp8_conv_and_quantisers(shared):
   assert rel_err(stats, s_ref) < 2e-3
   full = O.conv2d(xp, kern, 1, "valid")
   assert rel_l2(out.t, full) < 6e-2            # quantisation error of E4M3 operands with block scales
+
+
+@pytest.mark.parametrize("shared", [False, True])
+def test_mxfp8_flat_dgrad(shared):
+  """MXFP8 dgrad of the reflect-padded 3x3 conv in the zero-ringed flat domain: block-scaled dY (K = output
+  channels) x W^T from the strided weight quantiser. Oracle = autograd of the fp32 conv on the de-quantised
+  operands; ``shared``: one 272-row halo tile (two boxes) of bytes AND scale records per channel block."""
+  nv, no, O = _mods()
+  from tf2_cyclegan_b200.ops import mxfp8
+  C = nv.load()
+  torch.manual_seed(13)
+  n, h, c, cout = 2, 32, 256, 256
+  kmag = torch.exp2(torch.randint(-4, 5, (3, 3, c, cout // 32), device="cuda").float()).repeat_interleave(32, dim=3)
+  kern = bf(torch.randn(3, 3, c, cout, device="cuda") * 0.05 * kmag)
+  mag = torch.exp2(torch.randint(-6, 7, (n, h, h, cout // 32), device="cuda").float()).repeat_interleave(32, dim=-1)
+  dy = bf(torch.randn(n, h, h, cout, device="cuda") * mag)
+  # operands: dY twin (zero ring) from the reference quantiser, W^T from the kernel under test
+  q, sb = mxfp8.quantize(dy)
+  d8 = nv.Buf8(n, h, h, cout, halo=1)
+  dsf = nv.Buf8(n, h, h, 16, halo=1)
+  d8.interior().copy_(q)
+  dsf.interior()[..., :cout // 32].copy_(sb)
+  w2 = no.pack_conv_weight(kern).to(torch.bfloat16).contiguous()          # [cout, 9 * c]
+  w8t = torch.zeros(c, 9 * cout, dtype=torch.uint8, device="cuda")
+  wsft = torch.zeros(c * 9 * cout // 32, dtype=torch.uint8, device="cuda")
+  P = h + 2
+  rows = n * P * P
+  dxpad = nv.Buf(n, h, h, c, halo=1)
+  taps = [(0, 0, (1 - r) * P + (1 - s), 0, (r * 3 + s) * cout) for r in range(3) for s in range(3)]
+  plan = C.Plan()
+  no.add_mx_weight_quant(plan, "wtq", w2.data_ptr(), w8t.data_ptr(), wsft.data_ptr(), cout, 9, c, transposed=True)
+  halo = (lambda rb: (d8.tmap_flat(rows_box=rb), dsf.tmap_flat(rows_box=rb, cbox=16, swizzle=0))) if shared else None
+  no.add_conv_flat_mx(plan, "dgrad.mx", d8.tmap_flat(), dsf.tmap_flat(cbox=16, swizzle=0), taps, cout, w8t, wsft,
+                      dxpad.ptr(padded=True), c, rows, c, halo_maps=halo)
+  g = nv.Buf(n, h, h, c)
+  plan.add_in_bwd_reduce("fold", dxpad.view(), 1, nv.NULL_VIEW, nv.NULL_VIEW, 0, 0, 0, 1.0, 1e-3, 0,
+                         g.view(), 0, n, h, h, c)
+  run(plan)
+  # W^T[ci][tap * cout + co] = kern[r, s, ci, co]: quantised in blocks of 32 output channels
+  wt = kern.permute(2, 0, 1, 3).reshape(c, 9 * cout)
+  wq_ref, wsb_ref = mxfp8.quantize(wt)
+  assert torch.equal(w8t, wq_ref)
+  assert torch.equal(wsft, mxfp8.weight_scale_order(wsb_ref, 9, cout))
+  kq = mxfp8.dequantize(wq_ref, wsb_ref).reshape(c, 3, 3, cout).permute(1, 2, 0, 3).contiguous()
+  x = torch.zeros(n, h, h, c, device="cuda", requires_grad=True)
+  y = O.conv2d(O.reflect_pad(x, 1), kq, 1, "valid")
+  (gx,) = torch.autograd.grad(y, x, mxfp8.dequantize(q, sb))
+  assert rel_err(g.t, gx) < 1.5e-2 and rel_l2(g.t, gx) < 6e-3
+  x2 = torch.zeros(n, h, h, c, device="cuda", requires_grad=True)
+  (gfull,) = torch.autograd.grad(O.conv2d(O.reflect_pad(x2, 1), kern, 1, "valid"), x2, dy)
+  assert rel_l2(g.t, gfull) < 6e-2          # quantisation error of the E4M3 operands
+
+
+def test_mxfp8_twin_of_in_bwd_apply():
+  """The IN-backward-apply kernel's MXFP8 side output is the block quantisation of what it stores in bf16:
+  scale bytes within one step of the reference rule, de-quantised values within E4M3 rounding of dY."""
+  nv, no, O = _mods()
+  from tf2_cyclegan_b200.ops import mxfp8
+  C = nv.load()
+  torch.manual_seed(14)
+  n, h, c = 2, 32, 256
+  dyt = nv.Buf(n, h, h, c); dyt.t.copy_(torch.randn(n, h, h, c, device="cuda").to(torch.bfloat16))
+  raw = nv.Buf(n, h, h, c); raw.t.copy_((torch.randn(n, h, h, c, device="cuda") * 2 + 0.5).to(torch.bfloat16))
+  xr = raw.t.float()
+  stats = torch.stack([xr.sum((1, 2)), (xr * xr).sum((1, 2))], -1).contiguous()
+  bstats = torch.randn(n, c, 2, device="cuda") * 30
+  gamma = torch.rand(c, device="cuda") + 0.5
+  dY = nv.Buf(n, h, h, c, halo=1)
+  dY8 = nv.Buf8(n, h, h, c, halo=1)
+  dsf = nv.Buf8(n, h, h, 16, halo=1)
+  plan = C.Plan()
+  plan.add_in_bwd_apply("bwd", dyt.view(), raw.view(), stats.data_ptr(), bstats.data_ptr(), gamma.data_ptr(),
+                        1.0 / (h * h), 1e-3, dY.view(), 0, 0, n, h, h, c, dY8.view(), dsf.view())
+  run(plan)
+  ref = dY.interior().float()                                    # bf16 result of the same kernel
+  sb_ref = mxfp8.scale_bytes(ref.reshape(n, h, h, c // 32, 32).abs().amax(-1))
+  sb = dsf.interior()[..., :c // 32]
+  assert (sb.int() - sb_ref.int()).abs().max().item() <= 1      # fp32 vs bf16-rounded block maximum
+  back = mxfp8.dequantize(dY8.interior().contiguous(), sb.contiguous())
+  s = mxfp8.scale_values(sb).repeat_interleave(32, dim=-1)
+  bound = torch.maximum(ref.abs() * 2.0 ** -4, s * 2.0 ** -10) + ref.abs() * 2.0 ** -8   # E4M3 + bf16 rounding
+  assert ((back - ref).abs() <= bound * 1.001).all()
+  # the zero ring of the flat dgrad domain stays zero in both twins
+  assert dY8.t[:, 0].abs().max() == 0 and dsf.t[:, :, 0].abs().max() == 0
 
 
 @pytest.mark.parametrize("n,h,c,cout", [(2, 64, 256, 256), (3, 32, 64, 256), (1, 16, 128, 512)])

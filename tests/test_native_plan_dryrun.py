@@ -96,12 +96,17 @@ def test_mxfp8_plan_builds(monkeypatch):
   be = NativeBackend(build_specs(A(2)), 2, Strategy(device="cpu"), seed=1, image_size=128, local_batch=2,
                      dtype="mxfp8")
   sp = be.plan_for(2)
-  mx = [n for n in sp.names if n.endswith(".mxfp8")]
+  mx = [n for n in sp.names if n.endswith(".mxfp8") and ".fwd" in n]
   assert len(mx) == 16 and all(".res" in n for n in mx)
+  mxd = [n for n in sp.names if n.endswith(".mxfp8") and ".dgrad" in n]
+  bfd = [n for n in sp.names if ".res" in n and ".dgrad" in n and not n.endswith(".mxfp8")]
+  assert len(mxd) > 0 and not bfd            # every residual-block dgrad runs block-scaled too
   assert sum(n.endswith(".mx_w_quant") for n in sp.names) == 8      # 2 generators x 4 residual convs
+  assert sum(n.endswith(".mx_wt_quant") for n in sp.names) == 8     # ... and their dgrad operands W^T
   assert not any(n.endswith(".scales") or n.endswith(".w_amax") for n in sp.names)   # no scaling state
   ex = sp.ex["G"]
   assert set(ex.sf8) == set(ex.inp8) and all(b.c == 16 and b.halo == 1 for b in ex.sf8.values())
+  assert set(ex.dY8) == set(ex.dYsf) == set(ex.inp8) and all(b.halo == 1 for b in ex.dY8.values())
   st = be.state["G"]
   assert [t.numel() for t in st.w_sf] == [256 * 9 * 256 // 32] * 4
   assert be.extra_state() == {}

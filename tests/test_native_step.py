@@ -317,6 +317,39 @@ def test_mxfp8_forward_tracks_bf16():
   assert any(n.endswith(".mxfp8") for n in f.plan_for(2).names)
 
 
+def test_mxfp8_gradients_close_to_bf16():
+  """--dtype mxfp8 runs the residual-block forward AND dgrad convs block-scaled; the flat parameter gradients
+  of one step stay close to the bf16 path's (same weights, same batch)."""
+  from tf2_cyclegan_b200.engine.cyclegan import build_specs
+  from tf2_cyclegan_b200.engine.native_backend import NativeBackend, NETS
+  from tf2_cyclegan_b200.parallel.strategy import Strategy
+  st = Strategy(device="cuda")
+  specs = build_specs(A(2))
+  torch.manual_seed(3)
+  x = torch.rand(2, 128, 128, 3, device="cuda") * 2 - 1
+  y = torch.rand(2, 128, 128, 3, device="cuda") * 2 - 1
+  grads = {}
+  for dtype in ("bf16", "mxfp8"):
+    be = NativeBackend(specs, 2, st, seed=11, image_size=128, local_batch=2, use_graph=False, dtype=dtype)
+    sp = be.plan_for(2)
+    be._load_inputs(sp, x, y)
+    s = torch.cuda.current_stream().cuda_stream
+    pos, g = 0, {}
+    for n in sorted(NETS, key=lambda k: sp.marks[f"{k}_bwd_end"]):
+      sp.plan.run(pos, sp.marks[f"{n}_bwd_end"], s, True)
+      torch.cuda.synchronize()
+      g[n] = (be.state[n].g * be.state[n].mask.float()).clone()
+      pos = sp.marks[f"{n}_opt_end"]
+    grads[dtype] = g
+    if dtype == "mxfp8":
+      assert any(n.endswith(".mxfp8") and ".dgrad" in n for n in sp.names)
+  for n in NETS:
+    a, b = grads["bf16"][n], grads["mxfp8"][n]
+    err = ((a - b).norm() / a.norm().clamp_min(1e-12)).item()
+    print(f"mxfp8 vs bf16 gradient, network {n}: rel. L2 {err:.4f}")
+    assert b.isfinite().all() and err < (0.15 if n in ("G", "F") else 0.05), (n, err)
+
+
 def test_training_reduces_cycle_loss_on_fixed_batch():
   """40 native steps on one fixed batch: cycle / identity L1 terms must go down, stay finite."""
   from tf2_cyclegan_b200.engine.cyclegan import build_specs

@@ -685,28 +685,36 @@ conv_gemm_mx_ts_kernel(const __grid_constant__ ConvGemmMxParams q, int num_image
   if (warp == 2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
 }
 
-// one thread per (output channel, 32-element K block)
+// one thread per (row, 32-element K block)
 __global__ void __launch_bounds__(256) mx_weight_quant_kernel(const MxWeightQuantParams p) {
-  const int kblocks = p.taps * p.cin / kMxBlock;
+  const int per_tap = p.kdim / kMxBlock;
+  const int kblocks = p.taps * per_tap;
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= p.cout * kblocks) return;
+  if (idx >= p.rows * kblocks) return;
   const int n = idx / kblocks, kb = idx - n * kblocks;
-  const long long off = static_cast<long long>(n) * kblocks * kMxBlock + static_cast<long long>(kb) * kMxBlock;
-  const uint4* src = reinterpret_cast<const uint4*>(p.w + off);
+  const int tap = kb / per_tap, r = kb - tap * per_tap;
+  const __nv_bfloat16* src = p.w + n * p.s_row + tap * p.s_tap + static_cast<long long>(r) * kMxBlock * p.s_k;
   float v[32];
   float amax = 0.f;
+  if (p.s_k == 1) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint4 u = __ldg(src + i);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    for (int i = 0; i < 4; ++i) {
+      const uint4 u = __ldg(s4 + i);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = unpack_bf16x2(w[j]);
-      v[i * 8 + 2 * j] = f.x;
-      v[i * 8 + 2 * j + 1] = f.y;
-      amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_bf16x2(w[j]);
+        v[i * 8 + 2 * j] = f.x;
+        v[i * 8 + 2 * j + 1] = f.y;
+      }
     }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __bfloat162float(src[i * p.s_k]);
   }
+#pragma unroll
+  for (int i = 0; i < 32; ++i) amax = fmaxf(amax, fabsf(v[i]));
   const uint32_t sb = mx_scale_byte(amax);
   const float inv = mx_inv_scale(sb);
   uint32_t o[8];
@@ -716,14 +724,12 @@ __global__ void __launch_bounds__(256) mx_weight_quant_kernel(const MxWeightQuan
     const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(v[4 * j + 2] * inv, v[4 * j + 3] * inv), __NV_SATFINITE, __NV_E4M3);
     o[j] = lo | (hi << 16);
   }
-  uint4* dst = reinterpret_cast<uint4*>(p.w8 + off);
+  uint4* dst = reinterpret_cast<uint4*>(p.w8 + (static_cast<long long>(n) * kblocks + kb) * kMxBlock);
   dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
   dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-  // scale position: [n / 128][cin block of 128][tap][n % 32][(n % 128) / 32][K slice]
-  const int per_tap = p.cin / kMxBlock;
-  const int tap = kb / per_tap, r = kb - tap * per_tap;
-  const int cin_blocks = p.cin / 128;
-  const long long chunk = (static_cast<long long>(n / 128) * cin_blocks + (r >> 2)) * p.taps + tap;
+  // scale position: [n / 128][K block of 128][tap][n % 32][(n % 128) / 32][K slice]
+  const int k_blocks = p.kdim / 128;
+  const long long chunk = (static_cast<long long>(n / 128) * k_blocks + (r >> 2)) * p.taps + tap;
   p.sfb[chunk * 512 + (n & 31) * 16 + ((n & 127) >> 5) * 4 + (r & 3)] = static_cast<uint8_t>(sb);
 }
 
@@ -784,11 +790,11 @@ void launch_conv_gemm_mx(const ConvGemmMxParams& p, int num_images, cudaStream_t
 }
 
 void launch_mx_weight_quant(const MxWeightQuantParams& p, cudaStream_t stream) {
-  if (p.cin % 128 != 0 || p.cout % 128 != 0) {
-    fprintf(stderr, "launch_mx_weight_quant: cin and cout must be multiples of 128\n");
+  if (p.kdim % 128 != 0 || p.rows % 128 != 0) {
+    fprintf(stderr, "launch_mx_weight_quant: rows and K per tap must be multiples of 128\n");
     abort();
   }
-  const int total = p.cout * (p.taps * p.cin / kMxBlock);
+  const int total = p.rows * (p.taps * p.kdim / kMxBlock);
   mx_weight_quant_kernel<<<(total + 255) / 256, 256, 0, stream>>>(p);
 }
 

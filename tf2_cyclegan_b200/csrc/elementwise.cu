@@ -656,23 +656,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_apply_stream_kernel(cons
     stv(D, h, w, pk);
     uint2 pk8 = make_uint2(0u, 0u), sfrec = make_uint2(0u, 0u);
     if constexpr (MX) {
-      // block = 4 adjacent lanes of this pixel's warp; quantises the fp32 values (as the direct kernel does)
-      const float (&q)[8] = o;
-      float bmax = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) bmax = fmaxf(bmax, fabsf(q[j]));
-      bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, 1));
-      bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, 2));
-      const uint32_t sb = mx_scale_byte(bmax);
-      const float inv = mx_inv_scale(sb);
-      uint32_t o8[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        o8[j] = __nv_cvt_float2_to_fp8x2(make_float2(q[2 * j] * inv, q[2 * j + 1] * inv), __NV_SATFINITE, __NV_E4M3);
-        sfrec.x |= __shfl_sync(0xffffffffu, sb, 4 * j) << (8 * j);
-        sfrec.y |= __shfl_sync(0xffffffffu, sb, 16 + 4 * j) << (8 * j);
-      }
-      pk8 = make_uint2(o8[0] | (o8[1] << 16), o8[2] | (o8[3] << 16));
+      mx_quant_pixel(o, pk8, sfrec);   // this warp == this pixel (C == 256); quantises the fp32 values
       *reinterpret_cast<uint2*>(d8 + (h * d8sh + w * d8sw)) = pk8;
       if (lane0) *reinterpret_cast<uint2*>(sf + (h * sfsh + w * sfsw)) = sfrec;
     }
@@ -807,6 +791,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_bwd_reduce_stream_kernel
   }
 }
 
+template <bool MX>
 __global__ void __launch_bounds__(kStreamThreads, 2) in_bwd_apply_stream_kernel(const InBwdApplyParams p,
                                                                                int pix_per_block, uint32_t rcp_w) {
   extern __shared__ __align__(128) uint8_t ring[];
@@ -855,6 +840,18 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_bwd_apply_stream_kernel(
     }
   }
   const V32 DX = v32(p.dx, n, c);
+  uint8_t* d8 = nullptr;
+  uint8_t* sf = nullptr;
+  int d8sh = 0, d8sw = 0, sfsh = 0, sfsw = 0;
+  if constexpr (MX) {
+    d8 = reinterpret_cast<uint8_t*>(p.dx8.p) + static_cast<long long>(n) * p.dx8.sn + c;
+    d8sh = static_cast<int>(p.dx8.sh);
+    d8sw = static_cast<int>(p.dx8.sw);
+    sf = reinterpret_cast<uint8_t*>(p.sf8.p) + static_cast<long long>(n) * p.sf8.sn;
+    sfsh = static_cast<int>(p.sf8.sh);
+    sfsw = static_cast<int>(p.sf8.sw);
+  }
+  const bool lane0 = (threadIdx.x & 31) == 0;
   stream_run<NT, STAGES>(ring, views, g, c, ln, lanes, [&](int, int h, int w, const uint4 (&v)[NT]) {
     float d[8], x[8], o[8];
     unpack8(v[0], d);
@@ -862,6 +859,12 @@ __global__ void __launch_bounds__(kStreamThreads, 2) in_bwd_apply_stream_kernel(
 #pragma unroll
     for (int j = 0; j < 8; ++j) o[j] = fmaf(kA[j], d[j], fmaf(kB[j], x[j], kC[j]));
     stv(DX, h, w, pack8(o));
+    if constexpr (MX) {   // C == 256: this warp == this pixel
+      uint2 pk8, rec;
+      mx_quant_pixel(o, pk8, rec);
+      *reinterpret_cast<uint2*>(d8 + (h * d8sh + w * d8sw)) = pk8;
+      if (lane0) *reinterpret_cast<uint2*>(sf + (h * sfsh + w * sfsw)) = rec;
+    }
   });
 }
 
@@ -1350,13 +1353,20 @@ void launch_in_bwd_reduce(const InBwdReduceParams& p, cudaStream_t s) {
 void launch_in_bwd_apply(const InBwdApplyParams& p, cudaStream_t s) {
   const uint32_t rcp = rcp_for(p.H, p.W, p.C, "launch_in_bwd_apply");
   const int HW = p.H * p.W;
-  if (g_ew_stream && streamable(p.dy, p.C) && streamable(p.x, p.C)) {
+  const bool mx = p.sf8.p != nullptr;
+  if (mx && (p.dx8.p == nullptr || p.C != 256 || !streamable(p.dy, p.C) || !streamable(p.x, p.C))) {
+    fprintf(stderr, "launch_in_bwd_apply: the MXFP8 twin needs dx8, C == 256 and dense dy / x views\n");
+    abort();
+  }
+  if ((g_ew_stream || mx) && streamable(p.dy, p.C) && streamable(p.x, p.C)) {
     constexpr size_t smem = ring_bytes(2, 6);
-    static bool once = (stream_smem(in_bwd_apply_stream_kernel, smem), true);
+    static bool once = (stream_smem(in_bwd_apply_stream_kernel<false>, smem),
+                        stream_smem(in_bwd_apply_stream_kernel<true>, smem), true);
     (void)once;
     const int ppb = stream_ppb(HW, p.N, p.C);
     dim3 grid((HW + ppb - 1) / ppb, p.N);
-    in_bwd_apply_stream_kernel<<<grid, kStreamThreads, smem, s>>>(p, ppb, rcp);
+    if (mx) in_bwd_apply_stream_kernel<true><<<grid, kStreamThreads, smem, s>>>(p, ppb, rcp);
+    else in_bwd_apply_stream_kernel<false><<<grid, kStreamThreads, smem, s>>>(p, ppb, rcp);
     return;
   }
   const int lanes = kThreads / (p.C / 8);

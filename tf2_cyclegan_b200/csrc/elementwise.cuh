@@ -68,6 +68,9 @@ struct InBwdApplyParams {
   float* dgamma;        // fp32 grads, accumulated (+=)
   float* dbeta;
   int N, H, W, C;
+  // optional MXFP8 twin of dx for an MXFP8 dgrad (C == 256, streamed kernel): E4M3 bytes + 16-byte scale
+  // records per pixel, same geometry as dx (the zero ring of the flat dgrad domain stays zero)
+  View dx8, sf8;
 };
 void launch_in_bwd_apply(const InBwdApplyParams& p, cudaStream_t s);
 

@@ -350,8 +350,10 @@ class Plan {
     }
     return add(std::move(name), [p, num_images](cudaStream_t s) { launch_conv_gemm_mx(*p, num_images, s); });
   }
-  int add_mx_weight_quant(std::string name, uint64_t w, uint64_t w8, uint64_t sfb, int cout, int taps, int cin) {
-    MxWeightQuantParams p{P<const __nv_bfloat16>(w), P<uint8_t>(w8), P<uint8_t>(sfb), cout, taps, cin};
+  int add_mx_weight_quant(std::string name, uint64_t w, uint64_t w8, uint64_t sfb, int rows, int taps, int kdim,
+                          long long s_row, long long s_tap, long long s_k) {
+    MxWeightQuantParams p{P<const __nv_bfloat16>(w), P<uint8_t>(w8), P<uint8_t>(sfb), rows, taps, kdim,
+                          s_row, s_tap, s_k};
     return add(std::move(name), [p](cudaStream_t s) { launch_mx_weight_quant(p, s); });
   }
 
@@ -395,10 +397,11 @@ class Plan {
   }
   int add_in_bwd_apply(std::string name, ViewT dy, ViewT x, uint64_t stats, uint64_t bstats,
                        uint64_t gamma, float inv_count, float eps, ViewT dx, uint64_t dgamma,
-                       uint64_t dbeta, int N, int H, int W, int C) {
+                       uint64_t dbeta, int N, int H, int W, int C, ViewT dx8, ViewT sf8) {
     InBwdApplyParams p{view_from(dy), view_from(x), P<const float>(stats),
                        P<const float>(bstats), P<const float>(gamma), inv_count, eps,
-                       view_from(dx), P<float>(dgamma), P<float>(dbeta), N, H, W, C};
+                       view_from(dx), P<float>(dgamma), P<float>(dbeta), N, H, W, C,
+                       view_from(dx8), view_from(sf8)};
     return add(std::move(name), [p](cudaStream_t s) { launch_in_bwd_apply(p, s); });
   }
   int add_act_bwd(std::string name, ViewT g1, int fold1, ViewT g2, ViewT out, int act, ViewT dy,
@@ -591,7 +594,10 @@ PYBIND11_MODULE(_C, m) {
       .def("add_mx_weight_quant", &Plan::add_mx_weight_quant)
       .def("add_fp8_op", &Plan::add_fp8_op)
       .def("add_in_bwd_reduce", &Plan::add_in_bwd_reduce)
-      .def("add_in_bwd_apply", &Plan::add_in_bwd_apply)
+      .def("add_in_bwd_apply", &Plan::add_in_bwd_apply, py::arg("name"), py::arg("dy"), py::arg("x"), py::arg("stats"),
+           py::arg("bstats"), py::arg("gamma"), py::arg("inv_count"), py::arg("eps"), py::arg("dx"),
+           py::arg("dgamma"), py::arg("dbeta"), py::arg("N"), py::arg("H"), py::arg("W"), py::arg("C"),
+           py::arg("dx8") = ViewT{0, 0, 0, 0}, py::arg("sf8") = ViewT{0, 0, 0, 0})
       .def("add_act_bwd", &Plan::add_act_bwd)
       .def("add_img_prep", &Plan::add_img_prep)
       .def("add_l1_loss", &Plan::add_l1_loss)

@@ -65,9 +65,12 @@ class NetState:
     self.fp8_layers = [l for l in self.spec.layers if fp8_ok(l)]
     L = max(1, len(self.fp8_layers))
     self.w8 = torch.zeros(self.n, dtype=torch.uint8, device=dev)
-    # MX weight scales: one byte per (output channel, 32 K elements), per layer
-    self.w_sf = [torch.zeros(self.seg(l, "kernel").numel // 32 if mode == "mx" else 0, dtype=torch.uint8, device=dev)
-                 for l in self.fp8_layers]
+    # MX weight scales: one byte per (row, 32 K elements), per layer — of the forward operand [cout][taps * cin]
+    # and of the dgrad operand W^T [cin][taps * cout] (its own E4M3 copy: the blocks run over output channels)
+    nsf = [self.seg(l, "kernel").numel // 32 if mode == "mx" else 0 for l in self.fp8_layers]
+    self.w_sf = [torch.zeros(k, dtype=torch.uint8, device=dev) for k in nsf]
+    self.w_sft = [torch.zeros(k, dtype=torch.uint8, device=dev) for k in nsf]
+    self.w8t = torch.zeros(self.n if mode == "mx" else 0, dtype=torch.uint8, device=dev)
     self.act_amax = torch.zeros(L, device=dev)
     self.w_amax = torch.zeros(L, device=dev)
     self.act_scale = torch.ones(L, device=dev)
@@ -81,6 +84,11 @@ class NetState:
     s = self.seg(l, "kernel")
     return self.w8[s.offset:s.offset + s.numel].view(*s.shape)
 
+  def kernel_fp8_t(self, l: ConvLayer) -> torch.Tensor:
+    """MXFP8 dgrad operand W^T as [cin, taps * cout] E4M3 bytes."""
+    s = self.seg(l, "kernel")
+    return self.w8t[s.offset:s.offset + s.numel].view(l.cin, l.k * l.k * l.cout)
+
   def emit_fp8_refresh(self, plan, tag: str):
     """Start-of-step bookkeeping: weight amax -> scales (activations: previous step's amax) ->
     E4M3 weight copy. Reads the bf16 compute copy, which is complete on every rank."""
@@ -89,8 +97,11 @@ class NetState:
     if self.fp8_mode == "mx":
       for i, l in enumerate(self.fp8_layers):
         seg = self.seg(l, "kernel")
-        plan.add_mx_weight_quant(f"fp8.{tag}.{l.name}.mx_w_quant", self.wb.data_ptr() + 2 * seg.offset,
-                                 self.w8.data_ptr() + seg.offset, self.w_sf[i].data_ptr(), l.cout, l.k * l.k, l.cin)
+        taps, src = l.k * l.k, self.wb.data_ptr() + 2 * seg.offset
+        no.add_mx_weight_quant(plan, f"fp8.{tag}.{l.name}.mx_w_quant", src, self.w8.data_ptr() + seg.offset,
+                               self.w_sf[i].data_ptr(), l.cout, taps, l.cin)
+        no.add_mx_weight_quant(plan, f"fp8.{tag}.{l.name}.mx_wt_quant", src, self.w8t.data_ptr() + seg.offset,
+                               self.w_sft[i].data_ptr(), l.cout, taps, l.cin, transposed=True)
       return
     offs = [self.seg(l, "kernel").offset for l in self.fp8_layers]
     nums = [self.seg(l, "kernel").numel for l in self.fp8_layers]
@@ -217,6 +228,8 @@ class NetExec:
 
     # ---- backward buffers (allocated lazily by enable_backward)
     self.dY: List[Optional[Buf]] = [None] * L      # grad wrt conv output (zero ring for flat dgrad)
+    self.dY8: Dict[int, Buf8] = {}                 # MXFP8 twins of dY (residual-block convs, --dtype mxfp8)
+    self.dYsf: Dict[int, Buf8] = {}
     self.dyt: List[Optional[Buf]] = [None] * L     # g * act' scratch (doubles as the residual-sum gradient)
     self.gin: List[Optional[Buf]] = [None] * L     # grad wrt layer input, as produced by the layer's dgrad
     self.gout_final: Optional[Buf] = None          # grad wrt the network output (images / logits)
@@ -278,6 +291,10 @@ class NetExec:
       self.dY[j] = self._buf(f"dY{j}", nb, ho, wo, c_out, halo=halo, slack_rows=1 if c_out == 8 else 0)
       if l.norm:
         self.dyt[j] = self._buf(f"dyt{j}", nb, ho, wo, l.cout)
+      if self.mx and fp8_ok(l) and flat_dgrad and l.norm:
+        # MXFP8 twin of dY for the dgrad (written by the IN-backward-apply kernel): bytes + scale records
+        self.dY8[j] = self._buf(f"dY8_{j}", nb, ho, wo, l.cout, halo=halo, cls=Buf8)
+        self.dYsf[j] = self._buf(f"dYsf_{j}", nb, ho, wo, 16, halo=halo, cls=Buf8)
       if j > 0 or True:
         c_in = 8 if l.cin < 8 else l.cin
         self.gin[j] = self._buf(f"gin{j}", nb, hi, wi, c_in, halo=halo) if not is_small_cin(l) else None
@@ -469,7 +486,9 @@ class NetExec:
                               self.stats[j][n0:].data_ptr(), self.bstats[j][n0:].data_ptr(),
                               st.wptr(l, "gamma"), 1.0 / (ho * wo), IN_EPS, dY.view(n0),
                               st.gptr(l, "gamma") if wgrad else 0, st.gptr(l, "beta") if wgrad else 0,
-                              nimg, ho, wo, l.cout)
+                              nimg, ho, wo, l.cout,
+                              self.dY8[j].view(n0) if j in self.dY8 else NULL_VIEW,
+                              self.dYsf[j].view(n0) if j in self.dY8 else NULL_VIEW)
         if l.res == "b":
           pending_skip = dyt.view(n0)   # == gradient wrt the block output (IN-b has no activation)
       elif last and gout_is_dy:
@@ -593,6 +612,16 @@ class NetExec:
         taps = [(0, 0, (p - r) * P - p, 0, r * 64) for r in range(l.k)]
         no.add_conv_flat(plan, name, amap, taps, 64, self.w_dgrad[j], gin.ptr(n0, padded=True), l.cin,
                          rows, l.cin, b_mn=False)
+      elif j in self.dY8:
+        # MXFP8 dgrad: block-scaled dY x W^T (K = output channels), same flat zero-ringed domain
+        d8, dsf = self.dY8[j], self.dYsf[j]
+        taps = [(0, 0, (p - r) * P + (p - s), 0, (r * l.k + s) * l.cout)
+                for r in range(l.k) for s in range(l.k)]
+        no.add_conv_flat_mx(plan, name + ".mxfp8", d8.tmap_flat(n0, nimg), dsf.tmap_flat(n0, nimg, cbox=16, swizzle=0),
+                            taps, l.cout, self.st.kernel_fp8_t(l), self.st.w_sft[self.st.fp8_slot(l)],
+                            gin.ptr(n0, padded=True), l.cin, rows, l.cin,
+                            halo_maps=lambda rb: (d8.tmap_flat(n0, nimg, rows_box=rb),
+                                                  dsf.tmap_flat(n0, nimg, rows_box=rb, cbox=16, swizzle=0)))
       else:
         taps = [(0, 0, (p - r) * P + (p - s), 0, (r * l.k + s) * l.cin)
                 for r in range(l.k) for s in range(l.k)]

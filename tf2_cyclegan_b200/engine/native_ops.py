@@ -157,6 +157,16 @@ def add_conv_flat_mx(plan, name: str, a_map: bytes, sfa_map: bytes, taps: Sequen
                                n_channels, 0, 0, 0, 1, ts_map, sfts_map, ts)
 
 
+def add_mx_weight_quant(plan, name: str, w2_ptr: int, w8_ptr: int, sfb_ptr: int, cout: int, taps: int, cin: int,
+                        transposed: bool = False):
+  """bf16 conv weights [cout][taps * cin] -> MXFP8 operand + scales: the forward operand (same indexing,
+  blocks of 32 input channels) or, ``transposed``, the dgrad operand W^T [cin][taps * cout] (blocks of 32
+  output channels)."""
+  if transposed:
+    return plan.add_mx_weight_quant(name, w2_ptr, w8_ptr, sfb_ptr, cin, taps, cout, 1, cin, taps * cin)
+  return plan.add_mx_weight_quant(name, w2_ptr, w8_ptr, sfb_ptr, cout, taps, cin, taps * cin, cin, 1)
+
+
 def _check_mx(name: str, k_channels: int, n_channels: int, ntaps: int, sfb: torch.Tensor):
   if k_channels % 128 or not 128 <= k_channels <= 512 or n_channels % 128:
     raise ValueError(f"{name}: MXFP8 conv needs cin in 128..512 and cout as multiples of 128")
