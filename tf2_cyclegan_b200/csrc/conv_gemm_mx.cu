@@ -1,7 +1,10 @@
 // MXFP8 implicit-GEMM convolution for sm_100a: tcgen05.mma.kind::mxf8f6f4.block_scale with E4M3
 // activations and weights and one E8M0 scale per 32 K elements of either operand (the OCP MX
-// format; BASELINE config 3). Same tap-walking TMA scheme as conv_gemm.cu, M = 128 pixels x
-// N = 128 channels per tile, K block = 128 channels (128 bytes), four K = 32 MMAs per block.
+// format; BASELINE config 3). K block = 128 channels (128 bytes), four K = 32 MMAs per block.
+// Two kernels: `conv_gemm_mx_kernel` (one CTA, M = 128 x N = 128 tiles, one activation box per filter
+// tap: the tap-walking TMA scheme of conv_gemm.cu) and, further down, `conv_gemm_mx_ts_kernel` (CTA
+// pair, tap-shared halo tiles: the fast path, used whenever the halo tile fits). The first block of
+// comments describes what they share and the per-tap kernel.
 //
 // Scale factors live in TMEM next to the accumulators, in the layout the instruction reads
 // (taken from the CUTLASS headers vendored in this image, cute/atom/mma_traits_sm100.hpp
@@ -14,8 +17,8 @@
 // the interleaved order from a pixel-major tensor). Weight scales are pre-arranged per
 // (tile, tap, K block) and fetched with one 512-byte bulk copy.
 //
-// Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
-// warps 4-7 epilogue, warps 8-11 scale factors. TMEM: columns [0, 256) two accumulators,
+// Per-tap kernel, warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM
+// allocator, warps 4-7 epilogue, warps 8-11 scale factors. TMEM: columns [0, 256) two accumulators,
 // [256, 256 + 8 * stages) scale factors (4 columns SFA + 4 columns SFB per stage).
 #include <cuda_fp8.h>
 #include <stdlib.h>
@@ -272,9 +275,11 @@ conv_gemm_mx_kernel(const __grid_constant__ ConvGemmMxParams q, int num_images, 
 // of the same shifted rows. Operand traffic per 128 x 128 output tile drops from 621 KB to ~200 KB,
 // which is what the per-tap kernel above is bound by.
 //
-// Barriers: a_full / b_full / sf_bar / tmem_* live in the leader (both CTAs' operand loads complete
-// there, as in conv_gemm_ts.cu); the scale data of each CTA lands on ITS OWN sfa_full / sfb_full
-// barriers because its own scale warpgroup consumes it.
+// Warp roles (512 threads per CTA): 0 activation / weight producer, 1 MMA issuer (leader CTA), 2 TMEM
+// allocator, 3 scale-data producer, 4-7 and 12-15 the two epilogue warpgroups (64 accumulator columns
+// each), 8-11 scale warpgroup. Barriers: a_full / b_full / sf_bar / tmem_* live in the leader (both CTAs'
+// operand loads complete there, as in conv_gemm_ts.cu); the scale data of each CTA lands on ITS OWN
+// sfd_full barrier because its own scale warpgroup consumes it.
 // Optional stall attribution (tools/kernel_bench.py --mx_profile): cycles every role of CTA 0 spends in
 // each of its barrier waits, written to a 16-slot device buffer. Off (nullptr) in normal runs.
 __device__ unsigned long long* g_mx_prof = nullptr;

@@ -285,11 +285,13 @@ wgrad_gemm2_kernel(const __grid_constant__ WgradParams p, int dbg) {
       if (rank == 0) {
         constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N, 1, 1);
         const uint32_t smem_base = smem_u32(smem);
+        bool ready = false;   // non-blocking probe of the next stage, issued before the current MMAs
         for (int kb = 0; kb < num_kb; ++kb) {
           const int s = kb % Cfg::kStages;
           const uint32_t ph = (kb / Cfg::kStages) & 1;
-          mbar_wait(&full_bar[s], ph);
+          if (!ready) mbar_wait(&full_bar[s], ph);
           tc_fence_after();
+          ready = mbar_test_wait(&full_bar[(kb + 1) % Cfg::kStages], ((kb + 1) / Cfg::kStages) & 1);
           const uint32_t sa = smem_base + s * Cfg::kStageBytes;
           const uint32_t sb = sa + Cfg::kABytes;
           const uint64_t da = make_desc_mnmajor(sa, 64);
