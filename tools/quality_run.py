@@ -47,6 +47,7 @@ ap.add_argument("--images", type=int, default=64)
 ap.add_argument("--batch", type=int, default=4)
 ap.add_argument("--nres", type=int, default=9)
 ap.add_argument("--out", default="gpurun_out/quality.json")
+ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp8", "mxfp8"], help="compute dtype of the native run")
 ap.add_argument("--summarize", default="", help="re-print the table of a saved json (no GPU needed)")
 a = ap.parse_args()
 if a.summarize:
@@ -68,7 +69,7 @@ with tempfile.TemporaryDirectory() as tmp:
     out = os.path.join(tmp, backend)
     argv = ["--output_dir", out, "--epochs", str(a.epochs), "--image_size", str(a.size),
             "--num_residual_blocks", str(a.nres), "--synthetic_size", str(a.images), "--batch_size", str(a.batch),
-            "--backend", backend, "--verbose", "0", "--dtype", "bf16" if backend == "native" else "fp32"]
+            "--backend", backend, "--verbose", "0", "--dtype", a.dtype if backend == "native" else "fp32"]
     main(parse_args(argv))
 
     def read(logdir, tags):
