@@ -116,7 +116,7 @@ conv_gemm_mx_kernel(const __grid_constant__ ConvGemmMxParams q, int num_images, 
   } else if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], 1 + 4);     // MMA commit + the four scale warps (they read the stage's scale bytes)
       mbar_init(&sf_bar[s], 4);            // one arrival per scale warp
     }
     for (int a = 0; a < 2; ++a) {
@@ -227,6 +227,8 @@ conv_gemm_mx_kernel(const __grid_constant__ ConvGemmMxParams q, int num_images, 
           for (int j = 0; j < 4; ++j)
             a[j] = *reinterpret_cast<const uint32_t*>(sfa + (lane + 32 * j) * kMxSfRecord + (cb & 3) * 4);
           const uint4 b = *reinterpret_cast<const uint4*>(sfb + lane * 16);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[s]);   // this warp's shared-memory reads of the stage are done
           if (dbg != 5) {   // timing experiment 5: no TMEM stores
             tmem_st_32x4(lane_base + 8 * s, a[0], a[1], a[2], a[3]);
             tmem_st_32x4(lane_base + 8 * s + 4, b.x, b.y, b.z, b.w);
@@ -402,7 +404,7 @@ conv_gemm_mx_ts_kernel(const __grid_constant__ ConvGemmMxParams q, int num_image
     }
     for (int s = 0; s < Cfg::kSfStages; ++s) {
       mbar_init(&sfd_full[s], 1);
-      mbar_init(&sf_empty[s], 1);
+      mbar_init(&sf_empty[s], 1 + 4);      // MMA commit + this CTA's four scale warps (readers of the slot)
       mbar_init(&sf_bar[s], 8);            // 4 scale warps x 2 CTAs
     }
     for (int s = 0; s < Cfg::kBStages; ++s) {
@@ -640,6 +642,8 @@ conv_gemm_mx_ts_kernel(const __grid_constant__ ConvGemmMxParams q, int num_image
             b[t] = *reinterpret_cast<const uint4*>(sfb + t_col[t] * (Cfg::kSfbBytes / 8));
           }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sf_empty[ss]);   // this warp's shared-memory reads of the slot are done
         if (dbg != 5) {   // timing experiment 5: no TMEM stores
 #pragma unroll
           for (int t = 0; t < Cfg::kMaxTaps; ++t) {
