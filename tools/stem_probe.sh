@@ -6,5 +6,4 @@ for d in 0 1 2 3 4; do
   echo "== kernel_debug=$d" >> gpurun_out/stem_probe.log
   B2_CONFIG=kernel_debug=$d timeout 120 python tools/kernel_bench.py --layer stem --images 8 >> gpurun_out/stem_probe.log 2>&1
 done
-for g in 148 296; do :; done
 tail -40 gpurun_out/stem_probe.log
