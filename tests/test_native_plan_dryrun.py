@@ -113,6 +113,23 @@ def test_mxfp8_plan_builds(monkeypatch):
   assert any(n.startswith("G.res0a.wgrad") for n in sp.names)
 
 
+def test_mxfp8_op_builders_reject_bad_shapes(monkeypatch):
+  fake_native.install(monkeypatch)
+  import pytest
+  from tf2_cyclegan_b200.engine import native_ops as no
+  from tf2_cyclegan_b200.ops import native as nv
+  plan = nv.load().Plan()
+  w8 = torch.zeros(256, 9 * 256, dtype=torch.uint8)
+  sfb = torch.zeros(256 * 9 * 256 // 32, dtype=torch.uint8)
+  view = (1 << 20, 0, 0, 256)
+  with pytest.raises(ValueError):      # 64 input channels: not a multiple of the 128-channel K block
+    no.add_conv_mx(plan, "x", b"", b"", no.taps_conv(3, 64), 64, w8, sfb, view, 64, 64, 1, 256)
+  with pytest.raises(ValueError):      # scale buffer of the wrong size
+    no.add_conv_mx(plan, "x", b"", b"", no.taps_conv(3, 256), 256, w8, sfb[:-32], view, 64, 64, 1, 256)
+  with pytest.raises(ValueError):      # 192 output channels: not a multiple of the 128-wide tile
+    no.add_conv_flat_mx(plan, "x", b"", b"", [(0, 0, 0, 0, 0)], 256, w8, sfb, 1 << 20, 256, 4096, 192)
+
+
 def test_allreduce_buckets_and_ownership(monkeypatch):
   """Bucket plan of the fused all-reduce (CPU logic only): buckets tile the kernel part of the flat
   buffer in backward order, the vector tail is one-shot (replicated), and the per-bucket rank shards

@@ -34,3 +34,21 @@ def test_convert_checkpoint_tool(tmp_path):
   a, ea = ckpt.load(src)
   b, eb = ckpt.load(dst)
   assert ea == eb == {"epoch": 2} and all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_shell_tools_parse():
+  """The GPU-side evidence / probe scripts are only ever run on a box: at least keep them syntactically valid."""
+  import glob
+  scripts = sorted(glob.glob(os.path.join(ROOT, "tools", "*.sh")))
+  assert len(scripts) >= 6
+  for s in scripts:
+    r = subprocess.run(["bash", "-n", s], capture_output=True, text=True)
+    assert r.returncode == 0, (s, r.stderr)
+
+
+def test_quality_run_summarises_a_saved_run():
+  saved = os.path.join(ROOT, "profiles", "r2", "quality_run_mxfp8.json")
+  r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "quality_run.py"), "--summarize", saved],
+                     capture_output=True, text=True, timeout=300, cwd=ROOT)
+  assert r.returncode == 0, r.stderr[-800:]
+  assert "error/MAE(X, F(G(X)))" in r.stdout and "first half of the run" in r.stdout
