@@ -50,8 +50,9 @@ class CycleGAN:
     if backend == "auto":
       native_ok = strategy.device.type == "cuda" and size >= 32 and size % 8 == 0
       backend = "native" if native_ok else "oracle"
+    emulate_mx = backend == "oracle" and dtype == "mxfp8"   # oracle: fp32 math on MXFP8-quantised operands
     if backend == "oracle" and dtype in ("fp8", "mxfp8"):
-      dtype = "bf16"
+      dtype = "fp32" if emulate_mx else "bf16"
     if backend == "native":
       from .native_backend import NativeBackend
       self.backend = NativeBackend(self.specs, self.global_batch_size, strategy, seed=seed,
@@ -62,7 +63,7 @@ class CycleGAN:
       from .oracle_backend import OracleBackend
       cd = {"fp32": torch.float32, "bf16": torch.bfloat16}[dtype]
       self.backend = OracleBackend(self.specs, self.global_batch_size, strategy, seed=seed,
-                                   compute_dtype=cd)
+                                   compute_dtype=cd, emulate_mxfp8=emulate_mx)
     else:
       raise ValueError(f"unknown backend {backend!r}")
     self.extra_state: Dict[str, object] = {}

@@ -33,7 +33,8 @@ class OracleBackend:
 
   def __init__(self, specs: Dict[str, NetSpec], global_batch_size: int,
                strategy: Strategy, seed: int = 1234,
-               compute_dtype: torch.dtype = torch.float32, emulate_bf16_storage: bool = False):
+               compute_dtype: torch.dtype = torch.float32, emulate_bf16_storage: bool = False,
+               emulate_mxfp8: bool = False):
     self.specs = specs
     self.strategy = strategy
     self.device = strategy.device
@@ -41,6 +42,8 @@ class OracleBackend:
     self.compute_dtype = compute_dtype
     # fp32 math on activations rounded to bf16 wherever the native engine stores them (tests)
     self.rnd = oracle_net.bf16_storage if emulate_bf16_storage else None
+    # the numerics of the native ``--dtype mxfp8``: block-scaled E4M3 operands in the generators' residual convs
+    self.mx = bool(emulate_mxfp8)
     gen = torch.Generator().manual_seed(seed)
     self.params: Dict[str, Dict[str, torch.Tensor]] = OrderedDict()
     self.opt: Dict[str, KerasAdam] = OrderedDict()
@@ -55,10 +58,10 @@ class OracleBackend:
   def net(self, n: str, x: torch.Tensor) -> torch.Tensor:
     if self.compute_dtype != torch.float32 and self.device.type == "cuda":
       with torch.autocast("cuda", dtype=self.compute_dtype):
-        return oracle_net.forward(self.specs[n], self.params[n], x).float()
+        return oracle_net.forward(self.specs[n], self.params[n], x, mx=self.mx).float()
     if self.rnd is not None:
       x = self.rnd(x)                                  # network inputs are stored as bf16 pixels
-    return oracle_net.forward(self.specs[n], self.params[n], x, self.rnd)
+    return oracle_net.forward(self.specs[n], self.params[n], x, self.rnd, self.mx)
 
   @torch.no_grad()
   def cycle_step(self, x: torch.Tensor, y: torch.Tensor):
